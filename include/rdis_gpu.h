@@ -1,0 +1,158 @@
+/*
+ * rdis_gpu.h — C-ABI of the B200-native subspace-solve / factor-sweep path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status codes, no C++ or
+ * torch types.  Each entry point names the reference interface it replaces
+ * (paths relative to the afriesen/rdis tree).  The C++ adapter that keeps the
+ * reference's plugin surface (class CudaSubspaceOptimizer : SubspaceOptimizer) lives in
+ * rdis_b200/host/ and calls only the functions declared here; INTEGRATION.md shows the
+ * reference-side binding.
+ *
+ * All arithmetic is IEEE fp64 (reference: typedef double Numeric, src/common.h:25).
+ * There is no CPU fallback: every call fails with RDISGPU_ERR_CUDA if no sm_100 device
+ * is usable.
+ *
+ * Threading: a context is single-threaded, like the reference (src/IntrusivePtrPool.h:53).
+ */
+#ifndef RDIS_GPU_H_
+#define RDIS_GPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RDISGPU_API __attribute__((visibility("default")))
+#else
+#define RDISGPU_API
+#endif
+
+typedef struct rdisgpu_ctx rdisgpu_ctx;     /* one OptimizableFunction resident on one GPU */
+typedef struct rdisgpu_batch rdisgpu_batch; /* a packed set of sibling subspace problems    */
+
+enum {
+  RDISGPU_OK = 0,
+  RDISGPU_ERR_CUDA = 1,      /* CUDA runtime error; text in rdisgpu_last_error            */
+  RDISGPU_ERR_ARG = 2,       /* bad argument (null pointer, id out of range, wrong state)  */
+  RDISGPU_ERR_STATE = 3,     /* call order violated (e.g. solve before finalize)           */
+  RDISGPU_ERR_OVERLAP = 4    /* problems of one batch share a variable or a factor         */
+};
+
+/* Per-problem termination status (rdisgpu_result.status). */
+enum {
+  RDISGPU_DONE_FTOL = 0,       /* Frprmn ftol return,   external/include/minimize_nrc.h:648-652 */
+  RDISGPU_DONE_GTOL = 1,       /* zero-gradient return, minimize_nrc.h:663-666                  */
+  RDISGPU_DONE_GG_ZERO = 2,    /* gg == 0 return,       minimize_nrc.h:676-679                  */
+  RDISGPU_DONE_MAXITERS = 3,   /* "Too many iterations in frprmn", minimize_nrc.h:690 (normal)  */
+  RDISGPU_DONE_DBRENT_ITMAX = 4, /* "Too many iterations in routine dbrent", minimize_nrc.h:403 */
+  RDISGPU_DONE_EMPTY = 5,      /* no factors: returns 0, delta 0, x untouched (CGDSubspaceOptimizer.cpp:26-29) */
+  RDISGPU_DONE_NONFINITE = 6,  /* a non-finite line-search abscissa was produced; start point restored        */
+  RDISGPU_DONE_BRACKET_CAP = 7 /* bracket expansion exceeded the device safety cap (reference would loop)     */
+};
+
+/* One SubspaceOptimizer::optimize call (src/SubspaceOptimizer.h:37-39):
+ * minimise sum_{j in fid} f_j over the variables vid, everything else held fixed. */
+typedef struct rdisgpu_problem {
+  int64_t nv;          /* |vars|                                                              */
+  const int32_t* vid;  /* variable ids, order = the reference's `vars` vector                 */
+  int64_t nf;          /* |factors|                                                           */
+  const int64_t* fid;  /* factor ids, order = the reference's `factors` vector (sorted by id
+                          when built by RDISOptimizer.cpp:1049-1059)                          */
+  const double* x0;    /* nv start values (`xval` on entry); NULL = current device values     */
+} rdisgpu_problem;
+
+typedef struct rdisgpu_result {
+  double* x;        /* out, nv values: domain-clamped final values (`xval` on exit); may be NULL */
+  double f_init;    /* f at the (clamped) start point                                            */
+  double f_end;     /* return value of optimize(): f at the returned point                       */
+  int32_t iters;    /* Frprmn::iter at exit                                                      */
+  int32_t status;   /* RDISGPU_DONE_*                                                            */
+  int64_t n_feval;  /* objective evaluations the device performed (each = nf factor evals)       */
+  int64_t n_geval;  /* of those, evaluations that also produced derivatives                      */
+} rdisgpu_result;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+RDISGPU_API int rdisgpu_create(rdisgpu_ctx** out, int device);
+RDISGPU_API void rdisgpu_destroy(rdisgpu_ctx* ctx);
+RDISGPU_API const char* rdisgpu_last_error(const rdisgpu_ctx* ctx); /* ctx may be NULL: last create error */
+/* All work of this context is enqueued on `cuda_stream` (a cudaStream_t; NULL = default). */
+RDISGPU_API int rdisgpu_set_stream(rdisgpu_ctx* ctx, void* cuda_stream);
+RDISGPU_API int rdisgpu_synchronize(rdisgpu_ctx* ctx);
+
+/* ---- function definition (replaces the OptimizableFunction / Factor object graph) ------ */
+/* Variables 0..V-1 with their single-interval domains (VariableDomain, src/VariableDomain.cpp:130-163). */
+RDISGPU_API int rdisgpu_set_vars(rdisgpu_ctx* ctx, int64_t V, const double* lb, const double* ub);
+/* NonlinearProductFactor list in CSR form by factor id (src/NonlinearProductFactor.h:27-55,100-113):
+ * factor j = coeff[j] * prod_{e in [rowptr[j],rowptr[j+1])} t_e,
+ * t_e = [sin]( (x[vid[e]] - konst[e]) ^ expo[e] ).                                              */
+RDISGPU_API int rdisgpu_add_nlpf(rdisgpu_ctx* ctx, int64_t F, const int64_t* rowptr, const int32_t* vid,
+                                 const double* expo, const double* konst, const uint8_t* use_sine,
+                                 const double* coeff);
+/* BundleAdjustmentFactor list (src/bundleadjust/BundleAdjustmentFactor.h:129-136): observation j of
+ * point pt[j] by camera cam[j] at pixel obs_xy[2j..2j+1].  Variable ids are implied by
+ * BundleAdjustmentFunction.h:88-96: camera c parameter p -> 9c+p, point i coordinate d -> 9*ncams+3i+d. */
+RDISGPU_API int rdisgpu_add_ba(rdisgpu_ctx* ctx, int64_t F, const int32_t* cam, const int32_t* pt,
+                               const double* obs_xy, int32_t ncams, int32_t npts);
+/* Builds the variable-major incidence and uploads everything (OptimizableFunction::init). */
+RDISGPU_API int rdisgpu_finalize(rdisgpu_ctx* ctx);
+
+/* ---- state ---------------------------------------------------------------------------- */
+/* Variable::assign for n variables (vid NULL = 0..n-1), src/Variable.cpp:66-88. */
+RDISGPU_API int rdisgpu_set_x(rdisgpu_ctx* ctx, int64_t n, const int32_t* vid, const double* x);
+RDISGPU_API int rdisgpu_get_x(rdisgpu_ctx* ctx, int64_t n, const int32_t* vid, double* x);
+/* Factors the tree search simplified to a constant (Factor::isAssigned, src/Factor.cpp:110-119):
+ * their value is val[i] while on[i] != 0; their gradient is still the full analytic one
+ * (src/NonlinearProductFactor.cpp:57-117, BundleAdjustmentFactor.cpp:338-348).                   */
+RDISGPU_API int rdisgpu_set_factor_const(rdisgpu_ctx* ctx, int64_t n, const int64_t* fid, const double* val,
+                                         const uint8_t* on);
+
+/* ---- sweeps --------------------------------------------------------------------------- */
+/* OptimizableFunction::evalFactors (src/OptimizableFunction.cpp:95-135) over a factor-id list
+ * (fid NULL = all F factors).  *sum = sum_j f_j; per_factor (nullable) receives nf values. */
+RDISGPU_API int rdisgpu_eval(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, double* sum, double* per_factor);
+/* OptimizableFunction::computeGradient(facs, pg) + the scatter of SubfunctionFD::df
+ * (src/OptimizableFunction.cpp:234-262, CGDSubspaceOptimizer.cpp:135-157): g[i] = d/dx_{vid[i]} sum_j f_j. */
+RDISGPU_API int rdisgpu_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, int64_t nv, const int32_t* vid,
+                             double* g);
+/* Factor::computeGradient for one factor list: rows[k*arity_max + s] = d f_{fid[k]} / d slot s. */
+RDISGPU_API int rdisgpu_factor_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, int32_t arity_max,
+                                    double* rows);
+
+/* ---- subspace solves ------------------------------------------------------------------- */
+/* CGDSubspaceOptimizer::optimize (src/optimizers/CGDSubspaceOptimizer.cpp:19-98) for nprobs
+ * problems in one call.  nprobs > 1 is the sibling-component batch (RDISOptimizer.cpp:184-211,
+ * 291-314): the problems must not share variables or factors, and no factor of one problem may
+ * touch a variable of another.  Host buffers in, host buffers out; final values are also
+ * committed to the device state (Variable::assign post-condition, CGD.cpp:61,84-86).            */
+RDISGPU_API int rdisgpu_solve_cgd(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t nprobs, int maxiters,
+                                  double ftol, rdisgpu_result* out);
+
+/* The same in three steps, for callers that revisit one component structure many times
+ * (alternating minimisation, RDISOptimizer.cpp:1148-1181): index lists stay resident in HBM. */
+RDISGPU_API int rdisgpu_batch_create(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t nprobs,
+                                     rdisgpu_batch** out);
+/* x0 (nullable): concatenated start values in problem order; NULL = current device values.
+ * Asynchronous on the context's stream. */
+RDISGPU_API int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiters, double ftol);
+/* Waits, then copies results out (out[i].x may be NULL).  sum_f_end (nullable) = sum of f_end. */
+RDISGPU_API int rdisgpu_batch_fetch(rdisgpu_batch* b, rdisgpu_result* out, double* sum_f_end);
+RDISGPU_API void rdisgpu_batch_destroy(rdisgpu_batch* b);
+/* Kernel launches the last rdisgpu_batch_solve_cgd enqueued (bench.py's gpu_launches). */
+RDISGPU_API int rdisgpu_batch_last_launches(const rdisgpu_batch* b);
+
+/* ---- introspection (tests / bench) ------------------------------------------------------ */
+RDISGPU_API int64_t rdisgpu_num_vars(const rdisgpu_ctx* ctx);
+RDISGPU_API int64_t rdisgpu_num_factors(const rdisgpu_ctx* ctx);
+/* Raw device pointer + element count of the committed state, for zero-copy interop
+ * (torch.from_blob / __cuda_array_interface__): V pairs {value, direction-slot}. */
+RDISGPU_API int rdisgpu_device_state(rdisgpu_ctx* ctx, void** dptr, int64_t* n_pairs);
+/* Total kernel launches issued by this context so far. */
+RDISGPU_API int64_t rdisgpu_launch_count(const rdisgpu_ctx* ctx);
+RDISGPU_API const char* rdisgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDIS_GPU_H_ */

@@ -1,0 +1,329 @@
+"""ctypes binding of the C-ABI declared in include/rdis_gpu.h (librdis_b200.so).
+
+This is plumbing for tests and bench.py: every call goes straight to the hand-written
+CUDA library.  There is no CPU fallback — if the shared library is missing the import
+fails, and if no sm_100 GPU is usable `Context()` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librdis_b200.so")
+
+DONE_NAMES = ("ftol", "gtol", "gg_zero", "maxiters", "dbrent_itmax", "empty", "nonfinite", "bracket_cap")
+
+# every symbol include/rdis_gpu.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "rdisgpu_create", "rdisgpu_destroy", "rdisgpu_last_error", "rdisgpu_set_stream", "rdisgpu_synchronize",
+    "rdisgpu_set_vars", "rdisgpu_add_nlpf", "rdisgpu_add_ba", "rdisgpu_finalize",
+    "rdisgpu_set_x", "rdisgpu_get_x", "rdisgpu_set_factor_const",
+    "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_factor_grad",
+    "rdisgpu_solve_cgd", "rdisgpu_batch_create", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
+    "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches",
+    "rdisgpu_num_vars", "rdisgpu_num_factors", "rdisgpu_device_state", "rdisgpu_launch_count", "rdisgpu_version",
+)
+
+
+class Problem(C.Structure):
+    _fields_ = [("nv", C.c_int64), ("vid", C.c_void_p), ("nf", C.c_int64), ("fid", C.c_void_p), ("x0", C.c_void_p)]
+
+
+class Result(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("f_init", C.c_double), ("f_end", C.c_double), ("iters", C.c_int32),
+                ("status", C.c_int32), ("n_feval", C.c_int64), ("n_geval", C.c_int64)]
+
+
+class RdisGpuError(RuntimeError):
+    pass
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  rdis_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+    sig = {
+        "rdisgpu_create": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "rdisgpu_destroy": (None, [vp]),
+        "rdisgpu_last_error": (C.c_char_p, [vp]),
+        "rdisgpu_set_stream": (C.c_int, [vp, vp]),
+        "rdisgpu_synchronize": (C.c_int, [vp]),
+        "rdisgpu_set_vars": (C.c_int, [vp, i64, vp, vp]),
+        "rdisgpu_add_nlpf": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
+        "rdisgpu_add_ba": (C.c_int, [vp, i64, vp, vp, vp, i32, i32]),
+        "rdisgpu_finalize": (C.c_int, [vp]),
+        "rdisgpu_set_x": (C.c_int, [vp, i64, vp, vp]),
+        "rdisgpu_get_x": (C.c_int, [vp, i64, vp, vp]),
+        "rdisgpu_set_factor_const": (C.c_int, [vp, i64, vp, vp, vp]),
+        "rdisgpu_eval": (C.c_int, [vp, i64, vp, C.POINTER(dbl), vp]),
+        "rdisgpu_grad": (C.c_int, [vp, i64, vp, i64, vp, vp]),
+        "rdisgpu_factor_grad": (C.c_int, [vp, i64, vp, i32, vp]),
+        "rdisgpu_solve_cgd": (C.c_int, [vp, C.POINTER(Problem), i64, C.c_int, dbl, C.POINTER(Result)]),
+        "rdisgpu_batch_create": (C.c_int, [vp, C.POINTER(Problem), i64, C.POINTER(vp)]),
+        "rdisgpu_batch_solve_cgd": (C.c_int, [vp, vp, C.c_int, dbl]),
+        "rdisgpu_batch_fetch": (C.c_int, [vp, C.POINTER(Result), C.POINTER(dbl)]),
+        "rdisgpu_batch_destroy": (None, [vp]),
+        "rdisgpu_batch_last_launches": (C.c_int, [vp]),
+        "rdisgpu_num_vars": (i64, [vp]),
+        "rdisgpu_num_factors": (i64, [vp]),
+        "rdisgpu_device_state": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "rdisgpu_launch_count": (i64, [vp]),
+        "rdisgpu_version": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = load_library()
+    return _lib
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class ProblemSet:
+    """Host-side description of a batch of subspace problems (CSR style)."""
+
+    def __init__(self, var_off, vids, fac_off, fids):
+        self.var_off = _arr(var_off, np.int64)
+        self.vids = _arr(vids, np.int32)
+        self.fac_off = _arr(fac_off, np.int64)
+        self.fids = _arr(fids, np.int64)
+        self.n = len(self.var_off) - 1
+        assert len(self.fac_off) == self.n + 1
+
+    @classmethod
+    def from_lists(cls, problems):
+        """problems: iterable of (vids, fids)."""
+        vo, fo, vs, fs = [0], [0], [], []
+        for v, f in problems:
+            vs.append(np.asarray(v, np.int32)); fs.append(np.asarray(f, np.int64))
+            vo.append(vo[-1] + len(v)); fo.append(fo[-1] + len(f))
+        return cls(vo, np.concatenate(vs) if vs else np.zeros(0, np.int32), fo,
+                   np.concatenate(fs) if fs else np.zeros(0, np.int64))
+
+    def subset(self, idx):
+        return ProblemSet.from_lists([(self.vids[self.var_off[i]:self.var_off[i + 1]],
+                                       self.fids[self.fac_off[i]:self.fac_off[i + 1]]) for i in idx])
+
+    def c_array(self, x0=None):
+        arr = (Problem * self.n)()
+        vbase, fbase = self.vids.ctypes.data, self.fids.ctypes.data
+        xbase = None if x0 is None else x0.ctypes.data
+        for i in range(self.n):
+            arr[i].nv = int(self.var_off[i + 1] - self.var_off[i])
+            arr[i].nf = int(self.fac_off[i + 1] - self.fac_off[i])
+            arr[i].vid = vbase + 4 * int(self.var_off[i])
+            arr[i].fid = fbase + 8 * int(self.fac_off[i])
+            arr[i].x0 = None if xbase is None else xbase + 8 * int(self.var_off[i])
+        return arr
+
+
+class Context:
+    """One OptimizableFunction resident on one GPU (rdisgpu_ctx)."""
+
+    def __init__(self, device=0):
+        self._lib = lib()
+        h = C.c_void_p()
+        rc = self._lib.rdisgpu_create(C.byref(h), device)
+        if rc != 0:
+            raise RdisGpuError(f"rdisgpu_create failed ({rc}): {self._lib.rdisgpu_last_error(None).decode()}")
+        self._h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rdisgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RdisGpuError(f"rdisgpu error {rc}: {self._lib.rdisgpu_last_error(self._h).decode()}")
+
+    # ---- definition ------------------------------------------------------------------
+    @classmethod
+    def from_spec(cls, spec, device=0, stream=None):
+        ctx = cls(device)
+        if stream is not None:
+            ctx.set_stream(stream)
+        lb = _arr(spec["lb"], np.float64); ub = _arr(spec["ub"], np.float64)
+        ctx._ck(ctx._lib.rdisgpu_set_vars(ctx._h, len(lb), _p(lb), _p(ub)))
+        if spec["kind"] == "ba":
+            cam = _arr(spec["cam"], np.int32); pt = _arr(spec["pt"], np.int32)
+            obs = _arr(spec["obs"], np.float64).reshape(-1)
+            ctx._ck(ctx._lib.rdisgpu_add_ba(ctx._h, len(cam), _p(cam), _p(pt), _p(obs), spec["ncams"], spec["npts"]))
+        else:
+            rp = _arr(spec["rowptr"], np.int64); vid = _arr(spec["vid"], np.int32)
+            ex = _arr(spec["expo"], np.float64); ko = _arr(spec["konst"], np.float64)
+            si = _arr(spec["sine"], np.uint8); co = _arr(spec["coeff"], np.float64)
+            ctx._ck(ctx._lib.rdisgpu_add_nlpf(ctx._h, len(co), _p(rp), _p(vid), _p(ex), _p(ko), _p(si), _p(co)))
+        ctx._ck(ctx._lib.rdisgpu_finalize(ctx._h))
+        return ctx
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._lib.rdisgpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._ck(self._lib.rdisgpu_synchronize(self._h))
+
+    @property
+    def V(self):
+        return self._lib.rdisgpu_num_vars(self._h)
+
+    @property
+    def F(self):
+        return self._lib.rdisgpu_num_factors(self._h)
+
+    @property
+    def launch_count(self):
+        return self._lib.rdisgpu_launch_count(self._h)
+
+    # ---- state -----------------------------------------------------------------------
+    def set_x(self, x, vid=None):
+        x = _arr(x, np.float64)
+        v = None if vid is None else _arr(vid, np.int32)
+        self._ck(self._lib.rdisgpu_set_x(self._h, len(x), _p(v), _p(x)))
+
+    def get_x(self, vid=None):
+        v = None if vid is None else _arr(vid, np.int32)
+        n = self.V if v is None else len(v)
+        out = np.empty(n)
+        self._ck(self._lib.rdisgpu_get_x(self._h, n, _p(v), _p(out)))
+        return out
+
+    def set_factor_const(self, fid, val, on):
+        fid = _arr(fid, np.int64); val = _arr(val, np.float64); on = _arr(on, np.uint8)
+        self._ck(self._lib.rdisgpu_set_factor_const(self._h, len(fid), _p(fid), _p(val), _p(on)))
+
+    def device_state(self):
+        p = C.c_void_p(); n = C.c_int64()
+        self._ck(self._lib.rdisgpu_device_state(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    # ---- sweeps ----------------------------------------------------------------------
+    def eval(self, fid=None, per_factor=False):
+        f = None if fid is None else _arr(fid, np.int64)
+        n = self.F if f is None else len(f)
+        s = C.c_double(0)
+        pf = np.empty(n) if per_factor else None
+        self._ck(self._lib.rdisgpu_eval(self._h, n, _p(f), C.byref(s), _p(pf)))
+        return (s.value, pf) if per_factor else s.value
+
+    def grad(self, fid=None, vid=None):
+        f = None if fid is None else _arr(fid, np.int64)
+        v = None if vid is None else _arr(vid, np.int32)
+        nv = self.V if v is None else len(v)
+        g = np.empty(nv)
+        self._ck(self._lib.rdisgpu_grad(self._h, self.F if f is None else len(f), _p(f), nv, _p(v), _p(g)))
+        return g
+
+    def factor_grad(self, fid, arity_max):
+        f = _arr(fid, np.int64)
+        rows = np.zeros((len(f), arity_max))
+        self._ck(self._lib.rdisgpu_factor_grad(self._h, len(f), _p(f), arity_max, _p(rows)))
+        return rows
+
+    # ---- solves ----------------------------------------------------------------------
+    def solve_cgd(self, problems, x0=None, maxiters=25, ftol=3e-8):
+        """rdisgpu_solve_cgd: host buffers in, host buffers out.
+        problems: ProblemSet; x0: concatenated start values or None (use device state).
+        Returns dict(x, f_init, f_end, iters, status, n_feval, n_geval)."""
+        ps = problems
+        x0a = None if x0 is None else _arr(x0, np.float64)
+        parr = ps.c_array(x0a)
+        xout = np.empty(len(ps.vids))
+        rarr = (Result * ps.n)()
+        for i in range(ps.n):
+            rarr[i].x = xout.ctypes.data + 8 * int(ps.var_off[i])
+        self._ck(self._lib.rdisgpu_solve_cgd(self._h, parr, ps.n, maxiters, ftol, rarr))
+        return _unpack(rarr, ps.n, xout)
+
+    def batch(self, problems):
+        return Batch(self, problems)
+
+
+def _unpack(rarr, n, xout):
+    buf = np.frombuffer(rarr, dtype=np.dtype([("x", np.uint64), ("f_init", np.float64), ("f_end", np.float64),
+                                              ("iters", np.int32), ("status", np.int32), ("n_feval", np.int64),
+                                              ("n_geval", np.int64)]), count=n)
+    return {"x": xout, "f_init": buf["f_init"].copy(), "f_end": buf["f_end"].copy(), "iters": buf["iters"].copy(),
+            "status": buf["status"].copy(), "n_feval": buf["n_feval"].copy(), "n_geval": buf["n_geval"].copy()}
+
+
+class Batch:
+    """rdisgpu_batch: index lists resident in HBM, solve asynchronously, fetch later."""
+
+    def __init__(self, ctx, problems):
+        self.ctx = ctx
+        self.ps = problems
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        parr = problems.c_array(None)
+        ctx._ck(self._lib.rdisgpu_batch_create(ctx._h, parr, problems.n, C.byref(h)))
+        self._h = h
+        self._rarr = (Result * problems.n)()
+        self._xout = np.empty(len(problems.vids))
+        for i in range(problems.n):
+            self._rarr[i].x = self._xout.ctypes.data + 8 * int(problems.var_off[i])
+
+    def solve(self, x0=None, maxiters=25, ftol=3e-8):
+        """Enqueue the solve.  x0: host array (pinned for a truly async copy) or None."""
+        if x0 is None:
+            ptr = None
+        elif isinstance(x0, np.ndarray):
+            assert x0.dtype == np.float64 and x0.flags.c_contiguous
+            self._x0_keep = x0
+            ptr = C.c_void_p(x0.ctypes.data)
+        else:  # raw host pointer (e.g. torch pinned tensor .data_ptr())
+            ptr = C.c_void_p(int(x0))
+        self.ctx._ck(self._lib.rdisgpu_batch_solve_cgd(self._h, ptr, maxiters, ftol))
+
+    def fetch(self, want_x=True):
+        s = C.c_double(0)
+        if want_x:
+            self.ctx._ck(self._lib.rdisgpu_batch_fetch(self._h, self._rarr, C.byref(s)))
+            out = _unpack(self._rarr, self.ps.n, self._xout.copy())
+        else:
+            self.ctx._ck(self._lib.rdisgpu_batch_fetch(self._h, None, C.byref(s)))
+            out = {}
+        out["sum_f_end"] = s.value
+        return out
+
+    @property
+    def last_launches(self):
+        return self._lib.rdisgpu_batch_last_launches(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rdisgpu_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

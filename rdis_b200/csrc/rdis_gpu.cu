@@ -1,0 +1,861 @@
+// rdis_gpu.cu — the C-ABI of include/rdis_gpu.h: context / HBM residency management, the
+// sweep kernels (evalFactors, computeGradient) and the launch logic of the batched subspace
+// solves (solve_kernels.cuh).  CUDA runtime only; no torch, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/rdis_gpu.h"
+#include "solve_kernels.cuh"
+#include "sweep_kernels.cuh"
+
+using namespace rdisgpu;
+
+namespace {
+
+std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t ensure(size_t count) {  // grow-only
+    if (count <= n && p) return cudaSuccess;
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+template <class T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  PinnedBuf() {}
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  ~PinnedBuf() {
+    if (p) cudaFreeHost(p);
+  }
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMallocHost((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+}  // namespace
+
+struct rdisgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+  bool finalized = false;
+  int kind = KIND_NONE;
+  int64_t V = 0, F = 0, E = 0;
+  int64_t launches = 0;
+
+  // host staging of the definition (dropped at finalize)
+  std::vector<double> h_lb, h_ub;
+  std::vector<int64_t> h_rowptr;
+  std::vector<int32_t> h_evid;
+  std::vector<double> h_expo, h_konst, h_coeff;
+  std::vector<uint8_t> h_sine;
+  std::vector<int32_t> h_cam, h_pt;
+  std::vector<double> h_obs;
+  int32_t ncams = 0, npts = 0;
+
+  // device residency
+  DevBuf<double2> xbd, dom;
+  DevBuf<int32_t> rowptr, evid, vrow, vedge, efac, cam, pt, crow, cfac, prow, pfac, fstamp;
+  DevBuf<double> expo, konst, coeff, gedge, gvec, hvec, xsave, fconst_val;
+  DevBuf<uint8_t> sine, fconst_on;
+  DevBuf<double2> obs;
+  bool has_fconst = false;
+  GraphView gv;
+
+  // scratch for the sweep / state calls
+  DevBuf<int32_t> s_i32a, s_i32b;
+  DevBuf<double> s_f64a, s_f64b, s_partials;
+  DevBuf<unsigned int> s_counter;
+  DevBuf<double> grid_partials;
+  PinnedBuf<char> pin;
+
+  int fail_cuda(cudaError_t e, const char* what) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return RDISGPU_ERR_CUDA;
+  }
+  int fail(int code, const char* what) {
+    err = what;
+    return code;
+  }
+};
+
+#define CK(call)                                            \
+  do {                                                      \
+    cudaError_t e_ = (call);                                \
+    if (e_ != cudaSuccess) return ctx->fail_cuda(e_, #call); \
+  } while (0)
+
+struct rdisgpu_batch {
+  rdisgpu_ctx* ctx = nullptr;
+  int64_t nprobs = 0;
+  int64_t total_nv = 0, total_nf = 0;
+  std::vector<ProblemDesc> h_probs;
+  DevBuf<ProblemDesc> probs;
+  DevBuf<int32_t> vids, fids;
+  DevBuf<double> x0, xout;
+  DevBuf<ResultRec> res;
+  // size classes
+  std::vector<int32_t> h_order;      // problem indices grouped by class
+  DevBuf<int32_t> order;
+  struct Class { int kind; int param; int64_t off; int64_t count; };  // kind 0 = tile(G), 1 = block(threads), 2 = grid
+  std::vector<Class> classes;
+  PinnedBuf<ResultRec> h_res;
+  PinnedBuf<double> h_x;  // staging for x0 upload and xout download
+  int last_launches = 0;
+  bool solved = false;
+};
+
+namespace {
+
+int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+void fill_view(rdisgpu_ctx* c) {
+  GraphView& g = c->gv;
+  std::memset(&g, 0, sizeof g);
+  g.kind = c->kind;
+  g.V = c->V; g.F = c->F; g.E = c->E;
+  g.xbd = c->xbd.p; g.dom = c->dom.p;
+  g.rowptr = c->rowptr.p; g.evid = c->evid.p; g.expo = c->expo.p; g.konst = c->konst.p;
+  g.sine = c->sine.p; g.coeff = c->coeff.p; g.vrow = c->vrow.p; g.vedge = c->vedge.p; g.efac = c->efac.p;
+  g.cam = c->cam.p; g.pt = c->pt.p; g.obs = c->obs.p; g.ncams = c->ncams; g.npts = c->npts;
+  g.crow = c->crow.p; g.cfac = c->cfac.p; g.prow = c->prow.p; g.pfac = c->pfac.p;
+  g.fconst_on = c->has_fconst ? c->fconst_on.p : nullptr;
+  g.fconst_val = c->has_fconst ? c->fconst_val.p : nullptr;
+  g.gedge = c->gedge.p; g.gvec = c->gvec.p; g.hvec = c->hvec.p; g.xsave = c->xsave.p; g.fstamp = c->fstamp.p;
+}
+
+template <class T>
+cudaError_t upload(DevBuf<T>& d, const T* h, size_t n, cudaStream_t s) {
+  cudaError_t e = d.ensure(n);
+  if (e != cudaSuccess) return e;
+  if (n == 0) return cudaSuccess;
+  return cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+// counting-sort incidence: for each key in [0,K) the list of items with that key, ascending item id
+void build_incidence(int64_t K, const std::vector<int32_t>& key_of_item, std::vector<int32_t>& row,
+                     std::vector<int32_t>& items) {
+  row.assign(K + 1, 0);
+  for (int32_t k : key_of_item) ++row[k + 1];
+  for (int64_t i = 0; i < K; ++i) row[i + 1] += row[i];
+  items.resize(key_of_item.size());
+  std::vector<int32_t> cur(row.begin(), row.end() - 1);
+  for (size_t it = 0; it < key_of_item.size(); ++it) items[cur[key_of_item[it]]++] = (int32_t)it;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// lifetime
+// ==========================================================================================
+extern "C" {
+
+int rdisgpu_create(rdisgpu_ctx** out, int device) {
+  if (!out) return RDISGPU_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return RDISGPU_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_error = "device index out of range";
+    return RDISGPU_ERR_ARG;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return RDISGPU_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+    return RDISGPU_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "this library carries sm_100a code only; device is sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor);
+    return RDISGPU_ERR_CUDA;
+  }
+  rdisgpu_ctx* c = new rdisgpu_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return RDISGPU_OK;
+}
+
+void rdisgpu_destroy(rdisgpu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  delete ctx;
+}
+
+const char* rdisgpu_last_error(const rdisgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rdisgpu_set_stream(rdisgpu_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return RDISGPU_OK;
+}
+
+int rdisgpu_synchronize(rdisgpu_ctx* ctx) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RDISGPU_OK;
+}
+
+// ==========================================================================================
+// definition
+// ==========================================================================================
+int rdisgpu_set_vars(rdisgpu_ctx* ctx, int64_t V, const double* lb, const double* ub) {
+  if (!ctx || V <= 0 || !lb || !ub) return ctx ? ctx->fail(RDISGPU_ERR_ARG, "set_vars: bad argument") : RDISGPU_ERR_ARG;
+  if (ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "set_vars after finalize");
+  if (V > 0x7fffffffLL) return ctx->fail(RDISGPU_ERR_ARG, "set_vars: V exceeds int32 ids");
+  ctx->V = V;
+  ctx->h_lb.assign(lb, lb + V);
+  ctx->h_ub.assign(ub, ub + V);
+  return RDISGPU_OK;
+}
+
+int rdisgpu_add_nlpf(rdisgpu_ctx* ctx, int64_t F, const int64_t* rowptr, const int32_t* vid, const double* expo,
+                     const double* konst, const uint8_t* use_sine, const double* coeff) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (ctx->finalized || ctx->kind != KIND_NONE) return ctx->fail(RDISGPU_ERR_STATE, "add_nlpf: factors already defined");
+  if (F <= 0 || !rowptr || !coeff) return ctx->fail(RDISGPU_ERR_ARG, "add_nlpf: bad argument");
+  const int64_t E = rowptr[F];
+  if (E > 0 && (!vid || !expo || !konst || !use_sine)) return ctx->fail(RDISGPU_ERR_ARG, "add_nlpf: null edge array");
+  if (E > 0x7fffffffLL || F > 0x7fffffffLL) return ctx->fail(RDISGPU_ERR_ARG, "add_nlpf: exceeds int32 ids");
+  for (int64_t j = 0; j < F; ++j)
+    if (rowptr[j + 1] < rowptr[j]) return ctx->fail(RDISGPU_ERR_ARG, "add_nlpf: rowptr not monotone");
+  for (int64_t e = 0; e < E; ++e)
+    if (vid[e] < 0 || vid[e] >= ctx->V) return ctx->fail(RDISGPU_ERR_ARG, "add_nlpf: variable id out of range");
+  ctx->kind = KIND_NLPF;
+  ctx->F = F;
+  ctx->E = E;
+  ctx->h_rowptr.assign(rowptr, rowptr + F + 1);
+  ctx->h_evid.assign(vid, vid + E);
+  ctx->h_expo.assign(expo, expo + E);
+  ctx->h_konst.assign(konst, konst + E);
+  ctx->h_sine.assign(use_sine, use_sine + E);
+  ctx->h_coeff.assign(coeff, coeff + F);
+  return RDISGPU_OK;
+}
+
+int rdisgpu_add_ba(rdisgpu_ctx* ctx, int64_t F, const int32_t* cam, const int32_t* pt, const double* obs_xy,
+                   int32_t ncams, int32_t npts) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (ctx->finalized || ctx->kind != KIND_NONE) return ctx->fail(RDISGPU_ERR_STATE, "add_ba: factors already defined");
+  if (F <= 0 || !cam || !pt || !obs_xy || ncams <= 0 || npts <= 0) return ctx->fail(RDISGPU_ERR_ARG, "add_ba: bad argument");
+  if (ctx->V != 9LL * ncams + 3LL * npts) return ctx->fail(RDISGPU_ERR_ARG, "add_ba: V != 9*ncams + 3*npts");
+  if (F * 12 > 0x7fffffffLL) return ctx->fail(RDISGPU_ERR_ARG, "add_ba: exceeds int32 edge ids");
+  for (int64_t j = 0; j < F; ++j)
+    if (cam[j] < 0 || cam[j] >= ncams || pt[j] < 0 || pt[j] >= npts)
+      return ctx->fail(RDISGPU_ERR_ARG, "add_ba: camera / point id out of range");
+  ctx->kind = KIND_BA;
+  ctx->F = F;
+  ctx->E = 12 * F;
+  ctx->ncams = ncams;
+  ctx->npts = npts;
+  ctx->h_cam.assign(cam, cam + F);
+  ctx->h_pt.assign(pt, pt + F);
+  ctx->h_obs.assign(obs_xy, obs_xy + 2 * F);
+  return RDISGPU_OK;
+}
+
+int rdisgpu_finalize(rdisgpu_ctx* ctx) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "finalize called twice");
+  if (ctx->V <= 0 || ctx->kind == KIND_NONE) return ctx->fail(RDISGPU_ERR_STATE, "finalize: variables / factors missing");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int64_t V = ctx->V, F = ctx->F, E = ctx->E;
+
+  std::vector<double2> dom(V), xbd(V);
+  const double qnan = std::nan("");
+  for (int64_t v = 0; v < V; ++v) {
+    dom[v] = make_double2(ctx->h_lb[v], ctx->h_ub[v]);
+    xbd[v] = make_double2(0.0, qnan);
+  }
+  CK(upload(ctx->dom, dom.data(), (size_t)V, s));
+  CK(upload(ctx->xbd, xbd.data(), (size_t)V, s));
+  CK(cudaStreamSynchronize(s));
+
+  if (ctx->kind == KIND_NLPF) {
+    std::vector<int32_t> rp(F + 1), efac(E);
+    for (int64_t j = 0; j <= F; ++j) rp[j] = (int32_t)ctx->h_rowptr[j];
+    for (int64_t j = 0; j < F; ++j)
+      for (int32_t e = rp[j]; e < rp[j + 1]; ++e) efac[e] = (int32_t)j;
+    std::vector<int32_t> vrow, vedge;
+    build_incidence(V, ctx->h_evid, vrow, vedge);  // items = edge ids, ascending = ascending factor id
+    CK(upload(ctx->rowptr, rp.data(), rp.size(), s));
+    CK(upload(ctx->evid, ctx->h_evid.data(), (size_t)E, s));
+    CK(upload(ctx->expo, ctx->h_expo.data(), (size_t)E, s));
+    CK(upload(ctx->konst, ctx->h_konst.data(), (size_t)E, s));
+    CK(upload(ctx->sine, ctx->h_sine.data(), (size_t)E, s));
+    CK(upload(ctx->coeff, ctx->h_coeff.data(), (size_t)F, s));
+    CK(upload(ctx->vrow, vrow.data(), vrow.size(), s));
+    CK(upload(ctx->vedge, vedge.data(), vedge.size(), s));
+    CK(upload(ctx->efac, efac.data(), efac.size(), s));
+    CK(cudaStreamSynchronize(s));
+  } else {
+    std::vector<int32_t> crow, cfac, prow, pfac;
+    build_incidence(ctx->ncams, ctx->h_cam, crow, cfac);
+    build_incidence(ctx->npts, ctx->h_pt, prow, pfac);
+    std::vector<double2> obs(F);
+    for (int64_t j = 0; j < F; ++j) obs[j] = make_double2(ctx->h_obs[2 * j], ctx->h_obs[2 * j + 1]);
+    CK(upload(ctx->cam, ctx->h_cam.data(), (size_t)F, s));
+    CK(upload(ctx->pt, ctx->h_pt.data(), (size_t)F, s));
+    CK(upload(ctx->obs, obs.data(), (size_t)F, s));
+    CK(upload(ctx->crow, crow.data(), crow.size(), s));
+    CK(upload(ctx->cfac, cfac.data(), cfac.size(), s));
+    CK(upload(ctx->prow, prow.data(), prow.size(), s));
+    CK(upload(ctx->pfac, pfac.data(), pfac.size(), s));
+    CK(cudaStreamSynchronize(s));
+  }
+  CK(ctx->gedge.ensure((size_t)std::max<int64_t>(E, 1)));
+  CK(ctx->gvec.ensure((size_t)V));
+  CK(ctx->hvec.ensure((size_t)V));
+  CK(ctx->xsave.ensure((size_t)V));
+  CK(ctx->fstamp.ensure((size_t)F));
+  CK(cudaMemsetAsync(ctx->fstamp.p, 0xff, (size_t)F * sizeof(int32_t), s));  // -1
+  CK(ctx->s_counter.ensure(4));
+  CK(cudaMemsetAsync(ctx->s_counter.p, 0, 4 * sizeof(unsigned int), s));
+  CK(cudaStreamSynchronize(s));
+
+  // the host copy of the definition is no longer needed
+  std::vector<double>().swap(ctx->h_lb);
+  std::vector<double>().swap(ctx->h_ub);
+  std::vector<int64_t>().swap(ctx->h_rowptr);
+  std::vector<int32_t>().swap(ctx->h_evid);
+  std::vector<double>().swap(ctx->h_expo);
+  std::vector<double>().swap(ctx->h_konst);
+  std::vector<double>().swap(ctx->h_coeff);
+  std::vector<uint8_t>().swap(ctx->h_sine);
+  std::vector<int32_t>().swap(ctx->h_cam);
+  std::vector<int32_t>().swap(ctx->h_pt);
+  std::vector<double>().swap(ctx->h_obs);
+
+  ctx->finalized = true;
+  fill_view(ctx);
+  return RDISGPU_OK;
+}
+
+// ==========================================================================================
+// state
+// ==========================================================================================
+int rdisgpu_set_x(rdisgpu_ctx* ctx, int64_t n, const int32_t* vid, const double* x) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "set_x before finalize");
+  if (n < 0 || (n > 0 && !x) || (!vid && n > ctx->V)) return ctx->fail(RDISGPU_ERR_ARG, "set_x: bad argument");
+  if (n == 0) return RDISGPU_OK;
+  if (vid)
+    for (int64_t i = 0; i < n; ++i)
+      if (vid[i] < 0 || vid[i] >= ctx->V) return ctx->fail(RDISGPU_ERR_ARG, "set_x: variable id out of range");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  CK(ctx->s_f64a.ensure((size_t)n));
+  CK(cudaMemcpyAsync(ctx->s_f64a.p, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (vid) {
+    CK(ctx->s_i32a.ensure((size_t)n));
+    CK(cudaMemcpyAsync(ctx->s_i32a.p, vid, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  }
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 65535);
+  scatter_x_kernel<<<blocks, threads, 0, s>>>(ctx->gv, n, vid ? ctx->s_i32a.p : nullptr, ctx->s_f64a.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));  // x / vid are caller-owned pageable memory
+  return RDISGPU_OK;
+}
+
+int rdisgpu_get_x(rdisgpu_ctx* ctx, int64_t n, const int32_t* vid, double* x) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "get_x before finalize");
+  if (n < 0 || (n > 0 && !x) || (!vid && n > ctx->V)) return ctx->fail(RDISGPU_ERR_ARG, "get_x: bad argument");
+  if (n == 0) return RDISGPU_OK;
+  if (vid)
+    for (int64_t i = 0; i < n; ++i)
+      if (vid[i] < 0 || vid[i] >= ctx->V) return ctx->fail(RDISGPU_ERR_ARG, "get_x: variable id out of range");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  CK(ctx->s_f64a.ensure((size_t)n));
+  if (vid) {
+    CK(ctx->s_i32a.ensure((size_t)n));
+    CK(cudaMemcpyAsync(ctx->s_i32a.p, vid, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  }
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 65535);
+  gather_x_kernel<<<blocks, threads, 0, s>>>(ctx->gv, n, vid ? ctx->s_i32a.p : nullptr, ctx->s_f64a.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(x, ctx->s_f64a.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return RDISGPU_OK;
+}
+
+int rdisgpu_set_factor_const(rdisgpu_ctx* ctx, int64_t n, const int64_t* fid, const double* val, const uint8_t* on) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "set_factor_const before finalize");
+  if (n < 0 || (n > 0 && (!fid || !val || !on))) return ctx->fail(RDISGPU_ERR_ARG, "set_factor_const: bad argument");
+  for (int64_t i = 0; i < n; ++i)
+    if (fid[i] < 0 || fid[i] >= ctx->F) return ctx->fail(RDISGPU_ERR_ARG, "set_factor_const: factor id out of range");
+  if (n == 0) return RDISGPU_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (!ctx->has_fconst) {
+    CK(ctx->fconst_on.ensure((size_t)ctx->F));
+    CK(ctx->fconst_val.ensure((size_t)ctx->F));
+    CK(cudaMemsetAsync(ctx->fconst_on.p, 0, (size_t)ctx->F, s));
+    CK(cudaMemsetAsync(ctx->fconst_val.p, 0, (size_t)ctx->F * sizeof(double), s));
+    ctx->has_fconst = true;
+    fill_view(ctx);
+  }
+  std::vector<int32_t> f32(n);
+  for (int64_t i = 0; i < n; ++i) f32[i] = (int32_t)fid[i];
+  CK(ctx->s_i32a.ensure((size_t)n));
+  CK(ctx->s_f64a.ensure((size_t)n));
+  CK(ctx->s_i32b.ensure((size_t)(n + 3) / 4 + 1));
+  CK(cudaMemcpyAsync(ctx->s_i32a.p, f32.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->s_f64a.p, val, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->s_i32b.p, on, (size_t)n, cudaMemcpyHostToDevice, s));
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 65535);
+  set_fconst_kernel<<<blocks, threads, 0, s>>>(ctx->fconst_on.p, ctx->fconst_val.p, n, ctx->s_i32a.p, ctx->s_f64a.p,
+                                               (const uint8_t*)ctx->s_i32b.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  return RDISGPU_OK;
+}
+
+// ==========================================================================================
+// sweeps
+// ==========================================================================================
+static int upload_fids(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, DevBuf<int32_t>& dst) {
+  for (int64_t i = 0; i < nf; ++i)
+    if (fid[i] < 0 || fid[i] >= ctx->F) return ctx->fail(RDISGPU_ERR_ARG, "factor id out of range");
+  std::vector<int32_t> f32(nf);
+  for (int64_t i = 0; i < nf; ++i) f32[i] = (int32_t)fid[i];
+  CK(dst.ensure((size_t)nf));
+  CK(cudaMemcpyAsync(dst.p, f32.data(), (size_t)nf * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RDISGPU_OK;
+}
+
+int rdisgpu_eval(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, double* sum, double* per_factor) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "eval before finalize");
+  if (!fid) nf = ctx->F;
+  if (nf < 0) return ctx->fail(RDISGPU_ERR_ARG, "eval: bad argument");
+  if (nf == 0) {
+    if (sum) *sum = 0.0;
+    return RDISGPU_OK;
+  }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (fid) {
+    int rc = upload_fids(ctx, nf, fid, ctx->s_i32a);
+    if (rc) return rc;
+  }
+  if (per_factor) CK(ctx->s_f64a.ensure((size_t)nf));
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((nf + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
+  CK(ctx->s_partials.ensure((size_t)blocks + 1));
+  double* dsum = ctx->s_partials.p + blocks;
+  if (ctx->kind == KIND_NLPF)
+    eval_sweep_kernel<NlpfOps><<<blocks, threads, 0, s>>>(ctx->gv, fid ? ctx->s_i32a.p : nullptr, nf,
+                                                          per_factor ? ctx->s_f64a.p : nullptr, ctx->s_partials.p,
+                                                          ctx->s_counter.p, dsum);
+  else
+    eval_sweep_kernel<BaOps><<<blocks, threads, 0, s>>>(ctx->gv, fid ? ctx->s_i32a.p : nullptr, nf,
+                                                        per_factor ? ctx->s_f64a.p : nullptr, ctx->s_partials.p,
+                                                        ctx->s_counter.p, dsum);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  double hsum = 0.0;
+  CK(cudaMemcpyAsync(&hsum, dsum, sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (per_factor) CK(cudaMemcpyAsync(per_factor, ctx->s_f64a.p, (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (sum) *sum = hsum;
+  return RDISGPU_OK;
+}
+
+int rdisgpu_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, int64_t nv, const int32_t* vid, double* g) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "grad before finalize");
+  if (!fid) nf = ctx->F;
+  if (!vid) nv = ctx->V;
+  if (nf < 0 || nv < 0 || (nv > 0 && !g)) return ctx->fail(RDISGPU_ERR_ARG, "grad: bad argument");
+  if (nv == 0) return RDISGPU_OK;
+  if (vid)
+    for (int64_t i = 0; i < nv; ++i)
+      if (vid[i] < 0 || vid[i] >= ctx->V) return ctx->fail(RDISGPU_ERR_ARG, "grad: variable id out of range");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const bool filter = (fid != nullptr);
+  const int32_t stamp = 0x40000000;  // outside the range of batch problem indices
+  if (fid) {
+    int rc = upload_fids(ctx, nf, fid, ctx->s_i32a);
+    if (rc) return rc;
+  }
+  if (vid) {
+    CK(ctx->s_i32b.ensure((size_t)nv));
+    CK(cudaMemcpyAsync(ctx->s_i32b.p, vid, (size_t)nv * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  }
+  CK(ctx->s_f64a.ensure((size_t)nv));
+  const int threads = 256;
+  if (nf > 0) {
+    const int fb = (int)std::min<int64_t>((nf + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
+    if (ctx->kind == KIND_NLPF)
+      factor_partials_kernel<NlpfOps><<<fb, threads, 0, s>>>(ctx->gv, fid ? ctx->s_i32a.p : nullptr, nf, filter ? stamp : -1);
+    else
+      factor_partials_kernel<BaOps><<<fb, threads, 0, s>>>(ctx->gv, fid ? ctx->s_i32a.p : nullptr, nf, filter ? stamp : -1);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+  }
+  const int vb = (int)std::min<int64_t>((nv + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
+  // with an explicit list an unlisted factor must not contribute; with nf == 0 nothing does
+  const bool eff_filter = filter || nf == 0;
+  if (ctx->kind == KIND_NLPF)
+    gather_grad_kernel<NlpfOps><<<vb, threads, 0, s>>>(ctx->gv, vid ? ctx->s_i32b.p : nullptr, nv, stamp, eff_filter, ctx->s_f64a.p);
+  else
+    gather_grad_kernel<BaOps><<<vb, threads, 0, s>>>(ctx->gv, vid ? ctx->s_i32b.p : nullptr, nv, stamp, eff_filter, ctx->s_f64a.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  if (filter && nf > 0) {
+    const int fb = (int)std::min<int64_t>((nf + threads - 1) / threads, 65535);
+    unstamp_kernel<<<fb, threads, 0, s>>>(ctx->gv, ctx->s_i32a.p, nf);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(g, ctx->s_f64a.p, (size_t)nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return RDISGPU_OK;
+}
+
+int rdisgpu_factor_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, int32_t arity_max, double* rows) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "factor_grad before finalize");
+  if (!fid) nf = ctx->F;
+  if (nf <= 0 || arity_max <= 0 || !rows) return ctx->fail(RDISGPU_ERR_ARG, "factor_grad: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (fid) {
+    int rc = upload_fids(ctx, nf, fid, ctx->s_i32a);
+    if (rc) return rc;
+  }
+  CK(ctx->s_f64b.ensure((size_t)nf * arity_max));
+  CK(cudaMemsetAsync(ctx->s_f64b.p, 0, (size_t)nf * arity_max * sizeof(double), s));
+  const int threads = 128;
+  const int blocks = (int)std::min<int64_t>((nf + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
+  if (ctx->kind == KIND_NLPF)
+    factor_rows_kernel<NlpfOps><<<blocks, threads, 0, s>>>(ctx->gv, fid ? ctx->s_i32a.p : nullptr, nf, arity_max, ctx->s_f64b.p);
+  else
+    factor_rows_kernel<BaOps><<<blocks, threads, 0, s>>>(ctx->gv, fid ? ctx->s_i32a.p : nullptr, nf, arity_max, ctx->s_f64b.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(rows, ctx->s_f64b.p, (size_t)nf * arity_max * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return RDISGPU_OK;
+}
+
+// ==========================================================================================
+// subspace solves
+// ==========================================================================================
+int rdisgpu_batch_create(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t nprobs, rdisgpu_batch** out) {
+  if (!ctx || !out) return RDISGPU_ERR_ARG;
+  *out = nullptr;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "batch_create before finalize");
+  if (nprobs <= 0 || !probs) return ctx->fail(RDISGPU_ERR_ARG, "batch_create: no problems");
+  if (nprobs >= 0x40000000LL) return ctx->fail(RDISGPU_ERR_ARG, "batch_create: too many problems");
+  CK(cudaSetDevice(ctx->device));
+
+  std::unique_ptr<rdisgpu_batch> b(new rdisgpu_batch());
+  b->ctx = ctx;
+  b->nprobs = nprobs;
+  b->h_probs.resize(nprobs);
+  int64_t tv = 0, tf = 0;
+  for (int64_t p = 0; p < nprobs; ++p) {
+    const rdisgpu_problem& P = probs[p];
+    if (P.nv < 0 || P.nf < 0 || (P.nv > 0 && !P.vid) || (P.nf > 0 && !P.fid) || P.nv > 0x7fffffffLL || P.nf > 0x7fffffffLL)
+      return ctx->fail(RDISGPU_ERR_ARG, "batch_create: malformed problem");
+    b->h_probs[p] = ProblemDesc{tv, tf, (int32_t)P.nv, (int32_t)P.nf};
+    tv += P.nv;
+    tf += P.nf;
+  }
+  b->total_nv = tv;
+  b->total_nf = tf;
+  std::vector<int32_t> vids(tv), fids(tf);
+  // sibling check: no variable and no factor may belong to two problems of one batch
+  std::vector<uint8_t> vseen((size_t)ctx->V, 0), fseen((size_t)ctx->F, 0);
+  for (int64_t p = 0; p < nprobs; ++p) {
+    const rdisgpu_problem& P = probs[p];
+    const ProblemDesc& D = b->h_probs[p];
+    for (int64_t j = 0; j < P.nv; ++j) {
+      const int32_t v = P.vid[j];
+      if (v < 0 || v >= ctx->V) return ctx->fail(RDISGPU_ERR_ARG, "batch_create: variable id out of range");
+      if (vseen[v]) return ctx->fail(RDISGPU_ERR_OVERLAP, "batch_create: a variable appears twice in the batch");
+      vseen[v] = 1;
+      vids[D.var_off + j] = v;
+    }
+    for (int64_t k = 0; k < P.nf; ++k) {
+      const int64_t f = P.fid[k];
+      if (f < 0 || f >= ctx->F) return ctx->fail(RDISGPU_ERR_ARG, "batch_create: factor id out of range");
+      if (fseen[f]) return ctx->fail(RDISGPU_ERR_OVERLAP, "batch_create: a factor appears twice in the batch");
+      fseen[f] = 1;
+      fids[D.fac_off + k] = (int32_t)f;
+    }
+  }
+
+  // size classes: tiles of 1..32 lanes, CTAs of 64..256 threads, cooperative grid
+  const int kTileMax = 32, kBlockMax = 4096;
+  std::vector<std::vector<int32_t>> tile_lists(6), block_lists(3);
+  std::vector<int32_t> grid_list;
+  for (int64_t p = 0; p < nprobs; ++p) {
+    const int nf = b->h_probs[p].nf;
+    if (nf <= kTileMax) {
+      int g = next_pow2(std::max(nf, 1)), lg = 0;
+      while ((1 << lg) < g) ++lg;
+      tile_lists[lg].push_back((int32_t)p);
+    } else if (nf <= kBlockMax) {
+      const int t = nf <= 64 ? 0 : (nf <= 128 ? 1 : 2);
+      block_lists[t].push_back((int32_t)p);
+    } else {
+      grid_list.push_back((int32_t)p);
+    }
+  }
+  b->h_order.clear();
+  for (int lg = 0; lg < 6; ++lg) {
+    if (tile_lists[lg].empty()) continue;
+    b->classes.push_back({0, 1 << lg, (int64_t)b->h_order.size(), (int64_t)tile_lists[lg].size()});
+    b->h_order.insert(b->h_order.end(), tile_lists[lg].begin(), tile_lists[lg].end());
+  }
+  for (int t = 0; t < 3; ++t) {
+    if (block_lists[t].empty()) continue;
+    b->classes.push_back({1, 64 << t, (int64_t)b->h_order.size(), (int64_t)block_lists[t].size()});
+    b->h_order.insert(b->h_order.end(), block_lists[t].begin(), block_lists[t].end());
+  }
+  if (!grid_list.empty()) {
+    b->classes.push_back({2, 256, (int64_t)b->h_order.size(), (int64_t)grid_list.size()});
+    b->h_order.insert(b->h_order.end(), grid_list.begin(), grid_list.end());
+  }
+
+  cudaStream_t s = ctx->stream;
+  CK(upload(b->probs, b->h_probs.data(), (size_t)nprobs, s));
+  CK(upload(b->vids, vids.data(), (size_t)tv, s));
+  CK(upload(b->fids, fids.data(), (size_t)tf, s));
+  CK(upload(b->order, b->h_order.data(), b->h_order.size(), s));
+  CK(b->x0.ensure((size_t)tv));
+  CK(b->xout.ensure((size_t)tv));
+  CK(b->res.ensure((size_t)nprobs));
+  CK(b->h_res.ensure((size_t)nprobs));
+  CK(b->h_x.ensure((size_t)tv));
+  CK(cudaStreamSynchronize(s));  // vids / fids / h_order staging vectors die here
+  *out = b.release();
+  return RDISGPU_OK;
+}
+
+int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiters, double ftol) {
+  if (!b) return RDISGPU_ERR_ARG;
+  rdisgpu_ctx* ctx = b->ctx;
+  if (maxiters <= 0) return ctx->fail(RDISGPU_ERR_ARG, "solve: maxiters must be positive");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (x0_host && b->total_nv > 0)  // pageable source: staged by the driver before the call returns; pinned: truly async
+    CK(cudaMemcpyAsync(b->x0.p, x0_host, (size_t)b->total_nv * sizeof(double), cudaMemcpyHostToDevice, s));
+  BatchView bv;
+  bv.probs = b->probs.p;
+  bv.vids = b->vids.p;
+  bv.fids = b->fids.p;
+  bv.x0 = x0_host ? b->x0.p : nullptr;
+  bv.xout = b->xout.p;
+  bv.res = b->res.p;
+  GraphView gv = ctx->gv;
+  int launches = 0;
+  for (const auto& c : b->classes) {
+    const int32_t* ord = b->order.p + c.off;
+    const int cnt = (int)c.count;
+    if (c.kind == 0) {
+      const int per_block = 128 / c.param;
+      const int blocks = (cnt + per_block - 1) / per_block;
+#define LAUNCH_TILE(OPS, GG) solve_tile_kernel<OPS, GG><<<blocks, 128, 0, s>>>(gv, bv, ord, cnt, maxiters, ftol)
+#define LAUNCH_TILE_G(OPS)                 \
+  switch (c.param) {                       \
+    case 1: LAUNCH_TILE(OPS, 1); break;    \
+    case 2: LAUNCH_TILE(OPS, 2); break;    \
+    case 4: LAUNCH_TILE(OPS, 4); break;    \
+    case 8: LAUNCH_TILE(OPS, 8); break;    \
+    case 16: LAUNCH_TILE(OPS, 16); break;  \
+    default: LAUNCH_TILE(OPS, 32); break;  \
+  }
+      if (ctx->kind == KIND_NLPF) { LAUNCH_TILE_G(NlpfOps) } else { LAUNCH_TILE_G(BaOps) }
+#undef LAUNCH_TILE_G
+#undef LAUNCH_TILE
+      ++launches;
+    } else if (c.kind == 1) {
+      if (ctx->kind == KIND_NLPF)
+        solve_block_kernel<NlpfOps><<<cnt, c.param, 0, s>>>(gv, bv, ord, cnt, maxiters, ftol);
+      else
+        solve_block_kernel<BaOps><<<cnt, c.param, 0, s>>>(gv, bv, ord, cnt, maxiters, ftol);
+      ++launches;
+    } else {
+      const int threads = 256;
+      int occ = 0;
+      const void* fn = (ctx->kind == KIND_NLPF) ? (const void*)solve_grid_kernel<NlpfOps> : (const void*)solve_grid_kernel<BaOps>;
+      if (ctx->kind == KIND_NLPF)
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_grid_kernel<NlpfOps>, threads, 0));
+      else
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_grid_kernel<BaOps>, threads, 0));
+      if (occ < 1) return ctx->fail(RDISGPU_ERR_CUDA, "cooperative solve kernel cannot be resident");
+      const int max_blocks = occ * ctx->sm_count;
+      CK(ctx->grid_partials.ensure((size_t)max_blocks * 8));
+      for (int i = 0; i < cnt; ++i) {
+        int pidx = b->h_order[c.off + i];
+        const ProblemDesc& D = b->h_probs[pidx];
+        const int work = std::max(D.nf, D.nv);
+        int blocks = std::min(max_blocks, std::max(1, (work + threads - 1) / threads));
+        double* partials = ctx->grid_partials.p;
+        void* args[] = {(void*)&gv, (void*)&bv, (void*)&pidx, (void*)&partials, (void*)&maxiters, (void*)&ftol};
+        CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(threads), args, 0, s));
+        ++launches;
+      }
+    }
+    CK(cudaGetLastError());
+  }
+  b->last_launches = launches;
+  ctx->launches += launches;
+  b->solved = true;
+  return RDISGPU_OK;
+}
+
+int rdisgpu_batch_fetch(rdisgpu_batch* b, rdisgpu_result* out, double* sum_f_end) {
+  if (!b) return RDISGPU_ERR_ARG;
+  rdisgpu_ctx* ctx = b->ctx;
+  if (!b->solved) return ctx->fail(RDISGPU_ERR_STATE, "batch_fetch before batch_solve");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemcpyAsync(b->h_res.p, b->res.p, (size_t)b->nprobs * sizeof(ResultRec), cudaMemcpyDeviceToHost, s));
+  bool want_x = false;
+  if (out)
+    for (int64_t p = 0; p < b->nprobs && !want_x; ++p) want_x = (out[p].x != nullptr);
+  if (want_x && b->total_nv > 0)
+    CK(cudaMemcpyAsync(b->h_x.p, b->xout.p, (size_t)b->total_nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  double tot = 0.0;
+  for (int64_t p = 0; p < b->nprobs; ++p) {
+    const ResultRec& r = b->h_res.p[p];
+    tot += r.f_end;
+    if (!out) continue;
+    out[p].f_init = r.f_init;
+    out[p].f_end = r.f_end;
+    out[p].iters = r.iters;
+    out[p].status = r.status;
+    out[p].n_feval = (int64_t)r.n_value + r.n_slope;
+    out[p].n_geval = r.n_slope;
+    if (out[p].x) std::memcpy(out[p].x, b->h_x.p + b->h_probs[p].var_off, (size_t)b->h_probs[p].nv * sizeof(double));
+  }
+  if (sum_f_end) *sum_f_end = tot;
+  return RDISGPU_OK;
+}
+
+void rdisgpu_batch_destroy(rdisgpu_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  delete b;
+}
+
+int rdisgpu_batch_last_launches(const rdisgpu_batch* b) { return b ? b->last_launches : 0; }
+
+int rdisgpu_solve_cgd(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t nprobs, int maxiters, double ftol,
+                      rdisgpu_result* out) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!out) return ctx->fail(RDISGPU_ERR_ARG, "solve_cgd: null result array");
+  rdisgpu_batch* b = nullptr;
+  int rc = rdisgpu_batch_create(ctx, probs, nprobs, &b);
+  if (rc) return rc;
+  // x0: either every problem brings start values or none does
+  bool any = false, all = true;
+  for (int64_t p = 0; p < nprobs; ++p) {
+    if (probs[p].x0) any = true;
+    else if (probs[p].nv > 0) all = false;
+  }
+  std::vector<double> x0;
+  if (any && !all) {
+    // mixed: fill the gaps from the device state
+    x0.resize(b->total_nv);
+    for (int64_t p = 0; p < nprobs && rc == RDISGPU_OK; ++p) {
+      double* dst = x0.data() + b->h_probs[p].var_off;
+      if (probs[p].x0) std::memcpy(dst, probs[p].x0, (size_t)probs[p].nv * sizeof(double));
+      else rc = rdisgpu_get_x(ctx, probs[p].nv, probs[p].vid, dst);
+    }
+  } else if (any) {
+    x0.resize(b->total_nv);
+    for (int64_t p = 0; p < nprobs; ++p)
+      if (probs[p].nv > 0) std::memcpy(x0.data() + b->h_probs[p].var_off, probs[p].x0, (size_t)probs[p].nv * sizeof(double));
+  }
+  if (rc == RDISGPU_OK) rc = rdisgpu_batch_solve_cgd(b, any ? x0.data() : nullptr, maxiters, ftol);
+  if (rc == RDISGPU_OK) rc = rdisgpu_batch_fetch(b, out, nullptr);
+  rdisgpu_batch_destroy(b);
+  return rc;
+}
+
+// ==========================================================================================
+// introspection
+// ==========================================================================================
+int64_t rdisgpu_num_vars(const rdisgpu_ctx* ctx) { return ctx ? ctx->V : 0; }
+int64_t rdisgpu_num_factors(const rdisgpu_ctx* ctx) { return ctx ? ctx->F : 0; }
+int rdisgpu_device_state(rdisgpu_ctx* ctx, void** dptr, int64_t* n_pairs) {
+  if (!ctx || !dptr || !n_pairs) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "device_state before finalize");
+  *dptr = ctx->xbd.p;
+  *n_pairs = ctx->V;
+  return RDISGPU_OK;
+}
+int64_t rdisgpu_launch_count(const rdisgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+const char* rdisgpu_version(void) { return "rdis_b200 0.1 (sm_100a, fp64)"; }
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+"""GPU parity tests proper: every call goes through the C-ABI (rdis_b200.capi -> librdis_b200.so)
+and is compared with the CPU oracle on the same seeded inputs.
+
+Tolerances (written here as the contract):
+  per-factor value / partial derivative   1e-12 relative (+1e-12 * scale absolute for cancellation)
+  sums over factors                       1e-12 relative
+  final objective of a subspace solve     1e-6 relative (north_star), typically observed ~1e-12
+  index bookkeeping (which variables moved, statuses of empty problems)   bit-exact
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(built_lib):
+    from rdis_b200 import Context  # noqa: F401
+    import rdis_b200
+    return rdis_b200
+
+
+def _relerr(a, b, floor=1e-300):
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+def _ba_small(P):
+    return P.ba_synthetic(ncams=7, npts=120, nobs=520, seed=11)
+
+
+def test_eval_and_grad_ba(gpu, oracle_mod):
+    from rdis_b200 import Context, problems as P
+    spec = _ba_small(P)
+    ctx = Context.from_spec(spec); orc = oracle_mod.OracleFunction.from_spec(spec)
+    ctx.set_x(spec["x0"]); orc.set_x(spec["x0"])
+    sg, pg = ctx.eval(per_factor=True)
+    so, po = orc.eval(per_factor=True)
+    assert _relerr(pg, po).max() <= 1e-12
+    assert abs(sg - so) <= 1e-12 * abs(so)
+    # subset in caller order
+    fid = np.random.default_rng(0).permutation(spec["F"])[:97]
+    assert abs(ctx.eval(fid) - orc.eval(fid)) <= 1e-12 * abs(orc.eval(fid))
+    # per-factor Jacobian rows
+    rows = ctx.factor_grad(np.arange(spec["F"]), 12)
+    ref = np.stack([orc.factor_grad(j, 12) for j in range(spec["F"])])
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(rows - ref) <= 1e-11 * scale + 1e-300).all()
+    # accumulated gradient, all factors / all vars and subset / subset
+    g = ctx.grad(); go = orc.grad()
+    assert (np.abs(g - go) <= 1e-11 * np.abs(go).max()).all()
+    vid = np.arange(9 * 3, 9 * 3 + 9)
+    fsub = np.nonzero(spec["cam"] == 3)[0][::2]
+    g2 = ctx.grad(fsub, vid); go2 = orc.grad(fsub, vid)
+    assert (np.abs(g2 - go2) <= 1e-11 * np.abs(go2).max()).all()
+
+
+def test_eval_and_grad_nlpf(gpu, oracle_mod):
+    from rdis_b200 import Context, problems as P
+    spec = P.sinusoid(6, 3, 4, odd=True)
+    x0 = P.random_start(spec, 3)
+    ctx = Context.from_spec(spec); orc = oracle_mod.OracleFunction.from_spec(spec)
+    ctx.set_x(x0); orc.set_x(x0)
+    sg, pg = ctx.eval(per_factor=True)
+    so, po = orc.eval(per_factor=True)
+    assert (np.abs(pg - po) <= 1e-13 * np.maximum(np.abs(po), 1.0)).all()
+    assert abs(sg - so) <= 1e-12 * max(abs(so), 1.0)
+    g = ctx.grad(); go = orc.grad()
+    assert (np.abs(g - go) <= 1e-12 * np.abs(go).max()).all()
+
+
+def test_nlpf_general_terms(gpu, oracle_mod):
+    """exponents != 1, constants, mixed sine flags, arity above the register fast path."""
+    from rdis_b200 import Context
+    rng = np.random.default_rng(5)
+    V, F = 40, 200
+    ar = rng.integers(1, 12, size=F)
+    rowptr = np.concatenate([[0], np.cumsum(ar)])
+    vid = np.concatenate([rng.choice(V, size=a, replace=False) for a in ar]).astype(np.int32)
+    E = len(vid)
+    expo = rng.choice([1.0, 2.0, 3.0, 0.5, 4.0], size=E)
+    konst = rng.choice([0.0, 0.0, 0.7, -1.3], size=E)
+    # keep (x-k) positive where the exponent is fractional
+    sine = rng.integers(0, 2, size=E).astype(np.uint8)
+    coeff = rng.normal(0, 2, size=F)
+    spec = dict(kind="nlpf", V=V, F=F, lb=np.full(V, 2.0), ub=np.full(V, 5.0), rowptr=rowptr, vid=vid, expo=expo,
+                konst=konst, sine=sine, coeff=coeff)
+    x0 = rng.uniform(2.0, 5.0, size=V)
+    ctx = Context.from_spec(spec); orc = oracle_mod.OracleFunction.from_spec(spec)
+    ctx.set_x(x0); orc.set_x(x0)
+    sg, pg = ctx.eval(per_factor=True); so, po = orc.eval(per_factor=True)
+    assert (np.abs(pg - po) <= 1e-12 * np.maximum(np.abs(po), 1e-300)).all()
+    g = ctx.grad(); go = orc.grad()
+    assert (np.abs(g - go) <= 1e-11 * np.abs(go).max()).all()
+
+
+def _check_solves(r, o, tol=1e-6):
+    rel = _relerr(r["f_end"], o["f_end"], 1e-12)
+    assert rel.max() <= tol, (rel.max(), int(rel.argmax()))
+    rel0 = _relerr(r["f_init"], o["f_init"], 1e-12)
+    assert rel0.max() <= 1e-12
+    return rel.max()
+
+
+def test_solve_ba_point_and_camera_blocks(gpu, oracle_mod):
+    from rdis_b200 import Context, problems as P
+    spec = _ba_small(P)
+    x0 = spec["x0"]
+    ctx = Context.from_spec(spec); orc = oracle_mod.OracleFunction.from_spec(spec)
+    for ps in (P.ba_point_problems(spec), P.ba_camera_problems(spec)):
+        ctx.set_x(x0); orc.set_x(x0)
+        x0c = x0[ps.vids]
+        r = ctx.solve_cgd(ps, x0c, 25, 3e-8)
+        o = orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0c, 25, 3e-8)
+        worst = _check_solves(r, o)
+        # committed state == returned x, untouched elsewhere (bit-exact bookkeeping)
+        xg = ctx.get_x()
+        assert np.array_equal(xg[ps.vids], r["x"])
+        mask = np.ones(spec["V"], bool); mask[ps.vids] = False
+        assert np.array_equal(xg[mask], x0[mask])
+        # the objective at the returned point is what was reported
+        tot = ctx.eval(ps.fids)
+        assert abs(tot - r["f_end"].sum()) <= 1e-9 * abs(tot)
+        assert (r["f_end"] <= r["f_init"]).all()
+        print("worst rel f_end diff", worst)
+
+
+def test_solve_full_problem_grid(gpu, oracle_mod):
+    """One large component -> cooperative-grid path (nf above the CTA threshold)."""
+    from rdis_b200 import Context, problems as P
+    spec = P.ba_synthetic(ncams=5, npts=40, nobs=160, seed=3)
+    # enlarge so that nf > 4096 without making the oracle slow: replicate observations
+    reps = 30
+    spec = dict(spec)
+    spec["cam"] = np.tile(spec["cam"], reps); spec["pt"] = np.tile(spec["pt"], reps)
+    spec["obs"] = np.tile(spec["obs"], (reps, 1)) + np.random.default_rng(1).normal(0, 0.3, (160 * reps, 2))
+    spec["F"] = 160 * reps
+    x0 = spec["x0"]
+    ps = P.ba_point_problems(spec)
+    full = P.full_problem(spec)
+    # only the points move (keeps the oracle's quadratic gradient merge cheap): one 120-var problem
+    from rdis_b200.capi import ProblemSet
+    big = ProblemSet([0, len(ps.vids)], ps.vids, [0, spec["F"]], np.arange(spec["F"]))
+    ctx = Context.from_spec(spec); orc = oracle_mod.OracleFunction.from_spec(spec)
+    ctx.set_x(x0); orc.set_x(x0)
+    x0c = x0[big.vids]
+    r = ctx.solve_cgd(big, x0c, 10, 3e-8)
+    o = orc.solve_cgd_batch(big.var_off, big.vids, big.fac_off, big.fids, x0c, 10, 3e-8)
+    _check_solves(r, o)
+    assert full.n == 1
+
+
+def test_solve_nlpf_subtrees(gpu, oracle_mod):
+    from rdis_b200 import Context, problems as P
+    spec = P.sinusoid(7, 2, 4)
+    x0 = P.random_start(spec, 9)
+    ps = P.sinusoid_subtree_problems(spec, 3)
+    ctx = Context.from_spec(spec); orc = oracle_mod.OracleFunction.from_spec(spec)
+    ctx.set_x(x0); orc.set_x(x0)
+    x0c = x0[ps.vids]
+    r = ctx.solve_cgd(ps, x0c, 25, 3e-8)
+    o = orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0c, 25, 3e-8)
+    _check_solves(r, o)
+
+
+def test_edge_cases(gpu, oracle_mod):
+    from rdis_b200 import Context, problems as P, RdisGpuError
+    from rdis_b200.capi import ProblemSet
+    spec = _ba_small(P)
+    x0 = spec["x0"]
+    ctx = Context.from_spec(spec)
+    ctx.set_x(x0)
+    # empty factor list: returns 0, delta 0, x untouched (CGD.cpp:26-29)
+    ps = ProblemSet.from_lists([(np.array([63, 64, 65]), np.array([], np.int64))])
+    r = ctx.solve_cgd(ps, x0[ps.vids])
+    assert r["f_end"][0] == 0.0 and r["f_init"][0] == 0.0 and r["status"][0] == 5
+    assert np.array_equal(r["x"], x0[ps.vids])
+    # overlapping problems are refused, not silently raced
+    pts = P.ba_point_problems(spec)
+    bad = ProblemSet.from_lists([(pts.vids[0:3], pts.fids[pts.fac_off[0]:pts.fac_off[1]]),
+                                 (pts.vids[0:3], pts.fids[pts.fac_off[1]:pts.fac_off[2]])])
+    with pytest.raises(RdisGpuError):
+        ctx.solve_cgd(bad, x0[bad.vids])
+    # a start point outside the domain is clamped on entry (quickAssignVals, sanitize=true)
+    one = pts.subset([0])
+    far = x0[one.vids] + 1e9
+    r = ctx.solve_cgd(one, far)
+    assert (r["x"] <= spec["ub"][one.vids]).all()
+    # x0 = None uses the device state
+    ctx.set_x(x0)
+    r1 = ctx.solve_cgd(pts.subset([1, 2]), None)
+    ctx.set_x(x0)
+    r2 = ctx.solve_cgd(pts.subset([1, 2]), x0[pts.subset([1, 2]).vids])
+    assert np.array_equal(r1["f_end"], r2["f_end"]) and np.array_equal(r1["x"], r2["x"])
+
+
+def test_assigned_constant_factors(gpu, oracle_mod):
+    """Simplified factors evaluate to their constant but keep full gradients."""
+    from rdis_b200 import Context, problems as P
+    spec = _ba_small(P)
+    x0 = spec["x0"]
+    ctx = Context.from_spec(spec); orc = oracle_mod.OracleFunction.from_spec(spec)
+    ctx.set_x(x0); orc.set_x(x0)
+    fid = np.array([0, 5, 17]); val = np.array([1.5, -2.0, 0.25]); on = np.array([1, 1, 1], np.uint8)
+    ctx.set_factor_const(fid, val, on); orc.set_factor_const(fid, val, on)
+    assert abs(ctx.eval() - orc.eval()) <= 1e-12 * abs(orc.eval())
+    g = ctx.grad(); go = orc.grad()
+    assert (np.abs(g - go) <= 1e-11 * np.abs(go).max()).all()
+
+
+def test_run_to_run_determinism(gpu):
+    from rdis_b200 import Context, problems as P
+    spec = _ba_small(P)
+    x0 = spec["x0"]
+    ctx = Context.from_spec(spec)
+    ps = P.ba_point_problems(spec)
+    outs = []
+    for _ in range(3):
+        ctx.set_x(x0)
+        outs.append(ctx.solve_cgd(ps, x0[ps.vids]))
+    for o in outs[1:]:
+        assert np.array_equal(o["f_end"], outs[0]["f_end"]) and np.array_equal(o["x"], outs[0]["x"])
+        assert np.array_equal(o["iters"], outs[0]["iters"])
