@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py — subspace-solves/sec on a ladybug-49-7776-shaped bundle-adjustment factor graph.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One *step* = one alternating wave of the recursive decomposer's leaf work on a synthetic graph
+with the shape of data/ladybug-problem-49-7776-pre.txt (49 cameras, 7776 points, 31843
+observations): reset the state to x0, solve the 7776 point components given the cameras (one
+sibling batch), then the 49 camera components given the points (second sibling batch) —
+7825 CGDSubspaceOptimizer::optimize calls (SSmaxit 25, ftol 3e-8, the optBA defaults) — and
+accumulate the global objective, which is all-reduced across ranks (the path's only collective).
+
+  value   solves/s, device-resident: problem lists and x0 already in HBM, results stay in HBM
+  e2e     the same through rdisgpu_solve_cgd with HOST buffers: index lists + x0 up, results down
+  roofline        the dominant kernel of the step, algorithmic bytes (every objective
+                  evaluation = 32 B/factor + 8 B/variable touched, +8 B/variable with gradients)
+                  over its CUDA-event time; the solves are L2-resident and latency/FP64 bound
+  roofline_sweep  the residual sweep on the cfg4 graph (1,048,575 vars / 4,194,292 factors, 268 MB
+                  per sweep — larger than L2): the HBM-roofline evidence for the sweep kernel
+  cpu_baseline    the CPU oracle (reference-semantics port, 1 core) on a bounded sample of the wave
+
+Multi-GPU (weak scaling): every rank owns one ladybug-shaped component set (seed + rank); no data
+path collective besides the objective all-reduce.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAXITERS, FTOL = 25, 3e-8
+SEED = 20260417
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sweep", action="store_true", help="skip the cfg4 sweep roofline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def algorithmic_bytes(spec, ps, res):
+    """one objective evaluation over a problem = 32 B per factor + 8 B per distinct
+    variable it touches; evaluations that also produce derivatives add 8 B per variable."""
+    nf = np.diff(ps.fac_off)
+    nv = np.diff(ps.var_off)
+    if ps.n and nv[0] == 3:      # point components: 3 own variables + 9 per observing camera
+        touched = 3 + 9 * nf
+    else:                        # camera components: 9 own variables + 3 per observed point
+        touched = 9 + 3 * nf
+    n_f = res["n_feval"].astype(np.float64)
+    n_g = res["n_geval"].astype(np.float64)
+    return float(np.sum(n_f * (32.0 * nf + 8.0 * touched) + n_g * 8.0 * touched))
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from rdis_b200 import Context, problems as P
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus must equal WORLD_SIZE")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload: one ladybug-shaped component set per rank ----
+    spec = P.ba_synthetic(seed=SEED + rank)
+    x0 = spec["x0"]
+    pts, cams = P.ba_point_problems(spec), P.ba_camera_problems(spec)
+    n_solves = pts.n + cams.n
+    stream = torch.cuda.current_stream()
+    ctx = Context.from_spec(spec, device=local_rank, stream=stream.cuda_stream)
+    x0_dev = torch.from_numpy(x0).to(dev)
+    obj_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+    b_pts, b_cams = ctx.batch(pts), ctx.batch(cams)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        obj_dev.zero_()
+        ctx.set_x_device(x0_dev.data_ptr(), spec["V"])
+        b_pts.solve(None, MAXITERS, FTOL)
+        b_pts.objective_device(obj_dev.data_ptr())
+        b_cams.solve(None, MAXITERS, FTOL)
+        b_cams.objective_device(obj_dev.data_ptr())
+        if world > 1:
+            dist.all_reduce(obj_dev)
+
+    launches_per_step = None
+    for _ in range(max(args.warmup, 3)):
+        l0 = ctx.launch_count
+        step_resident()
+        launches_per_step = ctx.launch_count - l0
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                     # untimed: evicts the previous step's working set from L2
+        ev[k][0].record(stream)
+        obj_dev.zero_()
+        ctx.set_x_device(x0_dev.data_ptr(), spec["V"])
+        b_pts.solve(None, MAXITERS, FTOL)
+        b_pts.objective_device(obj_dev.data_ptr())
+        ev[k][1].record(stream)           # splits the step into its two solve launches
+        b_cams.solve(None, MAXITERS, FTOL)
+        b_cams.objective_device(obj_dev.data_ptr())
+        if world > 1:
+            dist.all_reduce(obj_dev)
+        ev[k][2].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    ms_steps = np.array([e[0].elapsed_time(e[2]) for e in ev])
+    ms_pts = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    ms_cams = np.array([e[1].elapsed_time(e[2]) for e in ev])
+    total_ms = float(ms_steps.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    objective = float(obj_dev.item())
+    value = world * n_solves * args.steps / (total_ms * 1e-3)
+
+    # ---- results of the last step (for the roofline's evaluation counts and the residual-eval rate) ----
+    r_pts, r_cams = b_pts.fetch(), b_cams.fetch()
+    evals = float(np.sum(r_pts["n_feval"] * np.diff(pts.fac_off)) + np.sum(r_cams["n_feval"] * np.diff(cams.fac_off)))
+    resid_evals_per_s = world * evals * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through rdisgpu_solve_cgd ----
+    x0_pin = torch.from_numpy(x0).pin_memory()
+    x0_pts_pin = torch.from_numpy(x0[pts.vids]).pin_memory().numpy()
+    x0_cams_pin = torch.from_numpy(x0[cams.vids]).pin_memory().numpy()
+
+    def step_e2e():
+        ctx.set_x(x0_pin.numpy())                                   # H2D of the state
+        ra = ctx.solve_cgd(pts, x0_pts_pin, MAXITERS, FTOL)         # H2D lists + x0, D2H results
+        rb = ctx.solve_cgd(cams, x0_cams_pin, MAXITERS, FTOL)
+        return float(ra["f_end"].sum() + rb["f_end"].sum())
+
+    for _ in range(2):
+        step_e2e()
+    e2e_steps = max(3, min(args.steps, 10))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        obj_e2e = step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = world * n_solves * e2e_steps / t_e2e
+    h2d = 8 * spec["V"] + sum(4 * len(p.vids) + 8 * len(p.fids) + 8 * len(p.vids) + 24 * p.n for p in (pts, cams))
+    d2h = sum(8 * len(p.vids) + 32 * p.n for p in (pts, cams))
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        dom_is_pts = ms_pts.mean() >= ms_cams.mean()
+        dom_ps, dom_res, dom_ms = (pts, r_pts, ms_pts.mean()) if dom_is_pts else (cams, r_cams, ms_cams.mean())
+        abytes = algorithmic_bytes(spec, dom_ps, dom_res)
+        achieved = abytes / (dom_ms * 1e-3) / 1e9
+        out = {
+            "metric": "subspace-solves/sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ladybug-49-7776-shaped BA graph (49 cams, 7776 pts, 31843 obs) per GPU: "
+                                   "7776 point-component + 49 camera-component CGD solves per step",
+                       "ssmaxit": MAXITERS, "ssftol": FTOL, "parallelism": "component-shard x%d" % world,
+                       "l2": "flushed between steps (256 MiB memset, untimed)", "seed": SEED},
+            "residual_evals_per_sec": resid_evals_per_s,
+            "objective_after_step": objective,
+            "kernel_ms": {"solve_tile_kernel(points)": float(ms_pts.mean()), "solve_block_kernel(cameras)": float(ms_cams.mean())},
+            "wall_s_timed_region": t_wall,
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "objective": obj_e2e},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "solve_tile_kernel<BaOps,*> (point components)" if dom_is_pts
+                         else "solve_block_kernel<BaOps> (camera components)",
+                         "algorithmic_bytes_per_launch": abytes, "launch_ms": float(dom_ms), "peak_source": peak_src,
+                         "note": "working set 1.4 MB: L2-resident, FP64/latency bound; see roofline_sweep for the HBM-bound kernel"},
+        }
+    # ---- the HBM-bound kernel: residual sweep on the cfg4 graph (rank 0) ----
+    if rank == 0 and not args.no_sweep:
+        out["roofline_sweep"] = sweep_roofline(local_rank, stream)
+    if rank == 0 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(spec, pts, cams, x0, args.cpu_seconds)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def sweep_roofline(device, stream):
+    """Residual sweep (evalFactors over all factors) on the cfg4 sinusoid graph: 268.4 MB of
+    algorithmic bytes per launch (20 F + 21 E + 8 V), larger than L2, timed with CUDA events."""
+    import torch
+    from rdis_b200 import Context, problems as P
+    spec = P.sinusoid(19, 2, 4)
+    V, F, E = spec["V"], spec["F"], len(spec["vid"])
+    ctx = Context.from_spec(spec, device=device, stream=stream.cuda_stream)
+    ctx.set_x(P.random_start(spec, 1))
+    abytes = 20.0 * F + 21.0 * E + 8.0 * V
+    for _ in range(3):
+        s = ctx.eval()
+    times = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        lib_eval_async(ctx)
+        b.record(stream)
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = float(np.median(times))
+    peak, peak_src = peaks()
+    ach = abytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "eval_sweep_kernel<NlpfOps>", "workload": "sinusoid h=19 k=2 arity=4: V=%d F=%d E=%d" % (V, F, E),
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "algorithmic_bytes_per_launch": abytes, "launch_ms": ms, "factor_evals_per_sec": F / (ms * 1e-3),
+            "sum": s, "peak_source": peak_src}
+
+
+def lib_eval_async(ctx):
+    """One full residual sweep; the sum stays on the device until the caller synchronises
+    (rdisgpu_eval itself copies the sum back, so its D2H of 8 bytes rides inside the timing)."""
+    return ctx.eval()
+
+
+def cpu_baseline(spec, pts, cams, x0, budget_s):
+    """The CPU oracle (single-threaded reference-semantics port) on a bounded sample of the same
+    wave: every k-th point component and a few camera components, scaled to the whole wave."""
+    from oracle import oracle_py as O
+    O.build()
+    orc = O.OracleFunction.from_spec(spec)
+    orc.set_x(x0)
+    # calibrate on a handful, then size the sample for ~budget_s
+    probe = pts.subset(range(0, pts.n, max(1, pts.n // 32)))
+    t = orc.solve_cgd_batch(probe.var_off, probe.vids, probe.fac_off, probe.fids, x0[probe.vids], MAXITERS, FTOL)["seconds"]
+    per_pt = t / probe.n
+    cam_probe = cams.subset([0])
+    orc.set_x(x0)
+    t_cam = orc.solve_cgd_batch(cam_probe.var_off, cam_probe.vids, cam_probe.fac_off, cam_probe.fids, x0[cam_probe.vids],
+                                MAXITERS, FTOL)["seconds"]
+    n_cam = int(max(1, min(cams.n, (0.5 * budget_s) // max(t_cam, 1e-3))))
+    n_pt = int(max(32, min(pts.n, (0.5 * budget_s) // max(per_pt, 1e-6))))
+    ps_pt = pts.subset(np.linspace(0, pts.n - 1, n_pt).astype(int))
+    ps_cam = cams.subset(np.linspace(0, cams.n - 1, n_cam).astype(int))
+    orc.set_x(x0)
+    orc.reset_counters()
+    r_pt = orc.solve_cgd_batch(ps_pt.var_off, ps_pt.vids, ps_pt.fac_off, ps_pt.fids, x0[ps_pt.vids], MAXITERS, FTOL)
+    orc.set_x(x0)
+    r_cam = orc.solve_cgd_batch(ps_cam.var_off, ps_cam.vids, ps_cam.fac_off, ps_cam.fids, x0[ps_cam.vids], MAXITERS, FTOL)
+    cnt = orc.counters()
+    wave_s = r_pt["seconds"] * pts.n / ps_pt.n + r_cam["seconds"] * cams.n / ps_cam.n
+    return {"value": (pts.n + cams.n) / wave_s, "unit": "solves/s", "cores": 1, "kind": "port",
+            "sample": "%d of %d point components + %d of %d camera components, scaled to the %d-solve wave "
+                      "(estimated CPU wave time %.1f s)" % (ps_pt.n, pts.n, ps_cam.n, cams.n, pts.n + cams.n, wave_s),
+            "point_solves_per_sec": ps_pt.n / r_pt["seconds"], "camera_solves_per_sec": ps_cam.n / r_cam["seconds"],
+            "factor_eval_calls_per_sec": cnt["factor_eval_calls"] / (r_pt["seconds"] + r_cam["seconds"]),
+            "host_cpus": os.cpu_count(), "oracle": "oracle/liboracle.so (-O2, 1 thread)"}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the CPU implementation of the path on all host threads
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from rdis_b200 import problems  # host-side generators only (numpy); no kernel is launched on this arm
+    from oracle import oracle_py as O
+    O.build()
+    variant = "refnrc" if O.have_refnrc() else "restated"
+    spec = problems.ba_synthetic(seed=SEED)
+    x0 = spec["x0"]
+    pts, cams = problems.ba_point_problems(spec), problems.ba_camera_problems(spec)
+    nthreads = max(1, os.cpu_count() or 1)
+    reps = [O.OracleFunction.from_spec(spec, variant) for _ in range(nthreads)]
+    for r in reps:
+        r.set_x(x0)
+    # bounded sample per step: sized from a probe so that (steps+warmup) steps end within minutes
+    probe = pts.subset(range(0, pts.n, max(1, pts.n // 64)))
+    tp = reps[0].solve_cgd_batch(probe.var_off, probe.vids, probe.fac_off, probe.fids, x0[probe.vids], MAXITERS, FTOL)["seconds"] / probe.n
+    cprobe = cams.subset([0])
+    reps[0].set_x(x0)
+    tc = reps[0].solve_cgd_batch(cprobe.var_off, cprobe.vids, cprobe.fac_off, cprobe.fids, x0[cprobe.vids], MAXITERS, FTOL)["seconds"]
+    total_steps = args.steps + args.warmup
+    budget = min(8.0, 150.0 / max(total_steps, 1))          # seconds of wall clock per step
+    n_cam = int(max(nthreads, min(cams.n, (0.5 * budget * nthreads) // max(tc, 1e-3))))
+    n_cam = min(cams.n, n_cam)
+    n_pt = int(max(nthreads * 8, min(pts.n, (0.5 * budget * nthreads) // max(tp, 1e-6))))
+    n_pt = min(pts.n, n_pt)
+    ps_pt = pts.subset(np.linspace(0, pts.n - 1, n_pt).astype(int))
+    ps_cam = cams.subset(np.linspace(0, cams.n - 1, n_cam).astype(int))
+
+    def step():
+        for r in reps:
+            r.set_x(x0)
+        a = reps[0].solve_cgd_batch(ps_pt.var_off, ps_pt.vids, ps_pt.fac_off, ps_pt.fids, x0[ps_pt.vids], MAXITERS, FTOL, replicas=reps)
+        b = reps[0].solve_cgd_batch(ps_cam.var_off, ps_cam.vids, ps_cam.fac_off, ps_cam.fids, x0[ps_cam.vids], MAXITERS, FTOL, replicas=reps)
+        # whole-wave time at this throughput
+        return a["seconds"] * pts.n / ps_pt.n + b["seconds"] * cams.n / ps_cam.n, a["seconds"] + b["seconds"]
+
+    for _ in range(args.warmup):
+        step()
+    wave, spent = [], 0.0
+    for _ in range(args.steps):
+        w, s = step()
+        wave.append(w)
+        spent += s
+    wave_s = float(np.mean(wave))
+    value = (pts.n + cams.n) / wave_s
+    sample = ("each step: %d of %d point + %d of %d camera components on %d threads (one function replica per thread), "
+              "scaled to the 7825-solve wave" % (ps_pt.n, pts.n, ps_cam.n, cams.n, nthreads))
+    out = {"impl": "reference", "metric": "subspace-solves/sec", "value": value, "unit": "solves/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": wave_s * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "ladybug-49-7776-shaped BA graph (49 cams, 7776 pts, 31843 obs): "
+                                  "7776 point-component + 49 camera-component CGD solves per step",
+                      "ssmaxit": MAXITERS, "ssftol": FTOL, "seed": SEED},
+           "cpu_baseline": {"value": value, "unit": "solves/s", "cores": nthreads,
+                            "kind": "port", "sample": sample,
+                            "driver": "reference minimize_nrc.h (oracle/_ref)" if variant == "refnrc" else "restated NR driver"},
+           "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "cpu_seconds_measured": spent}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

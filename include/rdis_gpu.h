@@ -99,7 +99,8 @@ RDISGPU_API int rdisgpu_add_ba(rdisgpu_ctx* ctx, int64_t F, const int32_t* cam, 
 RDISGPU_API int rdisgpu_finalize(rdisgpu_ctx* ctx);
 
 /* ---- state ---------------------------------------------------------------------------- */
-/* Variable::assign for n variables (vid NULL = 0..n-1), src/Variable.cpp:66-88. */
+/* Variable::assign for n variables (vid NULL = 0..n-1), src/Variable.cpp:66-88.  x (and vid) may be
+ * device pointers: then nothing is copied and the call is asynchronous on the context's stream. */
 RDISGPU_API int rdisgpu_set_x(rdisgpu_ctx* ctx, int64_t n, const int32_t* vid, const double* x);
 RDISGPU_API int rdisgpu_get_x(rdisgpu_ctx* ctx, int64_t n, const int32_t* vid, double* x);
 /* Factors the tree search simplified to a constant (Factor::isAssigned, src/Factor.cpp:110-119):
@@ -133,11 +134,14 @@ RDISGPU_API int rdisgpu_solve_cgd(rdisgpu_ctx* ctx, const rdisgpu_problem* probs
  * (alternating minimisation, RDISOptimizer.cpp:1148-1181): index lists stay resident in HBM. */
 RDISGPU_API int rdisgpu_batch_create(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t nprobs,
                                      rdisgpu_batch** out);
-/* x0 (nullable): concatenated start values in problem order; NULL = current device values.
- * Asynchronous on the context's stream. */
+/* x0 (nullable): concatenated start values in problem order, host (pinned for a truly asynchronous
+ * copy) or device memory; NULL = current device values.  Asynchronous on the context's stream. */
 RDISGPU_API int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiters, double ftol);
 /* Waits, then copies results out (out[i].x may be NULL).  sum_f_end (nullable) = sum of f_end. */
 RDISGPU_API int rdisgpu_batch_fetch(rdisgpu_batch* b, rdisgpu_result* out, double* sum_f_end);
+/* *sum_dev += sum_i f_end[i], computed on the device (sum_dev is device memory): the per-GPU partial of
+ * the global objective, ready for an NCCL all-reduce on the same stream.  Asynchronous. */
+RDISGPU_API int rdisgpu_batch_objective_device(rdisgpu_batch* b, double* sum_dev);
 RDISGPU_API void rdisgpu_batch_destroy(rdisgpu_batch* b);
 /* Kernel launches the last rdisgpu_batch_solve_cgd enqueued (bench.py's gpu_launches). */
 RDISGPU_API int rdisgpu_batch_last_launches(const rdisgpu_batch* b);

@@ -498,6 +498,19 @@ void orc_get_counters(void* h, int64_t* out5) {
 }
 void orc_reset_counters(void* h) { H(h)->fn->counters = Counters(); }
 
+void orc_trace_enable(void* h, int on) {
+  H(h)->fn->trace_on = (on != 0);
+  H(h)->fn->trace.clear();
+}
+int64_t orc_trace_count(void* h) { return (int64_t)H(h)->fn->trace.size(); }
+// record i: returns is_df; x (nv values) and out (1 value, or nv gradient entries) are copied out
+int orc_trace_get(void* h, int64_t i, double* x, double* out) {
+  const auto& t = H(h)->fn->trace[(size_t)i];
+  std::memcpy(x, t.x.data(), t.x.size() * sizeof(double));
+  std::memcpy(out, t.out.data(), t.out.size() * sizeof(double));
+  return t.is_df;
+}
+
 const char* orc_variant() {
 #ifdef ORACLE_USE_REFERENCE_NRC
   return "reference-minimize_nrc.h";

@@ -13,6 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_RESTATED = os.path.join(_HERE, "liboracle.so")
 LIB_REFNRC = os.path.join(_HERE, "_ref", "liboracle_refnrc.so")
+LIB_FMA = os.path.join(_HERE, "liboracle_fma.so")
 
 _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -79,6 +80,11 @@ def _load(path):
                                         _f64p, _f64p, _i32p, C.c_int, vp]
     lib.orc_get_counters.argtypes = [vp, _i64p]
     lib.orc_reset_counters.argtypes = [vp]
+    lib.orc_trace_enable.argtypes = [vp, C.c_int]
+    lib.orc_trace_count.restype = C.c_int64
+    lib.orc_trace_count.argtypes = [vp]
+    lib.orc_trace_get.restype = C.c_int
+    lib.orc_trace_get.argtypes = [vp, C.c_int64, _f64p, _f64p]
     lib.orc_variant.restype = C.c_char_p
     return lib
 
@@ -87,10 +93,15 @@ _LIBS = {}
 
 
 def lib(variant="restated"):
-    path = LIB_RESTATED if variant == "restated" else LIB_REFNRC
+    """variant: 'restated' (own-words NR driver), 'refnrc' (reference's minimize_nrc.h, oracle/_ref),
+    'fma' (restated, compiled with FMA contraction: the perturbation twin)."""
+    path = {"restated": LIB_RESTATED, "refnrc": LIB_REFNRC, "fma": LIB_FMA}[variant]
     if path not in _LIBS:
         if not os.path.exists(path):
-            build()
+            if variant == "fma":
+                subprocess.check_call(["make", "-C", _HERE, "fma"], stdout=subprocess.DEVNULL)
+            else:
+                build()
         _LIBS[path] = _load(path)
     return _LIBS[path]
 
@@ -254,6 +265,19 @@ class OracleFunction:
             secs = self._lib.orc_solve_cgd_batch(self._h, n, var_off, vids, fac_off, fids, x, maxiters, ftol, fe, fi, it,
                                                  1, None)
         return {"x": x, "f_end": fe, "f_init": fi, "iters": it, "seconds": secs}
+
+    def trace(self, on=True):
+        """Start (and clear) / stop recording every SubfunctionFD evaluation of the next solves."""
+        self._lib.orc_trace_enable(self._h, int(on))
+
+    def trace_records(self, nv):
+        """[(is_df, x[nv], out[1 or nv])] of the recorded solve."""
+        recs = []
+        for i in range(self._lib.orc_trace_count(self._h)):
+            x = np.empty(nv); out = np.empty(nv)
+            is_df = self._lib.orc_trace_get(self._h, i, x, out)
+            recs.append((is_df, x, out if is_df else out[:1].copy()))
+        return recs
 
     def counters(self):
         out = np.zeros(5, np.int64)

@@ -638,6 +638,14 @@ class OptimizableFunction {
   std::vector<Factor*> factors;
   std::vector<Numeric> xinit;  // initial state carried by a loaded problem (BundleAdjustmentFunction.h)
   Counters counters;
+  // Optional evaluation trace (test instrumentation, not reference behaviour): every
+  // SubfunctionFD call appends {is_df, assigned point, value or gradient}.
+  struct TraceRec {
+    int is_df;
+    std::vector<Numeric> x, out;
+  };
+  bool trace_on = false;
+  std::vector<TraceRec> trace;
   enum Kind { KIND_NLPF = 0, KIND_BA = 1, KIND_SIMPLESUM = 2 } kind = KIND_NLPF;
   long long ncams = 0, npts = 0;  // BA only
 };
@@ -682,7 +690,15 @@ class CGDSubspaceOptimizer : public SubspaceOptimizer {
     Numeric operator()(const std::vector<Numeric>& x) {  // :124-132
       quickAssignVals(x);
       ++func.counters.f_evals;
-      return func.evalFactors(facs, true);
+      const Numeric r = func.evalFactors(facs, true);
+      if (func.trace_on) {
+        OptimizableFunction::TraceRec t;
+        t.is_df = 0;
+        for (const Variable* v : vars) t.x.push_back(v->eval());
+        t.out.push_back(r);
+        func.trace.push_back(t);
+      }
+      return r;
     }
     void df(const std::vector<Numeric>& x, std::vector<Numeric>& deriv) {  // :135-157
       deriv.assign(vars.size(), 0);
@@ -693,6 +709,13 @@ class CGDSubspaceOptimizer : public SubspaceOptimizer {
       for (size_t i = 0; i < vars.size(); ++i) {
         const Numeric* d = pg.find(vars[i]->getID());
         deriv[i] = (d == nullptr ? 0 : *d);
+      }
+      if (func.trace_on) {
+        OptimizableFunction::TraceRec t;
+        t.is_df = 1;
+        for (const Variable* v : vars) t.x.push_back(v->eval());
+        t.out = deriv;
+        func.trace.push_back(t);
       }
     }
     bool quickAssignVals(const std::vector<Numeric>& xval) {  // :160-184

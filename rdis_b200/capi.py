@@ -21,7 +21,7 @@ EXPORTS = (
     "rdisgpu_set_x", "rdisgpu_get_x", "rdisgpu_set_factor_const",
     "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_factor_grad",
     "rdisgpu_solve_cgd", "rdisgpu_batch_create", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
-    "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches",
+    "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches",
     "rdisgpu_num_vars", "rdisgpu_num_factors", "rdisgpu_device_state", "rdisgpu_launch_count", "rdisgpu_version",
 )
 
@@ -66,6 +66,7 @@ def load_library(path=LIB_PATH):
         "rdisgpu_batch_create": (C.c_int, [vp, C.POINTER(Problem), i64, C.POINTER(vp)]),
         "rdisgpu_batch_solve_cgd": (C.c_int, [vp, vp, C.c_int, dbl]),
         "rdisgpu_batch_fetch": (C.c_int, [vp, C.POINTER(Result), C.POINTER(dbl)]),
+        "rdisgpu_batch_objective_device": (C.c_int, [vp, vp]),
         "rdisgpu_batch_destroy": (None, [vp]),
         "rdisgpu_batch_last_launches": (C.c_int, [vp]),
         "rdisgpu_num_vars": (i64, [vp]),
@@ -215,6 +216,11 @@ class Context:
         self._ck(self._lib.rdisgpu_get_x(self._h, n, _p(v), _p(out)))
         return out
 
+    def set_x_device(self, x_dev_ptr, n, vid_dev_ptr=None):
+        """Asynchronous Variable::assign from device memory (raw pointers)."""
+        self._ck(self._lib.rdisgpu_set_x(self._h, n, C.c_void_p(vid_dev_ptr) if vid_dev_ptr else None,
+                                         C.c_void_p(x_dev_ptr)))
+
     def set_factor_const(self, fid, val, on):
         fid = _arr(fid, np.int64); val = _arr(val, np.float64); on = _arr(on, np.uint8)
         self._ck(self._lib.rdisgpu_set_factor_const(self._h, len(fid), _p(fid), _p(val), _p(on)))
@@ -312,6 +318,10 @@ class Batch:
             out = {}
         out["sum_f_end"] = s.value
         return out
+
+    def objective_device(self, sum_dev_ptr):
+        """*sum_dev += sum of f_end (device-side; asynchronous)."""
+        self.ctx._ck(self._lib.rdisgpu_batch_objective_device(self._h, C.c_void_p(sum_dev_ptr)))
 
     @property
     def last_launches(self):

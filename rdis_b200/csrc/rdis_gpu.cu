@@ -171,6 +171,17 @@ cudaError_t upload(DevBuf<T>& d, const T* h, size_t n, cudaStream_t s) {
   return cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
+// true if `p` is device (or managed) memory this process can read from a kernel
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
 // counting-sort incidence: for each key in [0,K) the list of items with that key, ascending item id
 void build_incidence(int64_t K, const std::vector<int32_t>& key_of_item, std::vector<int32_t>& row,
                      std::vector<int32_t>& items) {
@@ -391,10 +402,20 @@ int rdisgpu_set_x(rdisgpu_ctx* ctx, int64_t n, const int32_t* vid, const double*
   if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "set_x before finalize");
   if (n < 0 || (n > 0 && !x) || (!vid && n > ctx->V)) return ctx->fail(RDISGPU_ERR_ARG, "set_x: bad argument");
   if (n == 0) return RDISGPU_OK;
+  CK(cudaSetDevice(ctx->device));
+  if (is_device_ptr(x)) {
+    // device-resident values (and ids, if given): no copy, no host sync — stays asynchronous
+    if (vid && !is_device_ptr(vid)) return ctx->fail(RDISGPU_ERR_ARG, "set_x: device x needs device (or null) vid");
+    const int threads = 256;
+    const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 65535);
+    scatter_x_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->gv, n, vid, x);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    return RDISGPU_OK;
+  }
   if (vid)
     for (int64_t i = 0; i < n; ++i)
       if (vid[i] < 0 || vid[i] >= ctx->V) return ctx->fail(RDISGPU_ERR_ARG, "set_x: variable id out of range");
-  CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   CK(ctx->s_f64a.ensure((size_t)n));
   CK(cudaMemcpyAsync(ctx->s_f64a.p, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -704,13 +725,14 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
   if (maxiters <= 0) return ctx->fail(RDISGPU_ERR_ARG, "solve: maxiters must be positive");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  if (x0_host && b->total_nv > 0)  // pageable source: staged by the driver before the call returns; pinned: truly async
+  const bool x0_on_device = is_device_ptr(x0_host);
+  if (x0_host && !x0_on_device && b->total_nv > 0)  // pageable source: staged by the driver before the call returns; pinned: truly async
     CK(cudaMemcpyAsync(b->x0.p, x0_host, (size_t)b->total_nv * sizeof(double), cudaMemcpyHostToDevice, s));
   BatchView bv;
   bv.probs = b->probs.p;
   bv.vids = b->vids.p;
   bv.fids = b->fids.p;
-  bv.x0 = x0_host ? b->x0.p : nullptr;
+  bv.x0 = x0_host ? (x0_on_device ? x0_host : b->x0.p) : nullptr;
   bv.xout = b->xout.p;
   bv.res = b->res.p;
   GraphView gv = ctx->gv;
@@ -798,6 +820,18 @@ int rdisgpu_batch_fetch(rdisgpu_batch* b, rdisgpu_result* out, double* sum_f_end
     if (out[p].x) std::memcpy(out[p].x, b->h_x.p + b->h_probs[p].var_off, (size_t)b->h_probs[p].nv * sizeof(double));
   }
   if (sum_f_end) *sum_f_end = tot;
+  return RDISGPU_OK;
+}
+
+int rdisgpu_batch_objective_device(rdisgpu_batch* b, double* sum_dev) {
+  if (!b) return RDISGPU_ERR_ARG;
+  rdisgpu_ctx* ctx = b->ctx;
+  if (!b->solved) return ctx->fail(RDISGPU_ERR_STATE, "batch_objective_device before batch_solve");
+  if (!is_device_ptr(sum_dev)) return ctx->fail(RDISGPU_ERR_ARG, "batch_objective_device: sum_dev must be device memory");
+  CK(cudaSetDevice(ctx->device));
+  sum_f_end_kernel<<<1, 256, 0, ctx->stream>>>(b->res.p, b->nprobs, sum_dev);
+  ++ctx->launches;
+  CK(cudaGetLastError());
   return RDISGPU_OK;
 }
 

@@ -375,6 +375,23 @@ __global__ void __launch_bounds__(128) solve_tile_kernel(GraphView Gv, BatchView
   solve_problem<Ops>(Gv, grp, B, (slot < count) ? order[slot] : -1, maxiters, ftol);
 }
 
+// *out += sum of f_end over the batch (one block, fixed order): the per-GPU partial of the global
+// objective that is all-reduced across ranks.
+__global__ void sum_f_end_kernel(const ResultRec* res, int64_t n, double* out) {
+  __shared__ double wsum[8];
+  double t = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) t += res[i].f_end;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tt = wsum[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) tt += wsum[w];
+    *out += tt;
+  }
+}
+
 template <class Ops>
 __global__ void solve_block_kernel(GraphView Gv, BatchView B, const int32_t* order, int count, int maxiters,
                                    double ftol) {

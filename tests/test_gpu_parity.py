@@ -101,27 +101,102 @@ def _check_solves(r, o, tol=1e-6):
     return rel.max()
 
 
-def test_solve_ba_point_and_camera_blocks(gpu, oracle_mod):
+def _oracle_batch(oracle_mod, spec, ps, x0, maxiters, variant="restated"):
+    orc = oracle_mod.OracleFunction.from_spec(spec, variant)
+    orc.set_x(x0)
+    return orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[ps.vids], maxiters, 3e-8)
+
+
+def _check_committed_state(ctx, spec, ps, x0, r):
+    """bit-exact bookkeeping: returned x == committed device state; nothing else moved; the
+    reported objective is the objective at the returned point; never worse than the start."""
+    xg = ctx.get_x()
+    assert np.array_equal(xg[ps.vids], r["x"])
+    mask = np.ones(spec["V"], bool); mask[ps.vids] = False
+    assert np.array_equal(xg[mask], x0[mask])
+    tot = ctx.eval(ps.fids)
+    assert abs(tot - r["f_end"].sum()) <= 1e-9 * abs(tot)
+    assert (r["f_end"] <= r["f_init"]).all()
+    assert (r["x"] >= spec["lb"][ps.vids]).all() and (r["x"] <= spec["ub"][ps.vids]).all()
+
+
+def test_solve_ba_point_blocks(gpu, oracle_mod):
+    """Sibling batch of 3-variable point components (sub-warp tiles)."""
     from rdis_b200 import Context, problems as P
     spec = _ba_small(P)
     x0 = spec["x0"]
-    ctx = Context.from_spec(spec); orc = oracle_mod.OracleFunction.from_spec(spec)
-    for ps in (P.ba_point_problems(spec), P.ba_camera_problems(spec)):
-        ctx.set_x(x0); orc.set_x(x0)
-        x0c = x0[ps.vids]
-        r = ctx.solve_cgd(ps, x0c, 25, 3e-8)
-        o = orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0c, 25, 3e-8)
-        worst = _check_solves(r, o)
-        # committed state == returned x, untouched elsewhere (bit-exact bookkeeping)
-        xg = ctx.get_x()
-        assert np.array_equal(xg[ps.vids], r["x"])
-        mask = np.ones(spec["V"], bool); mask[ps.vids] = False
-        assert np.array_equal(xg[mask], x0[mask])
-        # the objective at the returned point is what was reported
-        tot = ctx.eval(ps.fids)
-        assert abs(tot - r["f_end"].sum()) <= 1e-9 * abs(tot)
-        assert (r["f_end"] <= r["f_init"]).all()
-        print("worst rel f_end diff", worst)
+    ps = P.ba_point_problems(spec)
+    ctx = Context.from_spec(spec)
+    ctx.set_x(x0)
+    r = ctx.solve_cgd(ps, x0[ps.vids], 25, 3e-8)
+    o = _oracle_batch(oracle_mod, spec, ps, x0, 25)
+    worst = _check_solves(r, o, 1e-6)
+    _check_committed_state(ctx, spec, ps, x0, r)
+    print("point blocks: worst rel f_end diff %.3e, iters equal on %d/%d" % (worst, (r["iters"] == o["iters"]).sum(), ps.n))
+
+
+def test_solve_ba_camera_blocks(gpu, oracle_mod):
+    """9-variable camera components (one CTA each).  These solves are ill-conditioned and stop at
+    maxiters unconverged, so the reference's own result moves by up to ~1e-2 relative when its
+    rounding is perturbed (FMA contraction of the same source; toggling its 1e-12 change filter).
+    Contract: (1) one CG iteration from the same start agrees to 1e-6; (2) at 25 iterations,
+    problems on which the oracle agrees with its perturbation twin to 1e-8 must match the GPU to
+    1e-6; (3) on the others the GPU must land inside 10x the oracle's own spread."""
+    from rdis_b200 import Context, problems as P
+    spec = _ba_small(P)
+    x0 = spec["x0"]
+    ps = P.ba_camera_problems(spec)
+    ctx = Context.from_spec(spec)
+    ctx.set_x(x0)
+    r1 = ctx.solve_cgd(ps, x0[ps.vids], 1, 3e-8)
+    o1 = _oracle_batch(oracle_mod, spec, ps, x0, 1)
+    _check_solves(r1, o1, 1e-6)
+    ctx.set_x(x0)
+    r = ctx.solve_cgd(ps, x0[ps.vids], 25, 3e-8)
+    _check_committed_state(ctx, spec, ps, x0, r)
+    o = _oracle_batch(oracle_mod, spec, ps, x0, 25)
+    try:
+        of = _oracle_batch(oracle_mod, spec, ps, x0, 25, "fma")
+    except Exception as e:  # host CPU without FMA
+        pytest.skip("perturbation twin unavailable: %s" % e)
+    spread = _relerr(of["f_end"], o["f_end"], 1e-12)
+    rel = _relerr(r["f_end"], o["f_end"], 1e-12)
+    stable = spread <= 1e-8
+    print("camera blocks: oracle-vs-twin spread", spread, "gpu-vs-oracle", rel)
+    assert (rel[stable] <= 1e-6).all()
+    assert (rel[~stable] <= np.maximum(10 * spread[~stable], 1e-6)).all()
+
+
+def test_pointwise_parity_along_reference_trajectory(gpu, oracle_mod):
+    """Replay every point the ORACLE's solve evaluated (its whole CG / line-search trajectory) on the
+    GPU through the C-ABI: objective to 1e-13 relative and gradient to 1e-11 of its scale at each of
+    them.  With the state machine proven bit-identical to the reference driver on equal inputs
+    (tests/test_machine_harness.py), rounding-level evaluation noise is the only thing that can
+    separate a GPU solve from a reference solve."""
+    from rdis_b200 import Context, problems as P
+    spec = _ba_small(P)
+    x0 = spec["x0"]
+    for ps in (P.ba_camera_problems(spec).subset([1]), P.ba_point_problems(spec).subset([5])):
+        orc = oracle_mod.OracleFunction.from_spec(spec)
+        orc.set_x(x0)
+        orc.trace(True)
+        orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[ps.vids], 25, 3e-8)
+        recs = orc.trace_records(len(ps.vids))
+        orc.trace(False)
+        assert len(recs) > 20
+        ctx = Context.from_spec(spec)
+        ctx.set_x(x0)
+        worst_f = worst_g = 0.0
+        for is_df, x, out in recs[:: max(1, len(recs) // 150)]:
+            ctx.set_x(x, ps.vids)
+            if is_df:
+                g = ctx.grad(ps.fids, ps.vids)
+                worst_g = max(worst_g, np.abs(g - out).max() / np.abs(out).max())
+            else:
+                f = ctx.eval(ps.fids)
+                worst_f = max(worst_f, abs(f - out[0]) / abs(out[0]))
+        print("trajectory replay: worst rel f %.2e, worst grad %.2e" % (worst_f, worst_g))
+        assert worst_f <= 1e-13 and worst_g <= 1e-11
 
 
 def test_solve_full_problem_grid(gpu, oracle_mod):
