@@ -315,6 +315,82 @@ void* orc_make_sinusoid(int64_t treeHeight, int64_t branches, int64_t maxArity, 
   return h;
 }
 
+// The ten known-answer functions of the reference's debug test (src/main.cpp:103-135), built from
+// SimpleSumFactors as src/OptimizableFunctionGenerator.cpp:215-543 builds them.  Each is described
+// here as a table: default domain, per-variable domain overrides, and per factor
+// {constant, exponent, coefficient, {variable, term exponent, term coefficient}...}.
+// Returns nullptr for idx outside 0..9; *expected receives the minimum main.cpp asserts (tol 1e-5).
+void* orc_make_debug_function(int idx, double* expected) {
+  struct T { int v; double e, a; };
+  struct FDesc { double k, e, c; std::vector<T> terms; };
+  struct Desc { double lo, hi; int nvars; std::vector<FDesc> fs; double want; std::vector<std::pair<int, Domain>> over; };
+  auto lin = [](std::initializer_list<int> vs) {  // plain sum of variables: k=0, e=1, c=1
+    FDesc f{0, 1, 1, {}};
+    for (int v : vs) f.terms.push_back(T{v, 1, 1});
+    return f;
+  };
+  auto with_exp = [](FDesc f, double e) { f.e = e; return f; };
+  Desc d;
+  switch (idx) {
+    case 0:  // makeSimplePoly :215-236
+      d = Desc{-3, 4, 3, {lin({0, 1}), lin({0, 2})}, -12, {}};
+      break;
+    case 1:  // makeNonDecompPoly :266-288
+      d = Desc{-2, 4, 3, {lin({0, 1}), lin({0, 2}), lin({1, 2})}, -12, {}};
+      break;
+    case 2:  // makeSetToConstFactor :291-296 (third factor raised to the power 0)
+      d = Desc{-2, 4, 3, {lin({0, 1}), lin({0, 2}), with_exp(lin({1, 2}), 0)}, -7, {}};
+      break;
+    case 3:  // makeSetToConstFactor2 :299-322
+      d = Desc{1, 4, 3, {lin({0, 1}), lin({0, 2}), FDesc{0, 1, 1, {T{1, -6, 1}, T{2, -6, 1}}}}, 5.01399, {}};
+      break;
+    case 4:  // make2ComponentPoly :387-412
+      d = Desc{1, 4, 6, {lin({0, 2}), lin({0, 3}), lin({1, 4}), lin({1, 5})}, 8, {}};
+      break;
+    case 5:  // makeTreePoly :325-349
+      d = Desc{1, 4, 5, {lin({0, 1}), lin({0, 2}), lin({1, 3}), lin({2, 4})}, 8, {}};
+      break;
+    case 6:  // makeMinStateWrongPoly :239-262
+      d = Desc{1, 4, 2, {FDesc{0, 2, -1, {T{0, 1, 1}, T{1, 1, 1}}}}, -3.0625, {{0, Domain{-2, 1}}, {1, Domain{0.25, 0.5}}}};
+      break;
+    case 7:  // makeCrossPoly :478-512
+      d = Desc{1, 1.3, 8, {lin({0, 2, 4, 6}), lin({1, 3, 5, 7}), lin({0, 2, 5, 7}), lin({1, 3, 4, 6})}, 16, {}};
+      break;
+    case 8:  // makePowellsFunction :515-549
+      d = Desc{-5, 5, 4,
+               {FDesc{0, 2, 0.5, {T{0, 1, 1}, T{1, 1, 10}}}, FDesc{0, 2, 5.0 * 0.5, {T{2, 1, 1}, T{3, 1, -1}}},
+                FDesc{0, 4, 0.5, {T{1, 1, 1}, T{2, 1, -2}}}, FDesc{0, 4, 10.0 * 0.5, {T{0, 1, 1}, T{3, 1, -1}}}},
+               0, {}};
+      break;
+    case 9: {  // makeTreePoly3 :416-474: fourteen squared pair sums
+      const int pairs[14][2] = {{0, 1}, {0, 2}, {0, 3}, {0, 4}, {1, 2}, {1, 3}, {1, 4}, {2, 5}, {2, 6}, {3, 7}, {3, 8}, {4, 9}, {4, 10}, {0, 5}};
+      d = Desc{-2, 2, 11, {}, 0, {}};
+      for (auto& p : pairs) d.fs.push_back(with_exp(lin({p[0], p[1]}), 2));
+      break;
+    }
+    default:
+      return nullptr;
+  }
+  Handle* h = new Handle();
+  OptimizableFunction& fn = *h->fn;
+  fn.kind = OptimizableFunction::KIND_SIMPLESUM;
+  for (int v = 0; v < d.nvars; ++v) {
+    Domain dom{d.lo, d.hi};
+    for (auto& o : d.over)
+      if (o.first == v) dom = o.second;
+    Variable* var = fn.addVariable(dom);
+    var->samp_lo = dom.lo;
+    var->samp_hi = dom.hi;
+  }
+  for (size_t j = 0; j < d.fs.size(); ++j) {
+    auto* f = new SimpleSumFactor((FactorID)j, d.fs[j].k, d.fs[j].e, d.fs[j].c);
+    fn.factors.push_back(f);
+    for (const T& t : d.fs[j].terms) f->addVariable(fn.variables[t.v], t.e, t.a);
+  }
+  if (expected) *expected = d.want;
+  return h;
+}
+
 void orc_destroy(void* h) { delete H(h); }
 
 int64_t orc_num_vars(void* h) { return (int64_t)H(h)->fn->variables.size(); }

@@ -253,19 +253,5 @@ def full_problem(spec):
 
 
 def shard_problems(ps, rank, world):
-    """Component shard of rank `rank`: greedy longest-processing-time packing by |factors|*|vars|
-    (deterministic; every rank computes the same assignment)."""
-    nv = np.diff(ps.var_off); nf = np.diff(ps.fac_off)
-    cost = (nf * np.maximum(nv, 1)).astype(np.int64)
-    order = np.argsort(-cost, kind="stable")
-    load = np.zeros(world, dtype=np.int64)
-    owner = np.empty(ps.n, dtype=np.int64)
-    if ps.n > 4 * world and np.all(cost[order[:1]] * ps.n < 50 * cost.sum()):
-        # many comparable components: round-robin over the cost-sorted list is LPT-equivalent and O(n)
-        owner[order] = np.arange(ps.n) % world
-    else:
-        for i in order:
-            r = int(np.argmin(load))
-            owner[i] = r
-            load[r] += cost[i]
-    return np.nonzero(owner == rank)[0]
+    from .shard import shard_problems as _impl
+    return _impl(ps, rank, world)
