@@ -228,7 +228,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     e2e_value = world * n_solves * e2e_steps / t_e2e
-    h2d = 8 * spec["V"] + sum(4 * len(p.vids) + 8 * len(p.fids) + 8 * len(p.vids) + 24 * p.n for p in (pts, cams))
+    # state + per batch: one index blob (24 B ProblemDesc + 3 x 4 B order lists + 12 B warp task per problem,
+    # 4 B per variable id and factor id) + start values; back: 32 B result record per problem + final values
+    h2d = 8 * spec["V"] + sum(4 * len(p.vids) + 4 * len(p.fids) + 8 * len(p.vids) + 48 * p.n for p in (pts, cams))
     d2h = sum(8 * len(p.vids) + 32 * p.n for p in (pts, cams))
 
     out = None
@@ -245,18 +247,19 @@ def run_ours(args):
             "config": {"workload": "ladybug-49-7776-shaped BA graph (49 cams, 7776 pts, 31843 obs) per GPU: "
                                    "7776 point-component + 49 camera-component CGD solves per step",
                        "ssmaxit": MAXITERS, "ssftol": FTOL, "parallelism": "component-shard x%d" % world,
-                       "l2": "flushed between steps (256 MiB memset, untimed)", "seed": SEED},
+                       "l2": "flushed between steps (256 MiB memset, untimed)", "seed": SEED,
+                       "mapping": {"points": b_pts.info(), "cameras": b_cams.info()}},
             "residual_evals_per_sec": resid_evals_per_s,
             "objective_after_step": objective,
-            "kernel_ms": {"solve_tile_kernel(points)": float(ms_pts.mean()), "solve_block_kernel(cameras)": float(ms_cams.mean())},
+            "kernel_ms": {"solve_ba_points_kernel": float(ms_pts.mean()), "solve_ba_cameras_kernel": float(ms_cams.mean())},
             "wall_s_timed_region": t_wall,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "objective": obj_e2e},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "solve_tile_kernel<BaOps,*> (point components)" if dom_is_pts
-                         else "solve_block_kernel<BaOps> (camera components)",
+                         "traffic": None, "kernel": "solve_ba_points_kernel (point components)" if dom_is_pts
+                         else "solve_ba_cameras_kernel (camera components)",
                          "algorithmic_bytes_per_launch": abytes, "launch_ms": float(dom_ms), "peak_source": peak_src,
                          "note": "working set 1.4 MB: L2-resident, FP64/latency bound; see roofline_sweep for the HBM-bound kernel"},
         }

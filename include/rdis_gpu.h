@@ -80,6 +80,9 @@ RDISGPU_API const char* rdisgpu_last_error(const rdisgpu_ctx* ctx); /* ctx may b
 /* All work of this context is enqueued on `cuda_stream` (a cudaStream_t; NULL = default). */
 RDISGPU_API int rdisgpu_set_stream(rdisgpu_ctx* ctx, void* cuda_stream);
 RDISGPU_API int rdisgpu_synchronize(rdisgpu_ctx* ctx);
+/* Tuning / test switches.  "generic_only" != 0: batches created afterwards bypass the bundle-adjustment
+ * block kernels and run every problem through the generic tile / CTA / grid kernels. */
+RDISGPU_API int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value);
 
 /* ---- function definition (replaces the OptimizableFunction / Factor object graph) ------ */
 /* Variables 0..V-1 with their single-interval domains (VariableDomain, src/VariableDomain.cpp:130-163). */
@@ -130,10 +133,22 @@ RDISGPU_API int rdisgpu_factor_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t*
 RDISGPU_API int rdisgpu_solve_cgd(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t nprobs, int maxiters,
                                   double ftol, rdisgpu_result* out);
 
+/* The same with the batch described by packed (CSR) lists — what a caller that holds a whole wave of
+ * sibling components naturally has: problem p owns vids[var_off[p]..var_off[p+1]) and
+ * fids[fac_off[p]..fac_off[p+1]).  x0 (nullable = current device values) and x_out (nullable) are
+ * concatenated in problem order; the per-problem outputs (each nullable) have nprobs entries.
+ * All buffers are host memory; index lists, start values and results cross PCIe once each.        */
+RDISGPU_API int rdisgpu_solve_cgd_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_off, const int32_t* vids,
+                                      const int64_t* fac_off, const int64_t* fids, const double* x0, int maxiters,
+                                      double ftol, double* x_out, double* f_init, double* f_end, int32_t* iters,
+                                      int32_t* status, int64_t* n_feval, int64_t* n_geval);
+
 /* The same in three steps, for callers that revisit one component structure many times
  * (alternating minimisation, RDISOptimizer.cpp:1148-1181): index lists stay resident in HBM. */
 RDISGPU_API int rdisgpu_batch_create(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t nprobs,
                                      rdisgpu_batch** out);
+RDISGPU_API int rdisgpu_batch_create_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_off, const int32_t* vids,
+                                         const int64_t* fac_off, const int64_t* fids, rdisgpu_batch** out);
 /* x0 (nullable): concatenated start values in problem order, host (pinned for a truly asynchronous
  * copy) or device memory; NULL = current device values.  Asynchronous on the context's stream. */
 RDISGPU_API int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiters, double ftol);
@@ -143,6 +158,10 @@ RDISGPU_API int rdisgpu_batch_fetch(rdisgpu_batch* b, rdisgpu_result* out, doubl
  * the global objective, ready for an NCCL all-reduce on the same stream.  Asynchronous. */
 RDISGPU_API int rdisgpu_batch_objective_device(rdisgpu_batch* b, double* sum_dev);
 RDISGPU_API void rdisgpu_batch_destroy(rdisgpu_batch* b);
+/* How the batch was mapped: out = {nprobs, point-block warps, camera blocks, cluster size, threads per
+ * CTA of the camera kernel, problems on the generic kernels, max observations of a camera block,
+ * launches of the last solve}. */
+RDISGPU_API int rdisgpu_batch_info(const rdisgpu_batch* b, int32_t out[8]);
 /* Kernel launches the last rdisgpu_batch_solve_cgd enqueued (bench.py's gpu_launches). */
 RDISGPU_API int rdisgpu_batch_last_launches(const rdisgpu_batch* b);
 

@@ -16,11 +16,11 @@ DONE_NAMES = ("ftol", "gtol", "gg_zero", "maxiters", "dbrent_itmax", "empty", "n
 
 # every symbol include/rdis_gpu.h declares (tests check the library exports all of them)
 EXPORTS = (
-    "rdisgpu_create", "rdisgpu_destroy", "rdisgpu_last_error", "rdisgpu_set_stream", "rdisgpu_synchronize",
+    "rdisgpu_create", "rdisgpu_destroy", "rdisgpu_last_error", "rdisgpu_set_stream", "rdisgpu_synchronize", "rdisgpu_set_option",
     "rdisgpu_set_vars", "rdisgpu_add_nlpf", "rdisgpu_add_ba", "rdisgpu_finalize",
     "rdisgpu_set_x", "rdisgpu_get_x", "rdisgpu_set_factor_const",
     "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_factor_grad",
-    "rdisgpu_solve_cgd", "rdisgpu_batch_create", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
+    "rdisgpu_solve_cgd", "rdisgpu_solve_cgd_csr", "rdisgpu_batch_create", "rdisgpu_batch_create_csr", "rdisgpu_batch_info", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
     "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches",
     "rdisgpu_num_vars", "rdisgpu_num_factors", "rdisgpu_device_state", "rdisgpu_launch_count", "rdisgpu_version",
 )
@@ -52,6 +52,7 @@ def load_library(path=LIB_PATH):
         "rdisgpu_last_error": (C.c_char_p, [vp]),
         "rdisgpu_set_stream": (C.c_int, [vp, vp]),
         "rdisgpu_synchronize": (C.c_int, [vp]),
+        "rdisgpu_set_option": (C.c_int, [vp, C.c_char_p, i64]),
         "rdisgpu_set_vars": (C.c_int, [vp, i64, vp, vp]),
         "rdisgpu_add_nlpf": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
         "rdisgpu_add_ba": (C.c_int, [vp, i64, vp, vp, vp, i32, i32]),
@@ -64,6 +65,9 @@ def load_library(path=LIB_PATH):
         "rdisgpu_factor_grad": (C.c_int, [vp, i64, vp, i32, vp]),
         "rdisgpu_solve_cgd": (C.c_int, [vp, C.POINTER(Problem), i64, C.c_int, dbl, C.POINTER(Result)]),
         "rdisgpu_batch_create": (C.c_int, [vp, C.POINTER(Problem), i64, C.POINTER(vp)]),
+        "rdisgpu_batch_create_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, C.POINTER(vp)]),
+        "rdisgpu_solve_cgd_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, C.c_int, dbl, vp, vp, vp, vp, vp, vp, vp]),
+        "rdisgpu_batch_info": (C.c_int, [vp, vp]),
         "rdisgpu_batch_solve_cgd": (C.c_int, [vp, vp, C.c_int, dbl]),
         "rdisgpu_batch_fetch": (C.c_int, [vp, C.POINTER(Result), C.POINTER(dbl)]),
         "rdisgpu_batch_objective_device": (C.c_int, [vp, vp]),
@@ -191,6 +195,9 @@ class Context:
     def synchronize(self):
         self._ck(self._lib.rdisgpu_synchronize(self._h))
 
+    def set_option(self, name, value):
+        self._ck(self._lib.rdisgpu_set_option(self._h, name.encode(), int(value)))
+
     @property
     def V(self):
         return self._lib.rdisgpu_num_vars(self._h)
@@ -255,9 +262,21 @@ class Context:
 
     # ---- solves ----------------------------------------------------------------------
     def solve_cgd(self, problems, x0=None, maxiters=25, ftol=3e-8):
-        """rdisgpu_solve_cgd: host buffers in, host buffers out.
+        """rdisgpu_solve_cgd_csr: host buffers in, host buffers out, one C call for the whole batch.
         problems: ProblemSet; x0: concatenated start values or None (use device state).
         Returns dict(x, f_init, f_end, iters, status, n_feval, n_geval)."""
+        ps = problems
+        x0a = None if x0 is None else _arr(x0, np.float64)
+        n = ps.n
+        out = {"x": np.empty(len(ps.vids)), "f_init": np.empty(n), "f_end": np.empty(n), "iters": np.empty(n, np.int32),
+               "status": np.empty(n, np.int32), "n_feval": np.empty(n, np.int64), "n_geval": np.empty(n, np.int64)}
+        self._ck(self._lib.rdisgpu_solve_cgd_csr(self._h, n, _p(ps.var_off), _p(ps.vids), _p(ps.fac_off), _p(ps.fids), _p(x0a),
+                                                 maxiters, ftol, _p(out["x"]), _p(out["f_init"]), _p(out["f_end"]),
+                                                 _p(out["iters"]), _p(out["status"]), _p(out["n_feval"]), _p(out["n_geval"])))
+        return out
+
+    def solve_cgd_structs(self, problems, x0=None, maxiters=25, ftol=3e-8):
+        """rdisgpu_solve_cgd (array of rdisgpu_problem / rdisgpu_result structs): same results."""
         ps = problems
         x0a = None if x0 is None else _arr(x0, np.float64)
         parr = ps.c_array(x0a)
@@ -288,8 +307,8 @@ class Batch:
         self.ps = problems
         self._lib = ctx._lib
         h = C.c_void_p()
-        parr = problems.c_array(None)
-        ctx._ck(self._lib.rdisgpu_batch_create(ctx._h, parr, problems.n, C.byref(h)))
+        ctx._ck(self._lib.rdisgpu_batch_create_csr(ctx._h, problems.n, _p(problems.var_off), _p(problems.vids),
+                                                   _p(problems.fac_off), _p(problems.fids), C.byref(h)))
         self._h = h
         self._rarr = (Result * problems.n)()
         self._xout = np.empty(len(problems.vids))
@@ -322,6 +341,12 @@ class Batch:
     def objective_device(self, sum_dev_ptr):
         """*sum_dev += sum of f_end (device-side; asynchronous)."""
         self.ctx._ck(self._lib.rdisgpu_batch_objective_device(self._h, C.c_void_p(sum_dev_ptr)))
+
+    def info(self):
+        out = np.zeros(8, np.int32)
+        self.ctx._ck(self._lib.rdisgpu_batch_info(self._h, _p(out)))
+        return dict(zip(("nprobs", "point_warps", "camera_blocks", "cluster_size", "camera_threads", "generic_problems",
+                         "camera_nf_max", "last_launches"), out.tolist()))
 
     @property
     def last_launches(self):

@@ -1,0 +1,524 @@
+// ba_block_kernels.cuh — register / shared-memory resident subspace solves for the two component
+// shapes the recursive decomposer produces on a bundle-adjustment graph, where whole variable
+// blocks are chosen together (src/RDISOptimizer.cpp:464-487):
+//
+//   point block    vars = the 3 coordinates of ONE point, factors = (some of) its observations,
+//                  at most 32 of them (ladybug: 2..29).          -> solve_ba_points_kernel
+//   camera block   vars = the 9 parameters of ONE camera, factors = (some of) its observations
+//                  (ladybug: 361..906).                          -> solve_ba_cameras_kernel
+//
+// What is staged where for the life of a solve (nothing but the final commit touches HBM):
+//   point block    one lane per observation (G = 1..32 lanes per problem, 32/G problems per warp).
+//                  The lane keeps its observation's FROZEN variable block in registers — the
+//                  camera's rotation already reduced to axis / angle / sin / cos, translation,
+//                  intrinsics, the pixel — and every lane keeps a replica of the problem's own
+//                  state (p, xi, g, h, domain: 3 each).  Reductions are warp shuffles.
+//   camera block   a thread-block CLUSTER of C CTAs on C SMs per problem (C*T threads >= #observations
+//                  where possible): a thread keeps its observation's frozen point + pixel in
+//                  registers, every CTA keeps a replica of the camera state (p, xi, g, h, domain:
+//                  9 each) in shared memory, and the per-evaluation all-reduce goes warp shuffle ->
+//                  distributed-shared-memory stores into every CTA of the cluster -> one cluster
+//                  barrier -> fixed-order fold.  The FP64 pipe of one SM (measured 58 DFMA/clk)
+//                  is the per-evaluation bound of a camera block, hence the spread over C SMs.
+//
+// Semantics are those of solve_problem (solve_kernels.cuh) — same CgdMachine, same factor
+// arithmetic (BaOps), same commit rules.  The point kernel folds objective sums with the same shuffle
+// trees as the generic tile path and the gradient in ascending factor id; the camera kernel folds its
+// sums in a different (tree) order.  Both agree with the generic path to rounding (FMA contraction
+// is decided per compilation context, so not to the bit).
+// Eligibility is decided on the host (rdis_gpu.cu: classify_ba_blocks); everything else goes
+// through the generic kernels.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "solve_kernels.cuh"
+
+namespace rdisgpu {
+
+__device__ __forceinline__ double qnan_f64() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// ------------------------------------------------------------------------------------------
+// point blocks
+// ------------------------------------------------------------------------------------------
+// G (lanes per problem) is a run-time value: every warp of the launch runs the same code whatever its
+// size class, which keeps the instruction working set to one copy of the solve loop.
+struct TileRt {
+  unsigned mask;
+  int r, G;
+  __device__ TileRt(int lg) {
+    const int lane = threadIdx.x & 31;
+    G = 1 << lg;
+    r = lane & (G - 1);
+    mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  }
+  __device__ __forceinline__ void sum2(double& a, double& b) const {
+    for (int o = G >> 1; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(mask, a, o);
+      b += __shfl_xor_sync(mask, b, o);
+    }
+  }
+  __device__ __forceinline__ void sum2max(double& a, double& b, double& mx) const {
+    for (int o = G >> 1; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(mask, a, o);
+      b += __shfl_xor_sync(mask, b, o);
+      const double om = __shfl_xor_sync(mask, mx, o);
+      mx = (om > mx) ? om : mx;
+    }
+  }
+};
+
+__device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const BatchView& B, int lg, int pidx, int maxiters,
+                                                    double ftol) {
+  const TileRt grp(lg);
+  const int r = grp.r;
+  const int G = grp.G;
+  const bool run = (pidx >= 0);
+  ProblemDesc P;
+  P.var_off = 0; P.fac_off = 0; P.nv = 0; P.nf = 0;
+  if (run) P = B.probs[pidx];
+  const int nf = P.nf;
+  const int32_t v0 = run ? B.vids[P.var_off] : 0;
+
+  // ---- the problem's own state, replicated in every lane of the tile ----
+  double p[3], xi[3], g[3], h[3], xs[3];
+  double2 dom[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    double xv = 0.0;
+    if (run) xv = (B.x0 != nullptr) ? B.x0[P.var_off + j] : Gv.xbd[v0 + j].x;
+    p[j] = xs[j] = xv;
+    xi[j] = 0.0;  // direction 0: evaluated clamped (quickAssignVals, CGD.cpp:33)
+    g[j] = h[j] = 0.0;
+    dom[j] = run ? __ldg(&Gv.dom[v0 + j]) : make_double2(0.0, 0.0);
+  }
+
+  // ---- this lane's observation: frozen camera block staged once ----
+  const bool have = run && (r < nf);
+  double x[12];
+  double2 ob = make_double2(0.0, 0.0);
+  BaOps::Fwd m;
+  bool fc_on = false;
+  double fc_val = 0.0;
+#pragma unroll
+  for (int s = 0; s < 12; ++s) x[s] = 0.0;
+  m.a0 = m.a1 = m.a2 = m.theta = m.s = 0.0; m.c = 1.0;
+  if (have) {
+    const int32_t fid = B.fids[P.fac_off + r];
+    const int32_t cam = __ldg(&Gv.cam[fid]);
+    ob = __ldg(&Gv.obs[fid]);
+#pragma unroll
+    for (int s = 0; s < 9; ++s) x[s] = Gv.xbd[9 * cam + s].x;  // frozen: read as stored, never clamped
+    BaOps::rotation(x[0], x[1], x[2], m);
+    if (Gv.fconst_on != nullptr && Gv.fconst_on[fid]) {
+      fc_on = true;
+      fc_val = Gv.fconst_val[fid];
+    }
+  }
+
+  CgdMachine mc;
+  mc.start(maxiters, ftol);
+  if (!run) mc.req = REQ_DONE;
+  double f_init = 0.0;
+
+  // Every iteration of this loop is one objective evaluation for every unfinished problem of the
+  // warp.  The evaluation and all shuffles run CONVERGED with the full-warp mask (xor / indexed
+  // shuffles below width G never leave a tile), whatever phase each problem's state machine is in;
+  // only the scalar state-machine step at the end diverges between the tiles of a warp.
+  const unsigned kFull = 0xffffffffu;
+  while (true) {
+    const bool fin = mc.done();
+    if (__all_sync(kFull, fin)) break;
+    const int kind = fin ? (int)REQ_DONE : mc.req;  // REQ_INIT_GRAD, REQ_VALUE, REQ_VALUE_SLOPE or REQ_GRADIENT
+    const bool along = (kind == REQ_VALUE) || (kind == REQ_VALUE_SLOPE);
+    const bool grad_kind = (kind == REQ_INIT_GRAD) || (kind == REQ_GRADIENT);
+    const bool want_g = (kind == REQ_VALUE_SLOPE) || grad_kind;
+    const bool live = have && !fin;
+    const double alpha = mc.alpha;
+    double fv = 0.0, g9 = 0.0, g10 = 0.0, g11 = 0.0;
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) x[9 + j] = clamp_to_domain(along ? (p[j] + alpha * xi[j]) : p[j], dom[j]);
+      fv = BaOps::project(x, ob, m);
+      if (want_g) {
+        double gq[12];
+        BaOps::partials(x, m, gq);
+        g9 = gq[9]; g10 = gq[10]; g11 = gq[11];
+      }
+      if (fc_on) fv = fc_val;  // Factor::eval of an assigned-constant factor, src/Factor.cpp:110-119
+    }
+
+    // SubfunctionFD::operator() + Df1dim::df: f and the directional derivative
+    double fs = 0.0, ss = 0.0;
+    if (live) {
+      double sl = 0.0;
+      if (kind == REQ_VALUE_SLOPE) {
+        if (xi[0] != 0.0) sl += g9 * xi[0];
+        if (xi[1] != 0.0) sl += g10 * xi[1];
+        if (xi[2] != 0.0) sl += g11 * xi[2];
+      }
+      fs += fv;
+      ss += sl;
+    }
+    for (int o = G >> 1; o > 0; o >>= 1) {
+      fs += __shfl_xor_sync(kFull, fs, o);
+      ss += __shfl_xor_sync(kFull, ss, o);
+    }
+
+    // full gradient (some problem of the warp asked for one): per variable, the incident factors'
+    // partials folded in ascending factor id (productGradient's accumulation order,
+    // src/State.h:157-194), then the Polak-Ribiere scalars of minimize_nrc.h:654-673
+    double gr[3] = {0.0, 0.0, 0.0};
+    double gg = 0.0, dgg = 0.0, tnum = 0.0;
+    if (__any_sync(kFull, grad_kind)) {
+      gr[0] = __shfl_sync(kFull, g9, 0, G);
+      gr[1] = __shfl_sync(kFull, g10, 0, G);
+      gr[2] = __shfl_sync(kFull, g11, 0, G);
+      for (int k = 1; k < G; ++k) {
+        const double b0 = __shfl_sync(kFull, g9, k, G), b1 = __shfl_sync(kFull, g10, k, G), b2 = __shfl_sync(kFull, g11, k, G);
+        if (k < nf) {
+          gr[0] = gr[0] + b0; gr[1] = gr[1] + b1; gr[2] = gr[2] + b2;
+        }
+      }
+      if (kind == REQ_GRADIENT) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if ((j & (G - 1)) == r) {  // the lane that owns variable j in the tile partition
+            const double pj = fabs(p[j]);
+            const double t = fabs(gr[j]) * ((pj < 1.0) ? 1.0 : pj);
+            tnum = (t > tnum) ? t : tnum;
+            gg += g[j] * g[j];
+            dgg += (gr[j] + g[j]) * gr[j];
+          }
+        }
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) {
+        gg += __shfl_xor_sync(kFull, gg, o);
+        dgg += __shfl_xor_sync(kFull, dgg, o);
+        const double om = __shfl_xor_sync(kFull, tnum, o);
+        tnum = (om > tnum) ? om : tnum;
+      }
+    }
+
+    // ---- the state machine's step: scalar work, the only part where tiles of a warp diverge ----
+    if (along) {
+      mc.on_eval(fs, ss);
+      if (mc.req == REQ_MOVE) {  // minimize_nrc.h:508-511
+        const double step = mc.alpha;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          xi[j] *= step;
+          p[j] += xi[j];
+        }
+        mc.on_moved();
+      }
+    } else if (kind == REQ_INIT_GRAD) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double gneg = -gr[j];
+        g[j] = gneg; h[j] = gneg; xi[j] = gneg;
+      }
+      f_init = fs;
+      mc.on_init(fs);
+    } else if (kind == REQ_GRADIENT) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) xi[j] = gr[j];
+      mc.on_gradient(tnum, gg, dgg);
+      if (mc.req == REQ_DIRECTION) {  // :681-685
+        const double gam = mc.gam;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double gj = -xi[j];
+          const double hj = gj + gam * h[j];
+          g[j] = gj; h[j] = hj; xi[j] = hj;
+        }
+        mc.on_directed();
+      }
+    }
+  }
+
+  if (!run) return;
+  // ---- commit (CGD.cpp:61-89) ----
+  double fret = mc.fret;
+  bool restore = (fret > f_init);
+  if (mc.status == ST_NONFINITE || mc.status == ST_BRACKET_CAP) restore = true;
+  if (restore) fret = f_init;
+  if (r == 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double val = clamp_to_domain(restore ? xs[j] : p[j], dom[j]);
+      Gv.xbd[v0 + j] = make_double2(val, qnan_f64());
+      B.xout[P.var_off + j] = val;
+    }
+    ResultRec res;
+    res.f_init = f_init;
+    res.f_end = fret;
+    res.iters = mc.iter;
+    res.status = mc.status;
+    res.n_value = mc.n_value;
+    res.n_slope = mc.n_slope;
+    B.res[pidx] = res;
+  }
+}
+
+// One warp per CTA.  warp_task[w] = {log2 G, first slot in `order`, number of problems of that
+// class still to hand out from that slot on}: every size class runs in the SAME launch, so the
+// launch lasts as long as the slowest single problem, not the sum of the per-class tails.
+struct PointWarpTask {
+  int32_t lg;
+  int32_t first;
+  int32_t count;
+};
+
+__global__ void __launch_bounds__(32) solve_ba_points_kernel(GraphView Gv, BatchView B, const int32_t* order,
+                                                             const PointWarpTask* tasks, int maxiters, double ftol) {
+  const PointWarpTask t = tasks[blockIdx.x];
+  const int slot = (int)threadIdx.x >> t.lg;
+  solve_ba_point_tile(Gv, B, t.lg, (slot < t.count) ? order[t.first + slot] : -1, maxiters, ftol);
+}
+
+// ------------------------------------------------------------------------------------------
+// camera blocks
+// ------------------------------------------------------------------------------------------
+constexpr int kCamMaxThreads = 256;
+constexpr int kCamMaxCluster = 8;
+constexpr int kCamMaxWarps = kCamMaxThreads / 32;
+constexpr int kCamRedWidth = 10;  // f + 9 partials (gradient mode); f + slope use the first two
+
+struct CamShared {
+  double p[9], xi[9], g[9], h[9], xs[9];
+  double2 dom[9];
+  double red[2][kCamMaxCluster * kCamMaxWarps][kCamRedWidth];
+};
+
+// All-reduce of `n` doubles per thread over the whole cluster, fixed order: warp butterfly, lane 0
+// stores the warp's partial into slot (cta*nw + warp) of EVERY CTA's buffer (distributed shared
+// memory), one cluster barrier, then every thread folds the C*nw partials in slot order.
+template <int N>
+__device__ __forceinline__ void cluster_allreduce(cooperative_groups::cluster_group& cluster, CamShared& sh, int& flip,
+                                                  double (&v)[N], int C, int cta) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  const int slot = cta * nw + warp;
+  if (C == 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) sh.red[flip][slot][i] = v[i];
+    }
+    __syncthreads();
+  } else {
+    if (lane < C) {  // lane d delivers this warp's partial to CTA d
+      double* remote = cluster.map_shared_rank(&sh.red[flip][slot][0], lane);
+#pragma unroll
+      for (int i = 0; i < N; ++i) remote[i] = v[i];
+    }
+    cluster.sync();
+  }
+  const int total = C * nw;
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = sh.red[flip][0][i];
+  for (int s = 1; s < total; ++s) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += sh.red[flip][s][i];
+  }
+  flip ^= 1;
+}
+
+// grid = nprobs * C CTAs, cluster = C CTAs (set at launch), `order` lists the camera-class problems.
+__global__ void __launch_bounds__(kCamMaxThreads) solve_ba_cameras_kernel(GraphView Gv, BatchView B, const int32_t* order,
+                                                                          int C, int maxiters, double ftol) {
+  namespace cgn = cooperative_groups;
+  cgn::cluster_group cluster = cgn::this_cluster();
+  __shared__ CamShared sh;
+  const int cta = (C > 1) ? (int)cluster.block_rank() : 0;
+  const int pidx = order[blockIdx.x / C];
+  const ProblemDesc P = B.probs[pidx];
+  const int nf = P.nf;
+  const int32_t v0 = B.vids[P.var_off];
+  const int cam = v0 / 9;
+  const int T = blockDim.x;
+  const int rank = cta * T + threadIdx.x;
+  const int size = C * T;
+  int flip = 0;
+
+  if (threadIdx.x < 9) {
+    const int j = threadIdx.x;
+    const double xv = (B.x0 != nullptr) ? B.x0[P.var_off + j] : Gv.xbd[v0 + j].x;
+    sh.p[j] = xv; sh.xs[j] = xv; sh.xi[j] = 0.0; sh.g[j] = 0.0; sh.h[j] = 0.0;
+    sh.dom[j] = __ldg(&Gv.dom[v0 + j]);
+  }
+  // this thread's first observation: frozen point block + pixel staged in registers
+  const bool have = (rank < nf);
+  double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+  double2 ob0 = make_double2(0.0, 0.0);
+  bool fc_on0 = false;
+  double fc_val0 = 0.0;
+  const int32_t pbase = 9 * Gv.ncams;
+  if (have) {
+    const int32_t fid = B.fids[P.fac_off + rank];
+    const int32_t pt = __ldg(&Gv.pt[fid]);
+    ob0 = __ldg(&Gv.obs[fid]);
+    q0 = Gv.xbd[pbase + 3 * pt].x; q1 = Gv.xbd[pbase + 3 * pt + 1].x; q2 = Gv.xbd[pbase + 3 * pt + 2].x;
+    if (Gv.fconst_on != nullptr && Gv.fconst_on[fid]) {
+      fc_on0 = true;
+      fc_val0 = Gv.fconst_val[fid];
+    }
+  }
+  __syncthreads();
+  (void)cam;
+
+  CgdMachine mc;
+  mc.start(maxiters, ftol);
+  double f_init = 0.0;
+
+  while (!mc.done()) {
+    const int kind = mc.req;
+    const bool along = (kind == REQ_VALUE) || (kind == REQ_VALUE_SLOPE);
+    const bool want_g = (kind != REQ_VALUE);
+    const double alpha = mc.alpha;
+    double x[12];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const double pj = sh.p[j];
+      x[j] = clamp_to_domain(along ? (pj + alpha * sh.xi[j]) : pj, sh.dom[j]);
+    }
+    BaOps::Fwd m;
+    BaOps::rotation(x[0], x[1], x[2], m);
+
+    // this thread's observations: round 0 from registers, later rounds (more observations than
+    // threads in the cluster) re-read their frozen block through L1/L2
+    auto stage = [&](int k, double2& ob, bool& fc_on, double& fc_val) {
+      if (k == rank) {
+        x[9] = q0; x[10] = q1; x[11] = q2; ob = ob0; fc_on = fc_on0; fc_val = fc_val0;
+      } else {
+        const int32_t fid = B.fids[P.fac_off + k];
+        const int32_t pt = __ldg(&Gv.pt[fid]);
+        ob = __ldg(&Gv.obs[fid]);
+        x[9] = Gv.xbd[pbase + 3 * pt].x; x[10] = Gv.xbd[pbase + 3 * pt + 1].x; x[11] = Gv.xbd[pbase + 3 * pt + 2].x;
+        fc_on = (Gv.fconst_on != nullptr) && Gv.fconst_on[fid];
+        fc_val = fc_on ? Gv.fconst_val[fid] : 0.0;
+      }
+    };
+
+    if (along) {
+      double v2[2] = {0.0, 0.0};
+      for (int k = rank; k < nf; k += size) {
+        double2 ob;
+        bool fc_on;
+        double fc_val;
+        stage(k, ob, fc_on, fc_val);
+        double fv = BaOps::project(x, ob, m);
+        if (want_g) {
+          double gq[12];
+          BaOps::partials(x, m, gq);
+          double sl = 0.0;
+#pragma unroll
+          for (int s = 0; s < 9; ++s) {
+            const double d = sh.xi[s];
+            if (d != 0.0) sl += gq[s] * d;
+          }
+          v2[1] += sl;
+        }
+        if (fc_on) fv = fc_val;
+        v2[0] += fv;
+      }
+      cluster_allreduce<2>(cluster, sh, flip, v2, C, cta);
+      mc.on_eval(v2[0], v2[1]);
+      if (mc.req == REQ_MOVE) {
+        const double step = mc.alpha;
+        if (threadIdx.x < 9) {
+          const int j = threadIdx.x;
+          const double d = sh.xi[j] * step;
+          sh.xi[j] = d;
+          sh.p[j] += d;
+        }
+        __syncthreads();
+        mc.on_moved();
+      }
+    } else {
+      double acc[kCamRedWidth];
+#pragma unroll
+      for (int i = 0; i < kCamRedWidth; ++i) acc[i] = 0.0;
+      for (int k = rank; k < nf; k += size) {
+        double2 ob;
+        bool fc_on;
+        double fc_val;
+        stage(k, ob, fc_on, fc_val);
+        double fv = BaOps::project(x, ob, m);
+        double gq[12];
+        BaOps::partials(x, m, gq);
+#pragma unroll
+        for (int s = 0; s < 9; ++s) acc[1 + s] += gq[s];
+        if (fc_on) fv = fc_val;
+        acc[0] += fv;
+      }
+      cluster_allreduce<kCamRedWidth>(cluster, sh, flip, acc, C, cta);
+      if (kind == REQ_INIT_GRAD) {
+        if (threadIdx.x < 9) {
+          const int j = threadIdx.x;
+          const double gneg = -acc[1 + j];
+          sh.g[j] = gneg; sh.h[j] = gneg; sh.xi[j] = gneg;
+        }
+        __syncthreads();
+        f_init = acc[0];
+        mc.on_init(acc[0]);
+      } else {
+        double gg = 0.0, dgg = 0.0, tnum = 0.0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const double gr = acc[1 + j];
+          const double pj = fabs(sh.p[j]);
+          const double t = fabs(gr) * ((pj < 1.0) ? 1.0 : pj);
+          tnum = (t > tnum) ? t : tnum;
+          const double gj = sh.g[j];
+          gg += gj * gj;
+          dgg += (gr + gj) * gr;
+        }
+        mc.on_gradient(tnum, gg, dgg);
+        __syncthreads();  // every thread has read g[] before anyone rewrites it
+        if (threadIdx.x < 9) {
+          const int j = threadIdx.x;
+          if (mc.req == REQ_DIRECTION) {
+            const double gj = -acc[1 + j];
+            const double hj = gj + mc.gam * sh.h[j];
+            sh.g[j] = gj; sh.h[j] = hj; sh.xi[j] = hj;
+          } else {
+            sh.xi[j] = acc[1 + j];
+          }
+        }
+        __syncthreads();
+        if (mc.req == REQ_DIRECTION) mc.on_directed();
+      }
+    }
+  }
+
+  // ---- commit (CGD.cpp:61-89): CTA 0 of the cluster writes ----
+  double fret = mc.fret;
+  bool restore = (fret > f_init);
+  if (mc.status == ST_NONFINITE || mc.status == ST_BRACKET_CAP) restore = true;
+  if (restore) fret = f_init;
+  if (cta == 0) {
+    if (threadIdx.x < 9) {
+      const int j = threadIdx.x;
+      const double val = clamp_to_domain(restore ? sh.xs[j] : sh.p[j], sh.dom[j]);
+      Gv.xbd[v0 + j] = make_double2(val, qnan_f64());
+      B.xout[P.var_off + j] = val;
+    }
+    if (threadIdx.x == 0) {
+      ResultRec res;
+      res.f_init = f_init;
+      res.f_end = fret;
+      res.iters = mc.iter;
+      res.status = mc.status;
+      res.n_value = mc.n_value;
+      res.n_slope = mc.n_slope;
+      B.res[pidx] = res;
+    }
+  }
+  if (C > 1) cluster.sync();  // no CTA leaves while a peer could still address its shared memory
+}
+
+}  // namespace rdisgpu

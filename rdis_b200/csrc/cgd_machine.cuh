@@ -182,50 +182,6 @@ struct CgdMachine {
     ask_value(bx, PH_BR_FB);
   }
 
-  // Top of the bracket while-loop (:101-148).
-  RDIS_HD void bracket_loop() {
-    if (!(fb > fc)) {
-      begin_dbrent();
-      return;
-    }
-    if (++br_iter > kBracketCap) {
-      finish(ST_BRACKET_CAP);
-      return;
-    }
-    const double r = (bx - ax) * (fb - fc);
-    const double q = (bx - cx) * (fb - fa);
-    const double qmr = q - r;
-    u = bx - ((bx - cx) * q - (bx - ax) * r) / (2.0 * copysign(pick_max(fabs(qmr), 1.0e-20), qmr));
-    const double ulim = bx + 100.0 * (cx - bx);
-    if ((bx - u) * (u - cx) > 0.0) {
-      ask_value(u, PH_BR_PARAB_INSIDE);
-    } else if ((cx - u) * (u - ulim) > 0.0) {
-      ask_value(u, PH_BR_PARAB_BEYOND);
-    } else if ((u - ulim) * (ulim - cx) >= 0.0) {
-      u = ulim;
-      ask_value(u, PH_BR_SHIFT);
-    } else {
-      u = cx + 1.618034 * (cx - bx);
-      ask_value(u, PH_BR_SHIFT);
-    }
-  }
-  RDIS_HD void bracket_shift() {  // :146-147
-    ax = bx; bx = cx; cx = u;
-    fa = fb; fb = fc; fc = fu;
-    bracket_loop();
-  }
-
-  // Dbrent::minimize prologue (:312-316); f(bx) is known (fb), only the slope is new.
-  RDIS_HD void begin_dbrent() {
-    a = (ax < cx ? ax : cx);
-    b = (ax > cx ? ax : cx);
-    x = w = v = bx;
-    d = 0.0;
-    e = 0.0;
-    db_iter = 0;
-    ask_value_slope(x, PH_DB_FIRST);
-  }
-
   RDIS_HD void line_search_done(double xmin, double fmin) {
     fret = fmin;  // :646
     alpha = xmin;
@@ -291,7 +247,14 @@ struct CgdMachine {
     ask_value_slope(u, PH_DB_EVAL);
   }
 
+  // One objective evaluation came back.  The phase switch only records what the evaluation was for;
+  // the loop bodies of bracket / dbrent exist ONCE below it (stage dispatch) instead of being inlined
+  // at each of their call sites: a third of the code, and thread groups that share a warp but sit
+  // in different phases reconverge between the stages.
+  enum Stage : int { SG_NONE = 0, SG_SHIFT, SG_BRACKET_LOOP, SG_BEGIN_DBRENT, SG_DBRENT_LOOP };
+
   RDIS_HD void advance(double f, double slope) {
+    int stage = SG_NONE;
     switch (phase) {
       case PH_BR_FB: {  // :89-98
         fb = f;
@@ -301,25 +264,25 @@ struct CgdMachine {
         }
         cx = bx + 1.618034 * (bx - ax);
         ask_value(cx, PH_BR_FC);
-        return;
+        break;
       }
       case PH_BR_FC:
         fc = f;
-        bracket_loop();
-        return;
+        stage = SG_BRACKET_LOOP;
+        break;
       case PH_BR_PARAB_INSIDE:  // :113-128
         fu = f;
         if (fu < fc) {
           ax = bx; bx = u; fa = fb; fb = fu;
-          begin_dbrent();
+          stage = SG_BEGIN_DBRENT;
         } else if (fu > fb) {
           cx = u; fc = fu;
-          begin_dbrent();
+          stage = SG_BEGIN_DBRENT;
         } else {
           u = cx + 1.618034 * (cx - bx);
           ask_value(u, PH_BR_SHIFT);
         }
-        return;
+        break;
       case PH_BR_PARAB_BEYOND:  // :130-135
         fu = f;
         if (fu < fc) {
@@ -328,24 +291,24 @@ struct CgdMachine {
           fb = fc; fc = fu;
           ask_value(u, PH_BR_PARAB_BEYOND2);
         } else {
-          bracket_shift();
+          stage = SG_SHIFT;
         }
-        return;
+        break;
       case PH_BR_PARAB_BEYOND2:
       case PH_BR_SHIFT:
         fu = f;
-        bracket_shift();
-        return;
+        stage = SG_SHIFT;
+        break;
       case PH_DB_FIRST:  // :315-316
         fw = fv = fx = f;
         dw = dv = dx = slope;
-        dbrent_loop();
-        return;
+        stage = SG_DBRENT_LOOP;
+        break;
       case PH_DB_EVAL: {  // :365-401
         fu = f;
         if (small_step && fu > fx) {
           line_search_done(x, fx);
-          return;
+          break;
         }
         const double du = slope;
         if (fu <= fx) {
@@ -363,13 +326,54 @@ struct CgdMachine {
           }
         }
         ++db_iter;
-        dbrent_loop();
-        return;
+        stage = SG_DBRENT_LOOP;
+        break;
       }
       default:
         finish(ST_NONFINITE);
-        return;
+        break;
     }
+    if (stage == SG_SHIFT) {  // :146-147
+      ax = bx; bx = cx; cx = u;
+      fa = fb; fb = fc; fc = fu;
+      stage = SG_BRACKET_LOOP;
+    }
+    if (stage == SG_BRACKET_LOOP) {  // top of the bracket while-loop, :101-148
+      if (!(fb > fc)) {
+        stage = SG_BEGIN_DBRENT;
+      } else if (++br_iter > kBracketCap) {
+        finish(ST_BRACKET_CAP);
+      } else {
+        const double r = (bx - ax) * (fb - fc);
+        const double q = (bx - cx) * (fb - fa);
+        const double qmr = q - r;
+        u = bx - ((bx - cx) * q - (bx - ax) * r) / (2.0 * copysign(pick_max(fabs(qmr), 1.0e-20), qmr));
+        const double ulim = bx + 100.0 * (cx - bx);
+        int next_phase;
+        if ((bx - u) * (u - cx) > 0.0) {
+          next_phase = PH_BR_PARAB_INSIDE;
+        } else if ((cx - u) * (u - ulim) > 0.0) {
+          next_phase = PH_BR_PARAB_BEYOND;
+        } else if ((u - ulim) * (ulim - cx) >= 0.0) {
+          u = ulim;
+          next_phase = PH_BR_SHIFT;
+        } else {
+          u = cx + 1.618034 * (cx - bx);
+          next_phase = PH_BR_SHIFT;
+        }
+        ask_value(u, next_phase);
+      }
+    }
+    if (stage == SG_BEGIN_DBRENT) {  // Dbrent::minimize prologue (:312-316); f(bx) is known (fb), only the slope is new
+      a = (ax < cx ? ax : cx);
+      b = (ax > cx ? ax : cx);
+      x = w = v = bx;
+      d = 0.0;
+      e = 0.0;
+      db_iter = 0;
+      ask_value_slope(x, PH_DB_FIRST);
+    }
+    if (stage == SG_DBRENT_LOOP) dbrent_loop();
   }
 };
 

@@ -296,9 +296,11 @@ struct BaOps {
     double s, c;                // sin/cos(theta)
   };
 
-  __device__ static __forceinline__ double forward(const double* x, double2 ob, Fwd& m) {
-    const double r0 = x[0], r1 = x[1], r2v = x[2];
-    const double q0 = x[9], q1 = x[10], q2 = x[11];
+  // Camera-only part of the forward model: theta = |r|, axis = r/theta, sin/cos(theta)
+  // (normalize + the theta > 0 branch of angleAxisRotateTranslatePoint, BundleAdjustmentFactor.cpp:266-335).
+  // It depends on the three rotation variables only, so the block kernels hoist it out of the
+  // per-factor work; the arithmetic is the same expression for expression.
+  __device__ static __forceinline__ void rotation(double r0, double r1, double r2v, Fwd& m) {
     const double nrm = sqrt(r0 * r0 + r1 * r1 + r2v * r2v);
     if (nrm != 0.0) {
       m.a0 = r0 / nrm; m.a1 = r1 / nrm; m.a2 = r2v / nrm;
@@ -306,19 +308,27 @@ struct BaOps {
       m.a0 = r0; m.a1 = r1; m.a2 = r2v;
     }
     m.theta = nrm;
+    if (nrm > 0.0) {
+      sincos(nrm, &m.s, &m.c);
+    } else {
+      m.s = 0.0; m.c = 1.0;  // sin(0), cos(0): what the gradient code recomputes from theta
+    }
+  }
+
+  // Rotate + translate + project + distort + residual, given rotation(): x[3..11] are read.
+  __device__ static __forceinline__ double project(const double* x, double2 ob, Fwd& m) {
+    const double q0 = x[9], q1 = x[10], q2 = x[11];
     m.c0 = m.a1 * q2 - m.a2 * q1;
     m.c1 = m.a2 * q0 - m.a0 * q2;
     m.c2 = m.a0 * q1 - m.a1 * q0;
     double P0, P1, P2;
-    if (nrm > 0.0) {
-      sincos(nrm, &m.s, &m.c);
+    if (m.theta > 0.0) {
       const double omc = 1 - m.c;
       m.adp = m.a0 * q0 + m.a1 * q1 + m.a2 * q2;
       P0 = q0 * m.c + m.c0 * m.s + m.a0 * omc * m.adp;
       P1 = q1 * m.c + m.c1 * m.s + m.a1 * omc * m.adp;
       P2 = q2 * m.c + m.c2 * m.s + m.a2 * omc * m.adp;
     } else {
-      m.s = 0.0; m.c = 1.0;  // sin(0), cos(0): what the gradient code recomputes from theta
       m.adp = 0;
       P0 = q0 + m.c0; P1 = q1 + m.c1; P2 = q2 + m.c2;
     }
@@ -333,6 +343,11 @@ struct BaOps {
     m.res0 = (pix0 - ob.x);
     m.res1 = (pix1 - ob.y);
     return (m.res0 * m.res0 + m.res1 * m.res1) / 2.0;
+  }
+
+  __device__ static __forceinline__ double forward(const double* x, double2 ob, Fwd& m) {
+    rotation(x[0], x[1], x[2], m);
+    return project(x, ob, m);
   }
 
   // 12 partials in slot order.
@@ -350,7 +365,7 @@ struct BaOps {
     const double J00 = m.dist + t1 * pp00, J01 = t1 * pp01, J10 = t1 * pp01, J11 = m.dist + t1 * pp11;
     const double omc = (1 - c);
 
-    auto project = [&](double dP0, double dP1, double dP2) -> double {
+    auto chain = [&](double dP0, double dP1, double dP2) -> double {
       const double dppx = (P[0] * dP2 - P[2] * dP0) / P22;
       const double dppy = (P[1] * dP2 - P[2] * dP1) / P22;
       const double drx = m.res0 * (J00 * dppx + J01 * dppy);
@@ -377,21 +392,21 @@ struct BaOps {
       const double d0 = (a[1] * a[1] + a[2] * a[2]) / vnorm;
       const double d1 = -a[0] * a[1] / vnorm;
       const double d2 = -a[0] * a[2] / vnorm;
-      g[0] = project(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[0], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[0],
+      g[0] = chain(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[0], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[0],
                      A20 * d0 + A21 * d1 + A22 * d2 + T2 * a[0]);
     }
     {
       const double d0 = -a[0] * a[1] / vnorm;
       const double d1 = (a[0] * a[0] + a[2] * a[2]) / vnorm;
       const double d2 = -a[1] * a[2] / vnorm;
-      g[1] = project(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[1], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[1],
+      g[1] = chain(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[1], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[1],
                      A20 * d0 + A21 * d1 + A22 * d2 + T2 * a[1]);
     }
     {
       const double d0 = -a[0] * a[2] / vnorm;
       const double d1 = -a[1] * a[2] / vnorm;
       const double d2 = (a[0] * a[0] + a[1] * a[1]) / vnorm;
-      g[2] = project(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[2], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[2],
+      g[2] = chain(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[2], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[2],
                      A20 * d0 + A21 * d1 + A22 * d2 + T2 * a[2]);
     }
     // translation
@@ -407,11 +422,11 @@ struct BaOps {
     g[7] = m.res0 * (f * m.r2 * m.pp0) + m.res1 * (f * m.r2 * m.pp1);
     g[8] = m.res0 * (f * m.r2 * m.r2 * m.pp0) + m.res1 * (f * m.r2 * m.r2 * m.pp1);
     // point: columns of the rotation matrix
-    g[9] = project(c * (1.0 - a[0] * a[0]) + a[0] * a[0], a[2] * s + a[0] * a[1] * (1.0 - c),
+    g[9] = chain(c * (1.0 - a[0] * a[0]) + a[0] * a[0], a[2] * s + a[0] * a[1] * (1.0 - c),
                    -a[1] * s + a[0] * a[2] * (1.0 - c));
-    g[10] = project(-a[2] * s + a[0] * a[1] * (1.0 - c), c * (1.0 - a[1] * a[1]) + a[1] * a[1],
+    g[10] = chain(-a[2] * s + a[0] * a[1] * (1.0 - c), c * (1.0 - a[1] * a[1]) + a[1] * a[1],
                     a[0] * s + a[1] * a[2] * (1.0 - c));
-    g[11] = project(a[1] * s + a[0] * a[2] * (1.0 - c), -a[0] * s + a[1] * a[2] * (1.0 - c),
+    g[11] = chain(a[1] * s + a[0] * a[2] * (1.0 - c), -a[0] * s + a[1] * a[2] * (1.0 - c),
                     c * (1.0 - a[2] * a[2]) + a[2] * a[2]);
   }
 

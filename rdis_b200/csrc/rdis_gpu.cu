@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/rdis_gpu.h"
+#include "ba_block_kernels.cuh"
 #include "solve_kernels.cuh"
 #include "sweep_kernels.cuh"
 
@@ -95,6 +96,10 @@ struct rdisgpu_ctx {
   DevBuf<uint8_t> sine, fconst_on;
   DevBuf<double2> obs;
   bool has_fconst = false;
+  std::vector<int32_t> vmark, fmark;  // sibling check: epoch stamps (no per-call clearing)
+  int32_t mark_epoch = 0;
+  rdisgpu_batch* scratch_batch = nullptr;  // reused by the one-shot solve entry points
+  bool generic_only = false;  // rdisgpu_set_option("generic_only"): bypass the BA block kernels (tests)
   GraphView gv;
 
   // scratch for the sweep / state calls
@@ -125,19 +130,40 @@ struct rdisgpu_batch {
   int64_t nprobs = 0;
   int64_t total_nv = 0, total_nf = 0;
   std::vector<ProblemDesc> h_probs;
-  DevBuf<ProblemDesc> probs;
-  DevBuf<int32_t> vids, fids;
+  // All index lists of the batch live in ONE device allocation, staged through one pinned buffer and
+  // uploaded with one copy: [ProblemDesc probs | vids | fids | order | pt_order | cam_order | pt_tasks]
+  DevBuf<char> blob;
+  PinnedBuf<char> h_blob;
+  ProblemDesc* d_probs = nullptr;
+  int32_t *d_vids = nullptr, *d_fids = nullptr, *d_order = nullptr, *d_pt_order = nullptr, *d_cam_order = nullptr;
+  PointWarpTask* d_pt_tasks = nullptr;
   DevBuf<double> x0, xout;
   DevBuf<ResultRec> res;
-  // size classes
+  // size classes of the generic kernels
   std::vector<int32_t> h_order;      // problem indices grouped by class
-  DevBuf<int32_t> order;
   struct Class { int kind; int param; int64_t off; int64_t count; };  // kind 0 = tile(G), 1 = block(threads), 2 = grid
   std::vector<Class> classes;
   PinnedBuf<ResultRec> h_res;
   PinnedBuf<double> h_x;  // staging for x0 upload and xout download
+  // bundle-adjustment block fast paths (ba_block_kernels.cuh)
+  int n_pt_warps = 0, n_cam = 0, cam_nf_max = 0;
+  int cam_C = 0, cam_T = 0;  // chosen at the first solve (needs the occupancy query)
   int last_launches = 0;
   bool solved = false;
+};
+
+// The two ways a caller can describe a batch: an array of rdisgpu_problem, or packed CSR lists.
+struct ProblemsView {
+  int64_t n = 0;
+  const rdisgpu_problem* arr = nullptr;
+  const int64_t* var_off = nullptr;
+  const int32_t* vids = nullptr;
+  const int64_t* fac_off = nullptr;
+  const int64_t* fids = nullptr;
+  int64_t nv(int64_t p) const { return arr ? arr[p].nv : var_off[p + 1] - var_off[p]; }
+  int64_t nf(int64_t p) const { return arr ? arr[p].nf : fac_off[p + 1] - fac_off[p]; }
+  const int32_t* vid(int64_t p) const { return arr ? arr[p].vid : vids + var_off[p]; }
+  const int64_t* fid(int64_t p) const { return arr ? arr[p].fid : fids + fac_off[p]; }
 };
 
 namespace {
@@ -240,6 +266,7 @@ void rdisgpu_destroy(rdisgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  delete ctx->scratch_batch;
   delete ctx;
 }
 
@@ -249,6 +276,15 @@ int rdisgpu_set_stream(rdisgpu_ctx* ctx, void* cuda_stream) {
   if (!ctx) return RDISGPU_ERR_ARG;
   ctx->stream = (cudaStream_t)cuda_stream;
   return RDISGPU_OK;
+}
+
+int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return RDISGPU_ERR_ARG;
+  if (std::strcmp(name, "generic_only") == 0) {
+    ctx->generic_only = (value != 0);
+    return RDISGPU_OK;
+  }
+  return ctx->fail(RDISGPU_ERR_ARG, "set_option: unknown option");
 }
 
 int rdisgpu_synchronize(rdisgpu_ctx* ctx) {
@@ -385,8 +421,7 @@ int rdisgpu_finalize(rdisgpu_ctx* ctx) {
   std::vector<double>().swap(ctx->h_konst);
   std::vector<double>().swap(ctx->h_coeff);
   std::vector<uint8_t>().swap(ctx->h_sine);
-  std::vector<int32_t>().swap(ctx->h_cam);
-  std::vector<int32_t>().swap(ctx->h_pt);
+  // h_cam / h_pt stay: batch_create classifies point / camera blocks on the host with them
   std::vector<double>().swap(ctx->h_obs);
 
   ctx->finalized = true;
@@ -626,47 +661,81 @@ int rdisgpu_factor_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, int32_
 // ==========================================================================================
 // subspace solves
 // ==========================================================================================
-int rdisgpu_batch_create(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t nprobs, rdisgpu_batch** out) {
-  if (!ctx || !out) return RDISGPU_ERR_ARG;
-  *out = nullptr;
-  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "batch_create before finalize");
-  if (nprobs <= 0 || !probs) return ctx->fail(RDISGPU_ERR_ARG, "batch_create: no problems");
-  if (nprobs >= 0x40000000LL) return ctx->fail(RDISGPU_ERR_ARG, "batch_create: too many problems");
-  CK(cudaSetDevice(ctx->device));
-
-  std::unique_ptr<rdisgpu_batch> b(new rdisgpu_batch());
-  b->ctx = ctx;
+// (Re)builds `b` in place from a problem description: validation, sibling check, size classes,
+// block-shape classification, and ONE upload of all index lists.  Device / pinned buffers only grow,
+// so a batch object that is rebuilt call after call (the context's scratch batch) allocates nothing
+// in steady state.
+static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
+  rdisgpu_ctx* ctx = b->ctx;
+  const int64_t nprobs = pv.n;
   b->nprobs = nprobs;
   b->h_probs.resize(nprobs);
+  b->classes.clear();
+  b->h_order.clear();
+  b->n_pt_warps = b->n_cam = b->cam_nf_max = 0;
+  b->cam_C = b->cam_T = 0;
+  b->solved = false;
   int64_t tv = 0, tf = 0;
   for (int64_t p = 0; p < nprobs; ++p) {
-    const rdisgpu_problem& P = probs[p];
-    if (P.nv < 0 || P.nf < 0 || (P.nv > 0 && !P.vid) || (P.nf > 0 && !P.fid) || P.nv > 0x7fffffffLL || P.nf > 0x7fffffffLL)
-      return ctx->fail(RDISGPU_ERR_ARG, "batch_create: malformed problem");
-    b->h_probs[p] = ProblemDesc{tv, tf, (int32_t)P.nv, (int32_t)P.nf};
-    tv += P.nv;
-    tf += P.nf;
+    const int64_t nv = pv.nv(p), nf = pv.nf(p);
+    if (nv < 0 || nf < 0 || (nv > 0 && !pv.vid(p)) || (nf > 0 && !pv.fid(p)) || nv > 0x7fffffffLL || nf > 0x7fffffffLL)
+      return ctx->fail(RDISGPU_ERR_ARG, "batch: malformed problem");
+    b->h_probs[p] = ProblemDesc{tv, tf, (int32_t)nv, (int32_t)nf};
+    tv += nv;
+    tf += nf;
   }
+  if (tv > 0x7fffffffLL || tf > 0x7fffffffLL) return ctx->fail(RDISGPU_ERR_ARG, "batch: too many variables / factors");
   b->total_nv = tv;
   b->total_nf = tf;
-  std::vector<int32_t> vids(tv), fids(tf);
+
+  // upper bounds of every list, then carve the pinned staging blob
+  const size_t npt_tasks_max = (size_t)nprobs + 6;
+  auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  const size_t o_probs = 0;
+  const size_t o_vids = align16(o_probs + sizeof(ProblemDesc) * (size_t)nprobs);
+  const size_t o_fids = align16(o_vids + 4 * (size_t)tv);
+  const size_t o_order = align16(o_fids + 4 * (size_t)tf);
+  const size_t o_pt = align16(o_order + 4 * (size_t)nprobs);
+  const size_t o_cam = align16(o_pt + 4 * (size_t)nprobs);
+  const size_t o_tasks = align16(o_cam + 4 * (size_t)nprobs);
+  const size_t total = align16(o_tasks + sizeof(PointWarpTask) * npt_tasks_max);
+  CK(b->h_blob.ensure(total));
+  CK(b->blob.ensure(total));
+  char* hb = b->h_blob.p;
+  ProblemDesc* h_probs = reinterpret_cast<ProblemDesc*>(hb + o_probs);
+  int32_t* vids = reinterpret_cast<int32_t*>(hb + o_vids);
+  int32_t* fids = reinterpret_cast<int32_t*>(hb + o_fids);
+  int32_t* h_order = reinterpret_cast<int32_t*>(hb + o_order);
+  int32_t* h_pt = reinterpret_cast<int32_t*>(hb + o_pt);
+  int32_t* h_cam = reinterpret_cast<int32_t*>(hb + o_cam);
+  PointWarpTask* h_tasks = reinterpret_cast<PointWarpTask*>(hb + o_tasks);
+  std::memcpy(h_probs, b->h_probs.data(), sizeof(ProblemDesc) * (size_t)nprobs);
+
   // sibling check: no variable and no factor may belong to two problems of one batch
-  std::vector<uint8_t> vseen((size_t)ctx->V, 0), fseen((size_t)ctx->F, 0);
+  if ((int64_t)ctx->vmark.size() != ctx->V) ctx->vmark.assign((size_t)ctx->V, 0);
+  if ((int64_t)ctx->fmark.size() != ctx->F) ctx->fmark.assign((size_t)ctx->F, 0);
+  if (++ctx->mark_epoch == 0x7fffffff) {
+    std::fill(ctx->vmark.begin(), ctx->vmark.end(), 0);
+    std::fill(ctx->fmark.begin(), ctx->fmark.end(), 0);
+    ctx->mark_epoch = 1;
+  }
+  const int32_t epoch = ctx->mark_epoch;
   for (int64_t p = 0; p < nprobs; ++p) {
-    const rdisgpu_problem& P = probs[p];
     const ProblemDesc& D = b->h_probs[p];
-    for (int64_t j = 0; j < P.nv; ++j) {
-      const int32_t v = P.vid[j];
-      if (v < 0 || v >= ctx->V) return ctx->fail(RDISGPU_ERR_ARG, "batch_create: variable id out of range");
-      if (vseen[v]) return ctx->fail(RDISGPU_ERR_OVERLAP, "batch_create: a variable appears twice in the batch");
-      vseen[v] = 1;
+    const int32_t* pvid = pv.vid(p);
+    const int64_t* pfid = pv.fid(p);
+    for (int64_t j = 0; j < D.nv; ++j) {
+      const int32_t v = pvid[j];
+      if (v < 0 || v >= ctx->V) return ctx->fail(RDISGPU_ERR_ARG, "batch: variable id out of range");
+      if (ctx->vmark[v] == epoch) return ctx->fail(RDISGPU_ERR_OVERLAP, "batch: a variable appears twice in the batch");
+      ctx->vmark[v] = epoch;
       vids[D.var_off + j] = v;
     }
-    for (int64_t k = 0; k < P.nf; ++k) {
-      const int64_t f = P.fid[k];
-      if (f < 0 || f >= ctx->F) return ctx->fail(RDISGPU_ERR_ARG, "batch_create: factor id out of range");
-      if (fseen[f]) return ctx->fail(RDISGPU_ERR_OVERLAP, "batch_create: a factor appears twice in the batch");
-      fseen[f] = 1;
+    for (int64_t k = 0; k < D.nf; ++k) {
+      const int64_t f = pfid[k];
+      if (f < 0 || f >= ctx->F) return ctx->fail(RDISGPU_ERR_ARG, "batch: factor id out of range");
+      if (ctx->fmark[f] == epoch) return ctx->fail(RDISGPU_ERR_OVERLAP, "batch: a factor appears twice in the batch");
+      ctx->fmark[f] = epoch;
       fids[D.fac_off + k] = (int32_t)f;
     }
   }
@@ -675,7 +744,53 @@ int rdisgpu_batch_create(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t
   const int kTileMax = 32, kBlockMax = 4096;
   std::vector<std::vector<int32_t>> tile_lists(6), block_lists(3);
   std::vector<int32_t> grid_list;
+  // bundle-adjustment block shapes get the register / cluster resident kernels
+  std::vector<uint8_t> fast((size_t)nprobs, 0);  // 1 = point block, 2 = camera block
+  if (ctx->kind == KIND_BA && !ctx->generic_only) {
+    const int32_t pbase = 9 * ctx->ncams;
+    std::vector<int32_t> pt_lists[6];
+    for (int64_t p = 0; p < nprobs; ++p) {
+      const ProblemDesc& D = b->h_probs[p];
+      const int32_t* pvv = vids + D.var_off;
+      const int32_t* pf = fids + D.fac_off;
+      if (D.nf < 1) continue;
+      bool asc = true;
+      for (int k = 1; k < D.nf && asc; ++k) asc = pf[k] > pf[k - 1];
+      if (!asc) continue;
+      if (D.nv == 3 && D.nf <= 32 && pvv[0] >= pbase && (pvv[0] - pbase) % 3 == 0 && pvv[1] == pvv[0] + 1 && pvv[2] == pvv[0] + 2) {
+        const int32_t pt = (pvv[0] - pbase) / 3;
+        bool ok = true;
+        for (int k = 0; k < D.nf && ok; ++k) ok = (ctx->h_pt[pf[k]] == pt);
+        if (!ok) continue;
+        int lg = 0;
+        while ((1 << lg) < D.nf) ++lg;
+        pt_lists[lg].push_back((int32_t)p);
+        fast[p] = 1;
+      } else if (D.nv == 9 && pvv[0] < pbase && pvv[0] % 9 == 0) {
+        bool ok = true;
+        for (int j = 1; j < 9 && ok; ++j) ok = (pvv[j] == pvv[0] + j);
+        const int32_t cam = pvv[0] / 9;
+        for (int k = 0; k < D.nf && ok; ++k) ok = (ctx->h_cam[pf[k]] == cam);
+        if (!ok) continue;
+        h_cam[b->n_cam++] = (int32_t)p;
+        b->cam_nf_max = std::max(b->cam_nf_max, D.nf);
+        fast[p] = 2;
+      }
+    }
+    // point blocks: one warp per task, 32/G problems per warp; big classes first so that the
+    // longest-running warps are scheduled first
+    int32_t npt = 0;
+    for (int lg = 5; lg >= 0; --lg) {
+      const int per_warp = 32 >> lg;
+      const int32_t base = npt;
+      const int32_t cnt = (int32_t)pt_lists[lg].size();
+      if (cnt) std::memcpy(h_pt + npt, pt_lists[lg].data(), 4 * (size_t)cnt);
+      npt += cnt;
+      for (int32_t o = 0; o < cnt; o += per_warp) h_tasks[b->n_pt_warps++] = PointWarpTask{lg, base + o, std::min(per_warp, cnt - o)};
+    }
+  }
   for (int64_t p = 0; p < nprobs; ++p) {
+    if (fast[p]) continue;
     const int nf = b->h_probs[p].nf;
     if (nf <= kTileMax) {
       int g = next_pow2(std::max(nf, 1)), lg = 0;
@@ -688,7 +803,6 @@ int rdisgpu_batch_create(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t
       grid_list.push_back((int32_t)p);
     }
   }
-  b->h_order.clear();
   for (int lg = 0; lg < 6; ++lg) {
     if (tile_lists[lg].empty()) continue;
     b->classes.push_back({0, 1 << lg, (int64_t)b->h_order.size(), (int64_t)tile_lists[lg].size()});
@@ -703,18 +817,61 @@ int rdisgpu_batch_create(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t
     b->classes.push_back({2, 256, (int64_t)b->h_order.size(), (int64_t)grid_list.size()});
     b->h_order.insert(b->h_order.end(), grid_list.begin(), grid_list.end());
   }
+  if (!b->h_order.empty()) std::memcpy(h_order, b->h_order.data(), 4 * b->h_order.size());
 
   cudaStream_t s = ctx->stream;
-  CK(upload(b->probs, b->h_probs.data(), (size_t)nprobs, s));
-  CK(upload(b->vids, vids.data(), (size_t)tv, s));
-  CK(upload(b->fids, fids.data(), (size_t)tf, s));
-  CK(upload(b->order, b->h_order.data(), b->h_order.size(), s));
+  CK(cudaMemcpyAsync(b->blob.p, hb, total, cudaMemcpyHostToDevice, s));
+  char* db = b->blob.p;
+  b->d_probs = reinterpret_cast<ProblemDesc*>(db + o_probs);
+  b->d_vids = reinterpret_cast<int32_t*>(db + o_vids);
+  b->d_fids = reinterpret_cast<int32_t*>(db + o_fids);
+  b->d_order = reinterpret_cast<int32_t*>(db + o_order);
+  b->d_pt_order = reinterpret_cast<int32_t*>(db + o_pt);
+  b->d_cam_order = reinterpret_cast<int32_t*>(db + o_cam);
+  b->d_pt_tasks = reinterpret_cast<PointWarpTask*>(db + o_tasks);
   CK(b->x0.ensure((size_t)tv));
   CK(b->xout.ensure((size_t)tv));
   CK(b->res.ensure((size_t)nprobs));
   CK(b->h_res.ensure((size_t)nprobs));
   CK(b->h_x.ensure((size_t)tv));
-  CK(cudaStreamSynchronize(s));  // vids / fids / h_order staging vectors die here
+  // The pinned blob is only rewritten by the next batch_build on this object, which runs after
+  // the caller has fetched (= synchronised) this batch's results, so no sync is needed here.
+  return RDISGPU_OK;
+}
+
+int rdisgpu_batch_create(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t nprobs, rdisgpu_batch** out) {
+  if (!ctx || !out) return RDISGPU_ERR_ARG;
+  *out = nullptr;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "batch_create before finalize");
+  if (nprobs <= 0 || !probs) return ctx->fail(RDISGPU_ERR_ARG, "batch_create: no problems");
+  if (nprobs >= 0x40000000LL) return ctx->fail(RDISGPU_ERR_ARG, "batch_create: too many problems");
+  CK(cudaSetDevice(ctx->device));
+  std::unique_ptr<rdisgpu_batch> b(new rdisgpu_batch());
+  b->ctx = ctx;
+  ProblemsView pv;
+  pv.n = nprobs;
+  pv.arr = probs;
+  const int rc = batch_build(b.get(), pv);
+  if (rc) return rc;
+  *out = b.release();
+  return RDISGPU_OK;
+}
+
+int rdisgpu_batch_create_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_off, const int32_t* vids,
+                             const int64_t* fac_off, const int64_t* fids, rdisgpu_batch** out) {
+  if (!ctx || !out) return RDISGPU_ERR_ARG;
+  *out = nullptr;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "batch_create_csr before finalize");
+  if (nprobs <= 0 || !var_off || !fac_off) return ctx->fail(RDISGPU_ERR_ARG, "batch_create_csr: no problems");
+  if (nprobs >= 0x40000000LL) return ctx->fail(RDISGPU_ERR_ARG, "batch_create_csr: too many problems");
+  CK(cudaSetDevice(ctx->device));
+  std::unique_ptr<rdisgpu_batch> b(new rdisgpu_batch());
+  b->ctx = ctx;
+  ProblemsView pv;
+  pv.n = nprobs;
+  pv.var_off = var_off; pv.vids = vids; pv.fac_off = fac_off; pv.fids = fids;
+  const int rc = batch_build(b.get(), pv);
+  if (rc) return rc;
   *out = b.release();
   return RDISGPU_OK;
 }
@@ -729,16 +886,71 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
   if (x0_host && !x0_on_device && b->total_nv > 0)  // pageable source: staged by the driver before the call returns; pinned: truly async
     CK(cudaMemcpyAsync(b->x0.p, x0_host, (size_t)b->total_nv * sizeof(double), cudaMemcpyHostToDevice, s));
   BatchView bv;
-  bv.probs = b->probs.p;
-  bv.vids = b->vids.p;
-  bv.fids = b->fids.p;
+  bv.probs = b->d_probs;
+  bv.vids = b->d_vids;
+  bv.fids = b->d_fids;
   bv.x0 = x0_host ? (x0_on_device ? x0_host : b->x0.p) : nullptr;
   bv.xout = b->xout.p;
   bv.res = b->res.p;
   GraphView gv = ctx->gv;
   int launches = 0;
+  if (b->n_pt_warps > 0) {
+    solve_ba_points_kernel<<<b->n_pt_warps, 32, 0, s>>>(gv, bv, b->d_pt_order, b->d_pt_tasks, maxiters, ftol);
+    ++launches;
+    CK(cudaGetLastError());
+  }
+  if (b->n_cam > 0) {
+    if (b->cam_C == 0) {
+      // widest cluster such that every camera block of the batch is resident at once
+      for (int C = kCamMaxCluster; C >= 1 && b->cam_C == 0; --C) {
+        int T = ((b->cam_nf_max + C - 1) / C + 31) / 32 * 32;
+        T = std::min(std::max(T, 64), kCamMaxThreads);
+        if (C == 1) {
+          b->cam_C = 1;
+          b->cam_T = T;
+          break;
+        }
+        cudaLaunchConfig_t qc = {};
+        qc.gridDim = dim3((unsigned)(b->n_cam * C));
+        qc.blockDim = dim3((unsigned)T);
+        qc.stream = s;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = (unsigned)C;
+        qa[0].val.clusterDim.y = 1;
+        qa[0].val.clusterDim.z = 1;
+        qc.attrs = qa;
+        qc.numAttrs = 1;
+        int nclusters = 0;
+        cudaError_t qe = cudaOccupancyMaxActiveClusters(&nclusters, solve_ba_cameras_kernel, &qc);
+        if (qe != cudaSuccess) {
+          cudaGetLastError();
+          continue;
+        }
+        if (nclusters >= b->n_cam) {
+          b->cam_C = C;
+          b->cam_T = T;
+        }
+      }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(b->n_cam * b->cam_C));
+    cfg.blockDim = dim3((unsigned)b->cam_T);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)b->cam_C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const int32_t* cord = b->d_cam_order;
+    int Cc = b->cam_C;
+    CK(cudaLaunchKernelEx(&cfg, solve_ba_cameras_kernel, gv, bv, cord, Cc, maxiters, ftol));
+    ++launches;
+  }
   for (const auto& c : b->classes) {
-    const int32_t* ord = b->order.p + c.off;
+    const int32_t* ord = b->d_order + c.off;
     const int cnt = (int)c.count;
     if (c.kind == 0) {
       const int per_block = 128 / c.param;
@@ -844,12 +1056,27 @@ void rdisgpu_batch_destroy(rdisgpu_batch* b) {
 
 int rdisgpu_batch_last_launches(const rdisgpu_batch* b) { return b ? b->last_launches : 0; }
 
+static rdisgpu_batch* scratch_batch(rdisgpu_ctx* ctx) {
+  if (!ctx->scratch_batch) {
+    ctx->scratch_batch = new rdisgpu_batch();
+    ctx->scratch_batch->ctx = ctx;
+  }
+  return ctx->scratch_batch;
+}
+
 int rdisgpu_solve_cgd(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t nprobs, int maxiters, double ftol,
                       rdisgpu_result* out) {
   if (!ctx) return RDISGPU_ERR_ARG;
   if (!out) return ctx->fail(RDISGPU_ERR_ARG, "solve_cgd: null result array");
-  rdisgpu_batch* b = nullptr;
-  int rc = rdisgpu_batch_create(ctx, probs, nprobs, &b);
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "solve_cgd before finalize");
+  if (nprobs <= 0 || !probs) return ctx->fail(RDISGPU_ERR_ARG, "solve_cgd: no problems");
+  if (nprobs >= 0x40000000LL) return ctx->fail(RDISGPU_ERR_ARG, "solve_cgd: too many problems");
+  CK(cudaSetDevice(ctx->device));
+  rdisgpu_batch* b = scratch_batch(ctx);
+  ProblemsView pv;
+  pv.n = nprobs;
+  pv.arr = probs;
+  int rc = batch_build(b, pv);
   if (rc) return rc;
   // x0: either every problem brings start values or none does
   bool any = false, all = true;
@@ -857,24 +1084,71 @@ int rdisgpu_solve_cgd(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t np
     if (probs[p].x0) any = true;
     else if (probs[p].nv > 0) all = false;
   }
-  std::vector<double> x0;
+  double* x0 = b->h_x.p;  // pinned staging (re-used for the download after the solve)
   if (any && !all) {
     // mixed: fill the gaps from the device state
-    x0.resize(b->total_nv);
     for (int64_t p = 0; p < nprobs && rc == RDISGPU_OK; ++p) {
-      double* dst = x0.data() + b->h_probs[p].var_off;
+      double* dst = x0 + b->h_probs[p].var_off;
       if (probs[p].x0) std::memcpy(dst, probs[p].x0, (size_t)probs[p].nv * sizeof(double));
       else rc = rdisgpu_get_x(ctx, probs[p].nv, probs[p].vid, dst);
     }
   } else if (any) {
-    x0.resize(b->total_nv);
     for (int64_t p = 0; p < nprobs; ++p)
-      if (probs[p].nv > 0) std::memcpy(x0.data() + b->h_probs[p].var_off, probs[p].x0, (size_t)probs[p].nv * sizeof(double));
+      if (probs[p].nv > 0) std::memcpy(x0 + b->h_probs[p].var_off, probs[p].x0, (size_t)probs[p].nv * sizeof(double));
   }
-  if (rc == RDISGPU_OK) rc = rdisgpu_batch_solve_cgd(b, any ? x0.data() : nullptr, maxiters, ftol);
+  if (rc == RDISGPU_OK) rc = rdisgpu_batch_solve_cgd(b, any ? x0 : nullptr, maxiters, ftol);
   if (rc == RDISGPU_OK) rc = rdisgpu_batch_fetch(b, out, nullptr);
-  rdisgpu_batch_destroy(b);
   return rc;
+}
+
+int rdisgpu_solve_cgd_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_off, const int32_t* vids,
+                          const int64_t* fac_off, const int64_t* fids, const double* x0, int maxiters, double ftol,
+                          double* x_out, double* f_init, double* f_end, int32_t* iters, int32_t* status,
+                          int64_t* n_feval, int64_t* n_geval) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "solve_cgd_csr before finalize");
+  if (nprobs <= 0 || !var_off || !fac_off) return ctx->fail(RDISGPU_ERR_ARG, "solve_cgd_csr: no problems");
+  if (nprobs >= 0x40000000LL) return ctx->fail(RDISGPU_ERR_ARG, "solve_cgd_csr: too many problems");
+  CK(cudaSetDevice(ctx->device));
+  rdisgpu_batch* b = scratch_batch(ctx);
+  ProblemsView pv;
+  pv.n = nprobs;
+  pv.var_off = var_off; pv.vids = vids; pv.fac_off = fac_off; pv.fids = fids;
+  int rc = batch_build(b, pv);
+  if (rc) return rc;
+  rc = rdisgpu_batch_solve_cgd(b, x0, maxiters, ftol);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemcpyAsync(b->h_res.p, b->res.p, (size_t)nprobs * sizeof(ResultRec), cudaMemcpyDeviceToHost, s));
+  if (x_out && b->total_nv > 0)
+    CK(cudaMemcpyAsync(b->h_x.p, b->xout.p, (size_t)b->total_nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (x_out && b->total_nv > 0) std::memcpy(x_out, b->h_x.p, (size_t)b->total_nv * sizeof(double));
+  for (int64_t p = 0; p < nprobs; ++p) {
+    const ResultRec& r = b->h_res.p[p];
+    if (f_init) f_init[p] = r.f_init;
+    if (f_end) f_end[p] = r.f_end;
+    if (iters) iters[p] = r.iters;
+    if (status) status[p] = r.status;
+    if (n_feval) n_feval[p] = (int64_t)r.n_value + r.n_slope;
+    if (n_geval) n_geval[p] = r.n_slope;
+  }
+  return RDISGPU_OK;
+}
+
+int rdisgpu_batch_info(const rdisgpu_batch* b, int32_t out[8]) {
+  if (!b || !out) return RDISGPU_ERR_ARG;
+  int n_generic = 0;
+  for (const auto& c : b->classes) n_generic += (int)c.count;
+  out[0] = (int32_t)b->nprobs;
+  out[1] = b->n_pt_warps;
+  out[2] = b->n_cam;
+  out[3] = b->cam_C;
+  out[4] = b->cam_T;
+  out[5] = n_generic;
+  out[6] = b->cam_nf_max;
+  out[7] = b->last_launches;
+  return RDISGPU_OK;
 }
 
 // ==========================================================================================
