@@ -139,7 +139,7 @@ def run_ours(args):
     x0_dev = torch.from_numpy(x0).to(dev)
     obj_dev = torch.zeros(1, dtype=torch.float64, device=dev)
     b_pts, b_cams = ctx.batch(pts), ctx.batch(cams)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def step_resident():
         obj_dev.zero_()
@@ -168,7 +168,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
-        flush.zero_()                     # untimed: evicts the previous step's working set from L2
+        flush.zero_()                     # untimed: evicts the previous step's working set from L2 ...
+        flush.sum()                       # ... and a read pass leaves clean lines (no write-backs inside the timing)
         ev[k][0].record(stream)
         obj_dev.zero_()
         ctx.set_x_device(x0_dev.data_ptr(), spec["V"])
@@ -247,7 +248,7 @@ def run_ours(args):
             "config": {"workload": "ladybug-49-7776-shaped BA graph (49 cams, 7776 pts, 31843 obs) per GPU: "
                                    "7776 point-component + 49 camera-component CGD solves per step",
                        "ssmaxit": MAXITERS, "ssftol": FTOL, "parallelism": "component-shard x%d" % world,
-                       "l2": "flushed between steps (256 MiB memset, untimed)", "seed": SEED,
+                       "l2": "flushed between steps (256 MiB memset + read pass, untimed)", "seed": SEED,
                        "mapping": {"points": b_pts.info(), "cameras": b_cams.info()}},
             "residual_evals_per_sec": resid_evals_per_s,
             "objective_after_step": objective,
@@ -276,38 +277,56 @@ def run_ours(args):
 
 
 def sweep_roofline(device, stream):
-    """Residual sweep (evalFactors over all factors) on the cfg4 sinusoid graph: 268.4 MB of
-    algorithmic bytes per launch (20 F + 21 E + 8 V), larger than L2, timed with CUDA events."""
+    """Residual sweep (evalFactors over all factors, every factor's value written back) and the
+    gradient sweep on the cfg4 sinusoid graph.  268.4 MB of algorithmic bytes per eval launch
+    (20 F + 21 E + 8 V) — larger than L2, and L2 is flushed between launches anyway.
+    Timed with CUDA events around the asynchronous device-pointer entry point (rdisgpu_eval_device):
+    nothing but the kernel is inside the events."""
     import torch
     from rdis_b200 import Context, problems as P
     spec = P.sinusoid(19, 2, 4)
     V, F, E = spec["V"], spec["F"], len(spec["vid"])
     ctx = Context.from_spec(spec, device=device, stream=stream.cuda_stream)
     ctx.set_x(P.random_start(spec, 1))
-    abytes = 20.0 * F + 21.0 * E + 8.0 * V
-    for _ in range(3):
-        s = ctx.eval()
-    times = []
-    for _ in range(10):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        lib_eval_async(ctx)
-        b.record(stream)
-        torch.cuda.synchronize()
-        times.append(a.elapsed_time(b))
-    ms = float(np.median(times))
+    dev = torch.device("cuda", device)
+    per_factor = torch.empty(F, dtype=torch.float64, device=dev)
+    total = torch.zeros(1, dtype=torch.float64, device=dev)
+    grad = torch.empty(V, dtype=torch.float64, device=dev)
+    flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     peak, peak_src = peaks()
+
+    def timed(fn, reps=12):
+        for _ in range(3):
+            fn()
+        times = []
+        for _ in range(reps):
+            flush.zero_()   # evict ...
+            flush.sum()     # ... then a read pass, so that no dirty lines are written back inside the timing
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        return float(np.mean(times)), float(np.min(times))
+
+    ms, ms_min = timed(lambda: ctx.eval_device(total.data_ptr(), per_factor.data_ptr()))
+    s = float(total.item())
+    assert abs(float(per_factor.sum().item()) - s) <= 1e-9 * abs(s)
+    abytes = 20.0 * F + 21.0 * E + 8.0 * V
     ach = abytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "eval_sweep_kernel<NlpfOps>", "workload": "sinusoid h=19 k=2 arity=4: V=%d F=%d E=%d" % (V, F, E),
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-            "algorithmic_bytes_per_launch": abytes, "launch_ms": ms, "factor_evals_per_sec": F / (ms * 1e-3),
-            "sum": s, "peak_source": peak_src}
-
-
-def lib_eval_async(ctx):
-    """One full residual sweep; the sum stays on the device until the caller synchronises
-    (rdisgpu_eval itself copies the sum back, so its D2H of 8 bytes rides inside the timing)."""
-    return ctx.eval()
+    out = {"bound": "hbm", "kernel": "nlpf_tile_sweep_kernel<false>", "workload": "sinusoid h=19 k=2 arity=4: V=%d F=%d E=%d" % (V, F, E),
+           "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+           "algorithmic_bytes_per_launch": abytes, "launch_ms": ms, "launch_ms_min": ms_min,
+           "factor_evals_per_sec": F / (ms * 1e-3), "sum": s, "peak_source": peak_src,
+           "l2": "flushed before every launch (256 MiB memset + read pass, untimed)"}
+    # eval + gradient: tile kernel writes the per-edge partials, the variable-major gather folds them
+    msg, msg_min = timed(lambda: ctx.grad_device(grad.data_ptr()))
+    gbytes = 20.0 * F + 21.0 * E + 16.0 * V
+    out["grad_sweep"] = {"kernels": "nlpf_tile_sweep_kernel<true> + gather_grad_kernel<NlpfOps>", "launch_ms": msg, "launch_ms_min": msg_min,
+                         "algorithmic_bytes": gbytes, "achieved": gbytes / (msg * 1e-3) / 1e9, "frac": gbytes / (msg * 1e-3) / 1e9 / peak,
+                         "unit": "GB/s", "grad_norm": float(grad.norm().item())}
+    return out
 
 
 def cpu_baseline(spec, pts, cams, x0, budget_s):

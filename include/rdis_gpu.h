@@ -120,6 +120,13 @@ RDISGPU_API int rdisgpu_eval(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, d
  * (src/OptimizableFunction.cpp:234-262, CGDSubspaceOptimizer.cpp:135-157): g[i] = d/dx_{vid[i]} sum_j f_j. */
 RDISGPU_API int rdisgpu_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, int64_t nv, const int32_t* vid,
                              double* g);
+/* The two sweeps with every pointer in DEVICE memory (int32 factor / variable ids, nullable = all):
+ * nothing is copied and the host does not wait — the call only enqueues kernels on the context's
+ * stream.  This is the form the roofline is measured on and the one a device-resident caller uses. */
+RDISGPU_API int rdisgpu_eval_device(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, double* sum_dev,
+                                    double* per_factor_dev);
+RDISGPU_API int rdisgpu_grad_device(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, int64_t nv,
+                                    const int32_t* vid_dev, double* g_dev);
 /* Factor::computeGradient for one factor list: rows[k*arity_max + s] = d f_{fid[k]} / d slot s. */
 RDISGPU_API int rdisgpu_factor_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, int32_t arity_max,
                                     double* rows);

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librdis_b200.so")
+LIB_PATH = os.environ.get("RDIS_B200_LIB", os.path.join(_HERE, "librdis_b200.so"))  # override: kernel experiments only
 
 DONE_NAMES = ("ftol", "gtol", "gg_zero", "maxiters", "dbrent_itmax", "empty", "nonfinite", "bracket_cap")
 
@@ -19,7 +19,7 @@ EXPORTS = (
     "rdisgpu_create", "rdisgpu_destroy", "rdisgpu_last_error", "rdisgpu_set_stream", "rdisgpu_synchronize", "rdisgpu_set_option",
     "rdisgpu_set_vars", "rdisgpu_add_nlpf", "rdisgpu_add_ba", "rdisgpu_finalize",
     "rdisgpu_set_x", "rdisgpu_get_x", "rdisgpu_set_factor_const",
-    "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_factor_grad",
+    "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_eval_device", "rdisgpu_grad_device", "rdisgpu_factor_grad",
     "rdisgpu_solve_cgd", "rdisgpu_solve_cgd_csr", "rdisgpu_batch_create", "rdisgpu_batch_create_csr", "rdisgpu_batch_info", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
     "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches",
     "rdisgpu_num_vars", "rdisgpu_num_factors", "rdisgpu_device_state", "rdisgpu_launch_count", "rdisgpu_version",
@@ -62,6 +62,8 @@ def load_library(path=LIB_PATH):
         "rdisgpu_set_factor_const": (C.c_int, [vp, i64, vp, vp, vp]),
         "rdisgpu_eval": (C.c_int, [vp, i64, vp, C.POINTER(dbl), vp]),
         "rdisgpu_grad": (C.c_int, [vp, i64, vp, i64, vp, vp]),
+        "rdisgpu_eval_device": (C.c_int, [vp, i64, vp, vp, vp]),
+        "rdisgpu_grad_device": (C.c_int, [vp, i64, vp, i64, vp, vp]),
         "rdisgpu_factor_grad": (C.c_int, [vp, i64, vp, i32, vp]),
         "rdisgpu_solve_cgd": (C.c_int, [vp, C.POINTER(Problem), i64, C.c_int, dbl, C.POINTER(Result)]),
         "rdisgpu_batch_create": (C.c_int, [vp, C.POINTER(Problem), i64, C.POINTER(vp)]),
@@ -253,6 +255,17 @@ class Context:
         g = np.empty(nv)
         self._ck(self._lib.rdisgpu_grad(self._h, self.F if f is None else len(f), _p(f), nv, _p(v), _p(g)))
         return g
+
+    def eval_device(self, sum_dev_ptr, per_factor_dev_ptr=None, fid_dev_ptr=None, nf=0):
+        """Asynchronous residual sweep, raw device pointers (None = all factors / no per-factor output)."""
+        self._ck(self._lib.rdisgpu_eval_device(self._h, nf, C.c_void_p(fid_dev_ptr) if fid_dev_ptr else None,
+                                               C.c_void_p(sum_dev_ptr) if sum_dev_ptr else None,
+                                               C.c_void_p(per_factor_dev_ptr) if per_factor_dev_ptr else None))
+
+    def grad_device(self, g_dev_ptr, vid_dev_ptr=None, nv=0, fid_dev_ptr=None, nf=0):
+        """Asynchronous gradient sweep, raw device pointers (None = all variables / all factors)."""
+        self._ck(self._lib.rdisgpu_grad_device(self._h, nf, C.c_void_p(fid_dev_ptr) if fid_dev_ptr else None, nv,
+                                               C.c_void_p(vid_dev_ptr) if vid_dev_ptr else None, C.c_void_p(g_dev_ptr)))
 
     def factor_grad(self, fid, arity_max):
         f = _arr(fid, np.int64)

@@ -1,0 +1,403 @@
+// nlpf_tile_sweep.cuh — the HBM-streaming form of the NonlinearProductFactor sweeps over ALL factors:
+//   nlpf_tile_sweep_kernel<false>   OptimizableFunction::evalFactors          src/OptimizableFunction.cpp:95-135
+//   nlpf_tile_sweep_kernel<true>    + Factor::computeGradient of every factor  src/NonlinearProductFactor.cpp:57-117
+//
+// The factor CSR is cut (on the host, at finalize) into TILES of consecutive factors whose edge rows
+// are one contiguous slice of the edge arrays: at most kTileFactors factors and kTileEdges edges.
+// The kernel is PERSISTENT (a few CTAs per SM, tiles dealt round-robin) and software-pipelined:
+//
+//   producer   a dedicated warp (one elected lane) streams the tile's six array slices — evid i32, expo f64, konst f64,
+//              sine u8 (21 B/edge), rowptr i32, coeff f64 (12 B/factor) — from HBM into a shared-memory
+//              stage with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx), kTileStages tiles
+//              ahead of the math (full / empty mbarrier ring).  No registers are spent on data in flight, so the bytes in flight per
+//              SM are set by the stage size (~28 KB x stages x CTAs/SM), not by occupancy.
+//   phase 1    (edge-parallel) thread t owns edges t, t+T, ... of the stage: the variable gather
+//              (L2-resident, 16 B/var) was put in flight one tile earlier; the thread parks the value term t_e = [sin]((x-k)^e) — with kGrad also
+//              its own-slot derivative — in shared memory.  The transcendental work is spread evenly
+//              over the threads whatever the arity mix of the tile.
+//   phase 2    (factor-parallel) thread t owns factors t, t+T, ...: folds the product from shared
+//              memory IN SLOT ORDER (the reference's loop order, NonlinearProductFactor.cpp:186-209),
+//              writes the value (coalesced) and accumulates it.
+// HBM sees each algorithmic byte once, as full-line bulk traffic.
+// Per-factor values are bit-identical to NlpfOps::value / NlpfOps::gradient (same expressions);
+// the grand total is folded in a fixed order (reproducible run to run on one device).
+#pragma once
+#include "factors.cuh"
+#include "sweep_kernels.cuh"
+
+namespace rdisgpu {
+
+// Tuning constants (the -D overrides exist for the sweeps recorded in profiles/; the defaults ship).
+#ifndef RDIS_TILE_THREADS
+#define RDIS_TILE_THREADS 256
+#endif
+#ifndef RDIS_TILE_EDGES
+#define RDIS_TILE_EDGES 512
+#endif
+#ifndef RDIS_TILE_FACTORS
+#define RDIS_TILE_FACTORS 512
+#endif
+#ifndef RDIS_TILE_STAGES
+#define RDIS_TILE_STAGES 4
+#endif
+#ifndef RDIS_TILE_CTAS
+#define RDIS_TILE_CTAS 3
+#endif
+constexpr int kTileThreads = RDIS_TILE_THREADS;   // consumer threads (one more warp is the TMA producer)
+constexpr int kTileEdges = RDIS_TILE_EDGES;
+constexpr int kTileFactors = RDIS_TILE_FACTORS;
+constexpr int kTileStages = RDIS_TILE_STAGES;
+constexpr int kTileCtasPerSm = RDIS_TILE_CTAS;
+constexpr int kEdgeBatch = kTileEdges / kTileThreads;  // gathers per thread per tile, issued one tile ahead
+
+// One tile: factors [f0, f1), edges [e0, e1).  e1 - e0 > kTileEdges marks a single over-wide factor
+// (folded serially from global memory; never produced by the reference's generators).
+struct TileDesc {
+  int32_t f0, f1, e0, e1;
+};
+
+// Shared-memory stage.  Bulk copies need 16-byte aligned source, destination and size, so a slice is
+// fetched from its start rounded down to 16 elements (edges) / 4 elements (factors) — the slack is
+// the +32 / +8 below — and the device arrays carry the same padding at their ends.
+struct TileStage {
+  double expo[kTileEdges + 32];
+  double konst[kTileEdges + 32];
+  double coeff[kTileFactors + 8];
+  int32_t evid[kTileEdges + 32];
+  int32_t rowptr[kTileFactors + 8];
+  uint8_t sine[kTileEdges + 32];
+  TileDesc desc;  // written by the producer before it arms the barrier: consumers never touch the descriptor array
+};
+static_assert(sizeof(TileStage) % 16 == 0, "stages must keep 16-byte alignment");
+
+struct TileSmem {
+  TileStage stage[kTileStages];
+  unsigned long long full[kTileStages];   // producer -> consumers: the stage's bytes have landed
+  unsigned long long empty[kTileStages];  // consumers -> producer: every consumer warp is done with the stage
+};
+
+// ---- PTX wrappers (mbarrier + TMA bulk copy) ----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t a = smem_addr_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+// producer-side wait: it is one thread with nothing else to do, so it sleeps between probes instead
+// of competing with the consumer warps for issue slots
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t a = smem_addr_u32(bar);
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(100);
+  }
+}
+// L2 policy of the streamed slices: evict-first, so that 268 MB of single-use stream does not push the
+// 17 MB of gathered variable values (re-used ~8 times each, loaded evict-last below) out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar,
+                                             uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_addr_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr_u32(bar)), "l"(policy)
+               : "memory");
+}
+// the variable gather: 16 B {value, direction slot}, kept in L2 with evict-last priority
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double2 gather_var_pair(const double2* p, uint64_t policy) {
+  double2 v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy));
+  return v;
+}
+
+// value term exactly as NlpfOps::value (no-slope path) computes it
+__device__ __forceinline__ double nlpf_term_value(double xv, double k, double ex, bool sn) {
+  double val = xv;
+  if (k != 0) val -= k;
+  if (ex != 1) val = rdis_power(val, ex);
+#ifndef RDIS_EXP_NOSIN
+  if (sn) val = sin(val);
+#endif
+  return val;
+}
+
+// value term + own-slot derivative exactly as NlpfOps::term computes them (plain slot: derivative 1,
+// and x * 1.0 == x to the bit, so the reference's "skip the multiplication" needs no flag)
+__device__ __forceinline__ void nlpf_term_grad(double xv, double k, double ex, bool sn, double& t, double& dt) {
+  double val = xv;
+  if (k != 0) val -= k;
+  if (ex != 1) val = rdis_power(val, ex);
+  if ((ex == 1) && !sn) {
+    t = val;
+    dt = 1.0;
+    return;
+  }
+  const double inner = xv - k;
+  const double innerexp = rdis_power(inner, ex);
+  double dv = rdis_power(inner, ex - 1.0);
+  dv *= ex;
+  if (sn) {
+    dv *= cos(innerexp);
+    t = sin(val);
+  } else {
+    t = val;
+  }
+  dt = dv;
+}
+
+// Producer: arm the stage's barrier with the byte count and launch the six bulk copies of tile `d`.
+__device__ __forceinline__ void tile_issue(const GraphView& G, const TileDesc d, TileStage& st, unsigned long long* bar,
+                                           uint64_t pol) {
+  const int ne = d.e1 - d.e0;
+  if (ne > kTileEdges) {  // over-wide factor: nothing to stage
+    mbar_arrive(bar);
+    return;
+  }
+  const int e_lo = d.e0 & ~15;
+  const uint32_t n_e = (uint32_t)((d.e1 - e_lo + 15) & ~15);
+  const int f_lo = d.f0 & ~3;
+  const uint32_t n_rp = (uint32_t)((d.f1 + 1 - f_lo + 3) & ~3);
+  const uint32_t n_cf = (uint32_t)((d.f1 - f_lo + 1) & ~1);
+  mbar_arrive_expect_tx(bar, n_e * 21u + n_rp * 4u + n_cf * 8u);
+  tma_bulk_g2s(st.expo, G.expo + e_lo, n_e * 8u, bar, pol);
+  tma_bulk_g2s(st.konst, G.konst + e_lo, n_e * 8u, bar, pol);
+  tma_bulk_g2s(st.evid, G.evid + e_lo, n_e * 4u, bar, pol);
+  tma_bulk_g2s(st.sine, G.sine + e_lo, n_e, bar, pol);
+  tma_bulk_g2s(st.rowptr, G.rowptr + f_lo, n_rp * 4u, bar, pol);
+  tma_bulk_g2s(st.coeff, G.coeff + f_lo, n_cf * 8u, bar, pol);
+}
+
+// Named barrier over the consumer warps only (the producer warp never joins it).
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTileThreads) : "memory"); }
+
+// Value of a gathered variable: frozen variables (direction slot NaN — every variable outside a
+// running solve) are used as stored; the others are clamped (load_var<false>).  Out of line on
+// purpose: the sweep never takes this path in steady state and it must not cost issue slots.
+__device__ __noinline__ double clamp_live_var(const GraphView& G, int32_t vid, double xv) {
+  return clamp_to_domain(xv, __ldg(&G.dom[vid]));
+}
+
+// Block layout: warps 0..kTileThreads/32-1 = consumers, one more warp = producer (one elected lane).
+// Terms are written IN PLACE over the stage's exponent slots (derivatives over the constant slots):
+// the thread that consumes expo[e] / konst[e] is the one that produces term[e], so the stage ring
+// doubles as the term buffer and a tile needs exactly one CTA-wide barrier.
+template <bool kGrad>
+__global__ void __launch_bounds__(kTileThreads + 32, kGrad ? 2 : kTileCtasPerSm)
+    nlpf_tile_sweep_kernel(GraphView G, const TileDesc* __restrict__ tiles, int ntiles, double* __restrict__ per_factor,
+                           double* partials, unsigned int* counter, double* sum_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int stride = gridDim.x;
+  const int my_tiles = (ntiles - (int)blockIdx.x + stride - 1) / stride;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTileStages; ++s) {
+      mbar_init(&S.full[s], 1);
+      mbar_init(&S.empty[s], kTileThreads / 32);  // one arrival per consumer warp
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  double acc = 0.0;
+  if (tid >= kTileThreads) {
+    // ---- producer warp: keeps kTileStages tiles in flight ahead of the consumers ----
+    // Descriptors are fetched 32 at a time (one per lane, the next batch already in flight), so the
+    // issue loop never waits on HBM for a descriptor; lane 0 issues the copies.
+    const int lane = tid & 31;
+    auto fetch = [&](int batch) {
+      const int i = batch * 32 + lane;
+      return tiles[(i < my_tiles) ? (blockIdx.x + i * stride) : 0];
+    };
+    TileDesc mine = fetch(0), ahead = fetch(1);
+    const uint64_t pol = l2_policy_evict_first();
+    for (int it = 0; it < my_tiles; ++it) {
+      if (it > 0 && (it & 31) == 0) {
+        mine = ahead;
+        ahead = fetch((it >> 5) + 1);
+      }
+      TileDesc d;
+      d.f0 = __shfl_sync(0xffffffffu, mine.f0, it & 31);
+      d.f1 = __shfl_sync(0xffffffffu, mine.f1, it & 31);
+      d.e0 = __shfl_sync(0xffffffffu, mine.e0, it & 31);
+      d.e1 = __shfl_sync(0xffffffffu, mine.e1, it & 31);
+      if (lane == 0) {
+        const int s = it % kTileStages;
+        if (it >= kTileStages) mbar_wait_backoff(&S.empty[s], (uint32_t)(it / kTileStages - 1) & 1u);  // stage released
+        S.stage[s].desc = d;
+        tile_issue(G, d, S.stage[s], &S.full[s], pol);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- consumers ----
+    const int lane = tid & 31;
+    int32_t vid[kEdgeBatch];
+    double2 xb[kEdgeBatch];
+    const uint64_t keep = l2_policy_evict_last();
+    // put the gathers of tile `j` (stage already landed) in flight
+    auto gather = [&](const TileStage& stg, const TileDesc& dd, int32_t (&v)[kEdgeBatch], double2 (&x)[kEdgeBatch]) {
+      const int n = dd.e1 - dd.e0, o = dd.e0 & 15;
+      if (n <= kTileEdges) {
+#pragma unroll
+        for (int i = 0; i < kEdgeBatch; ++i) {
+          const int le = i * kTileThreads + tid;
+          if (le < n) {
+            v[i] = stg.evid[o + le];
+#ifdef RDIS_EXP_NOGATHER
+            x[i] = make_double2((double)v[i], __longlong_as_double(0x7ff8000000000000LL));
+#else
+            x[i] = gather_var_pair(&G.xbd[v[i]], keep);
+#endif
+          }
+        }
+      }
+    };
+    mbar_wait(&S.full[0], 0u);
+    TileDesc d = S.stage[0].desc;
+    gather(S.stage[0], d, vid, xb);
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % kTileStages;
+      TileStage& st = S.stage[s];
+      const int ne = d.e1 - d.e0;
+      // ---- the next tile: wait for its stage and put its gathers in flight (hidden behind this tile's math) ----
+      TileDesc dn = d;
+      int32_t vid_n[kEdgeBatch];
+      double2 xb_n[kEdgeBatch];
+      if (it + 1 < my_tiles) {
+        const int sn = (it + 1) % kTileStages;
+        mbar_wait(&S.full[sn], (uint32_t)((it + 1) / kTileStages) & 1u);
+        dn = S.stage[sn].desc;
+        gather(S.stage[sn], dn, vid_n, xb_n);
+      }
+
+      if (ne > kTileEdges) {  // one over-wide factor, folded serially from global memory
+        if (tid == 0) {
+          double fv;
+          if (kGrad) {
+            fv = NlpfOps::gradient(G, d.f0, G.gedge + d.e0);
+          } else {
+            double sl;
+            fv = NlpfOps::value<false>(G, d.f0, 0.0, false, sl);
+          }
+          if (G.fconst_on != nullptr && G.fconst_on[d.f0]) fv = G.fconst_val[d.f0];
+          if (per_factor) per_factor[d.f0] = fv;
+          acc += fv;
+        }
+      } else {
+        // ---- phase 1: staged edge slices -> terms (in place) ----
+        double* term = st.expo + (d.e0 & 15);   // term[le] overwrites expo[le]
+        double* dterm = st.konst + (d.e0 & 15);  // dterm[le] overwrites konst[le]
+        const uint8_t* sine = st.sine + (d.e0 & 15);
+#pragma unroll
+        for (int i = 0; i < kEdgeBatch; ++i) {
+          const int le = i * kTileThreads + tid;
+          if (le < ne) {
+            double xv = xb[i].x;
+            if (xb[i].y == xb[i].y) xv = clamp_live_var(G, vid[i], xv);  // variable of a running solve
+            const double ex = term[le], kk = dterm[le];
+            const bool sn = sine[le] != 0;
+            if (kGrad) {
+              double tv, dt;
+              nlpf_term_grad(xv, kk, ex, sn, tv, dt);
+              term[le] = tv;
+              dterm[le] = dt;
+            } else {
+              term[le] = nlpf_term_value(xv, kk, ex, sn);
+            }
+          }
+        }
+        consumer_barrier();  // the only CTA-wide wait of a tile
+        // ---- phase 2: factors ----
+        const int fo = d.f0 & 3;
+        const int nfac = d.f1 - d.f0;
+        for (int lf = tid; lf < nfac; lf += kTileThreads) {
+          const int32_t f = d.f0 + lf;
+          const int r0 = st.rowptr[fo + lf] - d.e0;
+          const int n = st.rowptr[fo + lf + 1] - d.e0 - r0;
+          const double c = st.coeff[fo + lf];
+          double prod = 1.0;
+          if (n <= 4) {  // slot-order product, branch-free: a missing slot multiplies by 1.0 (exact)
+            const double t0 = (n > 0) ? term[r0] : 1.0, t1 = (n > 1) ? term[r0 + 1] : 1.0;
+            const double t2 = (n > 2) ? term[r0 + 2] : 1.0, t3 = (n > 3) ? term[r0 + 3] : 1.0;
+            prod = (((prod * t0) * t1) * t2) * t3;
+            if (kGrad) {  // getDerivative: product in slot order, own slot replaced by its derivative
+              const double d0 = (n > 0) ? dterm[r0] : 1.0, d1 = (n > 1) ? dterm[r0 + 1] : 1.0;
+              const double d2 = (n > 2) ? dterm[r0 + 2] : 1.0, d3 = (n > 3) ? dterm[r0 + 3] : 1.0;
+              double* ge = G.gedge + d.e0 + r0;
+              if (n > 0) ge[0] = ((((1.0 * d0) * t1) * t2) * t3) * c;
+              if (n > 1) ge[1] = ((((1.0 * t0) * d1) * t2) * t3) * c;
+              if (n > 2) ge[2] = ((((1.0 * t0) * t1) * d2) * t3) * c;
+              if (n > 3) ge[3] = ((((1.0 * t0) * t1) * t2) * d3) * c;
+            }
+          } else {
+            for (int r = r0; r < r0 + n; ++r) prod *= term[r];
+            if (kGrad) {
+              for (int i = r0; i < r0 + n; ++i) {
+                double pe = 1.0;
+                for (int j = r0; j < r0 + n; ++j) pe *= (j == i) ? dterm[j] : term[j];
+                G.gedge[d.e0 + i] = pe * c;
+              }
+            }
+          }
+          double fv = prod * c;
+          if (G.fconst_on != nullptr && G.fconst_on[f]) fv = G.fconst_val[f];  // Factor::eval, src/Factor.cpp:110-119
+          if (per_factor) __stcs(&per_factor[f], fv);  // streaming store: written once, not re-read by the sweep
+          acc += fv;
+        }
+      }
+      // this warp is done with stage s: release it to the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.empty[s]);
+      d = dn;
+#pragma unroll
+      for (int i = 0; i < kEdgeBatch; ++i) {
+        vid[i] = vid_n[i];
+        xb[i] = xb_n[i];
+      }
+    }
+  }
+  block_then_grid_sum(acc, partials, counter, sum_out);
+}
+
+}  // namespace rdisgpu

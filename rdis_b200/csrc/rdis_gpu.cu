@@ -15,6 +15,7 @@
 #include "ba_block_kernels.cuh"
 #include "solve_kernels.cuh"
 #include "sweep_kernels.cuh"
+#include "nlpf_tile_sweep.cuh"
 
 using namespace rdisgpu;
 
@@ -92,6 +93,8 @@ struct rdisgpu_ctx {
   // device residency
   DevBuf<double2> xbd, dom;
   DevBuf<int32_t> rowptr, evid, vrow, vedge, efac, cam, pt, crow, cfac, prow, pfac, fstamp;
+  DevBuf<TileDesc> tiles;  // NLPF: factor tiles of the streaming sweep (nlpf_tile_sweep.cuh)
+  int ntiles = 0, tile_grid[2] = {0, 0};  // persistent grid size of the eval / grad instantiation
   DevBuf<double> expo, konst, coeff, gedge, gvec, hvec, xsave, fconst_val;
   DevBuf<uint8_t> sine, fconst_on;
   DevBuf<double2> obs;
@@ -377,6 +380,19 @@ int rdisgpu_finalize(rdisgpu_ctx* ctx) {
       for (int32_t e = rp[j]; e < rp[j + 1]; ++e) efac[e] = (int32_t)j;
     std::vector<int32_t> vrow, vedge;
     build_incidence(V, ctx->h_evid, vrow, vedge);  // items = edge ids, ascending = ascending factor id
+    // the streamed arrays carry 32 elements of tail padding: bulk copies fetch 16-byte-aligned slices
+    CK(ctx->rowptr.ensure(rp.size() + 32));
+    CK(ctx->evid.ensure((size_t)E + 32));
+    CK(ctx->expo.ensure((size_t)E + 32));
+    CK(ctx->konst.ensure((size_t)E + 32));
+    CK(ctx->sine.ensure((size_t)E + 32));
+    CK(ctx->coeff.ensure((size_t)F + 32));
+    CK(cudaMemsetAsync(ctx->rowptr.p, 0, (rp.size() + 32) * sizeof(int32_t), s));
+    CK(cudaMemsetAsync(ctx->evid.p, 0, ((size_t)E + 32) * sizeof(int32_t), s));
+    CK(cudaMemsetAsync(ctx->expo.p, 0, ((size_t)E + 32) * sizeof(double), s));
+    CK(cudaMemsetAsync(ctx->konst.p, 0, ((size_t)E + 32) * sizeof(double), s));
+    CK(cudaMemsetAsync(ctx->sine.p, 0, (size_t)E + 32, s));
+    CK(cudaMemsetAsync(ctx->coeff.p, 0, ((size_t)F + 32) * sizeof(double), s));
     CK(upload(ctx->rowptr, rp.data(), rp.size(), s));
     CK(upload(ctx->evid, ctx->h_evid.data(), (size_t)E, s));
     CK(upload(ctx->expo, ctx->h_expo.data(), (size_t)E, s));
@@ -386,6 +402,30 @@ int rdisgpu_finalize(rdisgpu_ctx* ctx) {
     CK(upload(ctx->vrow, vrow.data(), vrow.size(), s));
     CK(upload(ctx->vedge, vedge.data(), vedge.size(), s));
     CK(upload(ctx->efac, efac.data(), efac.size(), s));
+    // factor tiles of the streaming sweep: consecutive factors, <= kTileFactors of them, <= kTileEdges edges
+    std::vector<TileDesc> tiles;
+    for (int64_t f = 0; f < F;) {
+      const int64_t eb = rp[f];
+      int64_t g = f;
+      while (g < F && g - f < kTileFactors && rp[g + 1] - eb <= kTileEdges) ++g;
+      if (g == f) g = f + 1;  // a single factor wider than a tile: folded serially
+      tiles.push_back(TileDesc{(int32_t)f, (int32_t)g, rp[f], rp[g]});
+      f = g;
+    }
+    ctx->ntiles = (int)tiles.size();
+    CK(upload(ctx->tiles, tiles.data(), tiles.size(), s));
+    // persistent grids: as many CTAs as fit, from the occupancy calculator (dynamic shared memory opt-in)
+    {
+      const int smem_e = (int)sizeof(TileSmem), smem_g = (int)sizeof(TileSmem);
+      CK(cudaFuncSetAttribute(nlpf_tile_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_e));
+      CK(cudaFuncSetAttribute(nlpf_tile_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
+      int occ_e = 0, occ_g = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, nlpf_tile_sweep_kernel<false>, kTileThreads + 32, smem_e));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, nlpf_tile_sweep_kernel<true>, kTileThreads + 32, smem_g));
+      if (occ_e < 1 || occ_g < 1) return ctx->fail(RDISGPU_ERR_CUDA, "streaming sweep kernel cannot be resident");
+      ctx->tile_grid[0] = std::min(ctx->ntiles, occ_e * ctx->sm_count);
+      ctx->tile_grid[1] = std::min(ctx->ntiles, occ_g * ctx->sm_count);
+    }
     CK(cudaStreamSynchronize(s));
   } else {
     std::vector<int32_t> crow, cfac, prow, pfac;
@@ -541,6 +581,30 @@ static int upload_fids(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, DevBuf<
   return RDISGPU_OK;
 }
 
+// Enqueues one residual sweep: fid_dev (device, nullable = all factors), per_factor_dev (device, nullable);
+// the total lands in *dsum_out (device scratch of the context).  No copies, no waiting.
+static int enqueue_eval(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, double* per_factor_dev, double** dsum_out) {
+  cudaStream_t s = ctx->stream;
+  const int threads = 256;
+  const bool tiled = (ctx->kind == KIND_NLPF && fid_dev == nullptr);
+  const int blocks = tiled ? ctx->tile_grid[0] : (int)std::min<int64_t>((nf + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
+  CK(ctx->s_partials.ensure((size_t)blocks + 1));
+  double* dsum = ctx->s_partials.p + blocks;
+  if (tiled)
+    nlpf_tile_sweep_kernel<false><<<blocks, kTileThreads + 32, sizeof(TileSmem), s>>>(
+        ctx->gv, ctx->tiles.p, ctx->ntiles, per_factor_dev, ctx->s_partials.p, ctx->s_counter.p, dsum);
+  else if (ctx->kind == KIND_NLPF)
+    eval_sweep_kernel<NlpfOps><<<blocks, threads, 0, s>>>(ctx->gv, fid_dev, nf, per_factor_dev, ctx->s_partials.p,
+                                                          ctx->s_counter.p, dsum);
+  else
+    eval_sweep_kernel<BaOps><<<blocks, threads, 0, s>>>(ctx->gv, fid_dev, nf, per_factor_dev, ctx->s_partials.p,
+                                                        ctx->s_counter.p, dsum);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  *dsum_out = dsum;
+  return RDISGPU_OK;
+}
+
 int rdisgpu_eval(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, double* sum, double* per_factor) {
   if (!ctx) return RDISGPU_ERR_ARG;
   if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "eval before finalize");
@@ -557,25 +621,73 @@ int rdisgpu_eval(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, double* sum, 
     if (rc) return rc;
   }
   if (per_factor) CK(ctx->s_f64a.ensure((size_t)nf));
-  const int threads = 256;
-  const int blocks = (int)std::min<int64_t>((nf + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
-  CK(ctx->s_partials.ensure((size_t)blocks + 1));
-  double* dsum = ctx->s_partials.p + blocks;
-  if (ctx->kind == KIND_NLPF)
-    eval_sweep_kernel<NlpfOps><<<blocks, threads, 0, s>>>(ctx->gv, fid ? ctx->s_i32a.p : nullptr, nf,
-                                                          per_factor ? ctx->s_f64a.p : nullptr, ctx->s_partials.p,
-                                                          ctx->s_counter.p, dsum);
-  else
-    eval_sweep_kernel<BaOps><<<blocks, threads, 0, s>>>(ctx->gv, fid ? ctx->s_i32a.p : nullptr, nf,
-                                                        per_factor ? ctx->s_f64a.p : nullptr, ctx->s_partials.p,
-                                                        ctx->s_counter.p, dsum);
-  ++ctx->launches;
-  CK(cudaGetLastError());
+  double* dsum = nullptr;
+  int rc = enqueue_eval(ctx, nf, fid ? ctx->s_i32a.p : nullptr, per_factor ? ctx->s_f64a.p : nullptr, &dsum);
+  if (rc) return rc;
   double hsum = 0.0;
   CK(cudaMemcpyAsync(&hsum, dsum, sizeof(double), cudaMemcpyDeviceToHost, s));
   if (per_factor) CK(cudaMemcpyAsync(per_factor, ctx->s_f64a.p, (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (sum) *sum = hsum;
+  return RDISGPU_OK;
+}
+
+int rdisgpu_eval_device(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, double* sum_dev, double* per_factor_dev) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "eval_device before finalize");
+  if (!fid_dev) nf = ctx->F;
+  if (nf <= 0) return ctx->fail(RDISGPU_ERR_ARG, "eval_device: bad argument");
+  if ((fid_dev && !is_device_ptr(fid_dev)) || (sum_dev && !is_device_ptr(sum_dev)) ||
+      (per_factor_dev && !is_device_ptr(per_factor_dev)))
+    return ctx->fail(RDISGPU_ERR_ARG, "eval_device: every pointer must be device memory");
+  CK(cudaSetDevice(ctx->device));
+  double* dsum = nullptr;
+  int rc = enqueue_eval(ctx, nf, fid_dev, per_factor_dev, &dsum);
+  if (rc) return rc;
+  if (sum_dev) CK(cudaMemcpyAsync(sum_dev, dsum, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return RDISGPU_OK;
+}
+
+// Enqueues computeGradient over a factor list: phase A writes every listed factor's partials to gedge
+// (the streaming tile kernel when the list is "all NLPF factors"), phase B gathers them per variable in
+// ascending factor id.  Device pointers only; no copies, no waiting.
+static int enqueue_grad(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, int64_t nv, const int32_t* vid_dev,
+                        double* g_dev) {
+  cudaStream_t s = ctx->stream;
+  const bool filter = (fid_dev != nullptr);
+  const int32_t stamp = 0x40000000;  // outside the range of batch problem indices
+  const int threads = 256;
+  if (nf > 0) {
+    if (ctx->kind == KIND_NLPF && !filter) {
+      const int tg = ctx->tile_grid[1];
+      CK(ctx->s_partials.ensure((size_t)tg + 1));
+      nlpf_tile_sweep_kernel<true><<<tg, kTileThreads + 32, sizeof(TileSmem), s>>>(
+          ctx->gv, ctx->tiles.p, ctx->ntiles, nullptr, ctx->s_partials.p, ctx->s_counter.p, ctx->s_partials.p + tg);
+    } else {
+      const int fb = (int)std::min<int64_t>((nf + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
+      if (ctx->kind == KIND_NLPF)
+        factor_partials_kernel<NlpfOps><<<fb, threads, 0, s>>>(ctx->gv, fid_dev, nf, filter ? stamp : -1);
+      else
+        factor_partials_kernel<BaOps><<<fb, threads, 0, s>>>(ctx->gv, fid_dev, nf, filter ? stamp : -1);
+    }
+    ++ctx->launches;
+    CK(cudaGetLastError());
+  }
+  const int vb = (int)std::min<int64_t>((nv + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
+  // with an explicit list an unlisted factor must not contribute; with nf == 0 nothing does
+  const bool eff_filter = filter || nf == 0;
+  if (ctx->kind == KIND_NLPF)
+    gather_grad_kernel<NlpfOps><<<vb, threads, 0, s>>>(ctx->gv, vid_dev, nv, stamp, eff_filter, g_dev);
+  else
+    gather_grad_kernel<BaOps><<<vb, threads, 0, s>>>(ctx->gv, vid_dev, nv, stamp, eff_filter, g_dev);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  if (filter && nf > 0) {
+    const int fb = (int)std::min<int64_t>((nf + threads - 1) / threads, 65535);
+    unstamp_kernel<<<fb, threads, 0, s>>>(ctx->gv, fid_dev, nf);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+  }
   return RDISGPU_OK;
 }
 
@@ -591,8 +703,6 @@ int rdisgpu_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, int64_t nv, c
       if (vid[i] < 0 || vid[i] >= ctx->V) return ctx->fail(RDISGPU_ERR_ARG, "grad: variable id out of range");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  const bool filter = (fid != nullptr);
-  const int32_t stamp = 0x40000000;  // outside the range of batch problem indices
   if (fid) {
     int rc = upload_fids(ctx, nf, fid, ctx->s_i32a);
     if (rc) return rc;
@@ -602,34 +712,24 @@ int rdisgpu_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, int64_t nv, c
     CK(cudaMemcpyAsync(ctx->s_i32b.p, vid, (size_t)nv * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   }
   CK(ctx->s_f64a.ensure((size_t)nv));
-  const int threads = 256;
-  if (nf > 0) {
-    const int fb = (int)std::min<int64_t>((nf + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
-    if (ctx->kind == KIND_NLPF)
-      factor_partials_kernel<NlpfOps><<<fb, threads, 0, s>>>(ctx->gv, fid ? ctx->s_i32a.p : nullptr, nf, filter ? stamp : -1);
-    else
-      factor_partials_kernel<BaOps><<<fb, threads, 0, s>>>(ctx->gv, fid ? ctx->s_i32a.p : nullptr, nf, filter ? stamp : -1);
-    ++ctx->launches;
-    CK(cudaGetLastError());
-  }
-  const int vb = (int)std::min<int64_t>((nv + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
-  // with an explicit list an unlisted factor must not contribute; with nf == 0 nothing does
-  const bool eff_filter = filter || nf == 0;
-  if (ctx->kind == KIND_NLPF)
-    gather_grad_kernel<NlpfOps><<<vb, threads, 0, s>>>(ctx->gv, vid ? ctx->s_i32b.p : nullptr, nv, stamp, eff_filter, ctx->s_f64a.p);
-  else
-    gather_grad_kernel<BaOps><<<vb, threads, 0, s>>>(ctx->gv, vid ? ctx->s_i32b.p : nullptr, nv, stamp, eff_filter, ctx->s_f64a.p);
-  ++ctx->launches;
-  CK(cudaGetLastError());
-  if (filter && nf > 0) {
-    const int fb = (int)std::min<int64_t>((nf + threads - 1) / threads, 65535);
-    unstamp_kernel<<<fb, threads, 0, s>>>(ctx->gv, ctx->s_i32a.p, nf);
-    ++ctx->launches;
-    CK(cudaGetLastError());
-  }
+  int rc = enqueue_grad(ctx, nf, fid ? ctx->s_i32a.p : nullptr, nv, vid ? ctx->s_i32b.p : nullptr, ctx->s_f64a.p);
+  if (rc) return rc;
   CK(cudaMemcpyAsync(g, ctx->s_f64a.p, (size_t)nv * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return RDISGPU_OK;
+}
+
+int rdisgpu_grad_device(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, int64_t nv, const int32_t* vid_dev,
+                        double* g_dev) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "grad_device before finalize");
+  if (!fid_dev) nf = ctx->F;
+  if (!vid_dev) nv = ctx->V;
+  if (nf < 0 || nv <= 0 || !g_dev) return ctx->fail(RDISGPU_ERR_ARG, "grad_device: bad argument");
+  if ((fid_dev && !is_device_ptr(fid_dev)) || (vid_dev && !is_device_ptr(vid_dev)) || !is_device_ptr(g_dev))
+    return ctx->fail(RDISGPU_ERR_ARG, "grad_device: every pointer must be device memory");
+  CK(cudaSetDevice(ctx->device));
+  return enqueue_grad(ctx, nf, fid_dev, nv, vid_dev, g_dev);
 }
 
 int rdisgpu_factor_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, int32_t arity_max, double* rows) {

@@ -93,6 +93,62 @@ def test_nlpf_general_terms(gpu, oracle_mod):
     assert (np.abs(g - go) <= 1e-11 * np.abs(go).max()).all()
 
 
+def test_streaming_tile_sweep_equals_list_sweep(gpu, oracle_mod):
+    """The all-factor sweeps run the streaming tile kernel (nlpf_tile_sweep.cuh), sweeps over an explicit
+    factor list run the thread-per-factor kernel: per-factor values and gradients must agree to the BIT
+    (same expressions), on a graph that exercises tile boundaries (arity classes of the sinusoid tree),
+    an over-wide factor (more edges than a tile holds), constants, and the device-pointer entry points."""
+    import torch
+    from rdis_b200 import Context, problems as P
+    spec = P.sinusoid(11, 2, 4)                      # V=4095, F=16364: several tiles per arity class
+    # append one factor over 2100 variables (wider than kTileEdges = 2048) and a run of arity-7 factors
+    rng = np.random.default_rng(11)
+    wide = rng.choice(spec["V"], size=2100, replace=False).astype(np.int32)
+    extra = [wide] + [rng.choice(spec["V"], size=7, replace=False).astype(np.int32) for _ in range(300)]
+    lens = np.array([len(e) for e in extra])
+    spec = dict(spec)
+    spec["vid"] = np.concatenate([spec["vid"]] + extra).astype(np.int32)
+    spec["rowptr"] = np.concatenate([spec["rowptr"], spec["rowptr"][-1] + np.cumsum(lens)])
+    ne = int(lens.sum())
+    spec["expo"] = np.concatenate([spec["expo"], rng.choice([1.0, 2.0, 3.0], size=ne)])
+    spec["konst"] = np.concatenate([spec["konst"], rng.choice([0.0, 0.4], size=ne)])
+    sn = rng.integers(0, 2, size=ne).astype(np.uint8); sn[:2100] = 1
+    spec["sine"] = np.concatenate([spec["sine"], sn])
+    spec["coeff"] = np.concatenate([spec["coeff"], rng.normal(0, 1, size=len(extra))])
+    spec["F"] = len(spec["coeff"])
+    x0 = P.random_start(spec, 5)
+    ctx = Context.from_spec(spec); ctx.set_x(x0)
+    allf = np.arange(spec["F"])
+    for use_const in (False, True):
+        if use_const:
+            ctx.set_factor_const(np.array([5, 9000, spec["F"] - 1]), np.array([1.5, -2.0, 0.25]), np.ones(3, np.uint8))
+        s_tile, pf_tile = ctx.eval(per_factor=True)
+        s_list, pf_list = ctx.eval(allf, per_factor=True)
+        assert np.array_equal(pf_tile, pf_list)
+        assert abs(s_tile - s_list) <= 1e-12 * abs(s_list)
+        assert np.array_equal(ctx.grad(), ctx.grad(fid=allf))
+    # against the oracle (without the constant overlay)
+    ctx2 = Context.from_spec(spec); ctx2.set_x(x0)
+    orc = oracle_mod.OracleFunction.from_spec(spec); orc.set_x(x0)
+    so, po = orc.eval(per_factor=True)
+    sg, pg = ctx2.eval(per_factor=True)
+    assert (np.abs(pg - po) <= 1e-12 * np.maximum(np.abs(po), 1e-300)).all()
+    g = ctx2.grad(); go = orc.grad()
+    assert (np.abs(g - go) <= 1e-11 * np.abs(go).max()).all()
+    # device-pointer entry points: same numbers, nothing copied
+    dev = torch.device("cuda", 0)
+    pf_d = torch.empty(spec["F"], dtype=torch.float64, device=dev)
+    tot_d = torch.zeros(1, dtype=torch.float64, device=dev)
+    g_d = torch.empty(spec["V"], dtype=torch.float64, device=dev)
+    ctx2.eval_device(tot_d.data_ptr(), pf_d.data_ptr())
+    ctx2.grad_device(g_d.data_ptr())
+    ctx2.synchronize()
+    assert np.array_equal(pf_d.cpu().numpy(), pg) and float(tot_d.item()) == sg
+    assert np.array_equal(g_d.cpu().numpy(), g)
+    # run-to-run reproducible total
+    assert ctx2.eval() == sg
+
+
 def _check_solves(r, o, tol=1e-6):
     rel = _relerr(r["f_end"], o["f_end"], 1e-12)
     assert rel.max() <= tol, (rel.max(), int(rel.argmax()))
