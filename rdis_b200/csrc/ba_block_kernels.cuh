@@ -279,7 +279,14 @@ __global__ void __launch_bounds__(32) solve_ba_points_kernel(GraphView Gv, Batch
 // ------------------------------------------------------------------------------------------
 // camera blocks
 // ------------------------------------------------------------------------------------------
-constexpr int kCamMaxThreads = 256;
+#ifndef RDIS_CAM_THREADS
+#define RDIS_CAM_THREADS 192
+#endif
+#ifndef RDIS_CAM_MIN_CTAS
+#define RDIS_CAM_MIN_CTAS 2
+#endif
+// 2 CTAs per SM at <= 168 registers: clusters can be wide enough for one observation per thread
+constexpr int kCamMaxThreads = RDIS_CAM_THREADS;
 constexpr int kCamMaxCluster = 8;
 constexpr int kCamMaxWarps = kCamMaxThreads / 32;
 constexpr int kCamRedWidth = 10;  // f + 9 partials (gradient mode); f + slope use the first two
@@ -328,7 +335,7 @@ __device__ __forceinline__ void cluster_allreduce(cooperative_groups::cluster_gr
 }
 
 // grid = nprobs * C CTAs, cluster = C CTAs (set at launch), `order` lists the camera-class problems.
-__global__ void __launch_bounds__(kCamMaxThreads) solve_ba_cameras_kernel(GraphView Gv, BatchView B, const int32_t* order,
+__global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_cameras_kernel(GraphView Gv, BatchView B, const int32_t* order,
                                                                           int C, int maxiters, double ftol) {
   namespace cgn = cooperative_groups;
   cgn::cluster_group cluster = cgn::this_cluster();

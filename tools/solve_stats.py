@@ -1,25 +1,41 @@
-"""Diagnostic (GPU box): per-class statistics of the bench workload's solves."""
-import os, sys, time
-import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from rdis_b200 import Context, problems as P
+"""Evaluation-count statistics of the bench step's two sibling batches (how long the serial chains are).
+usage: python tools/solve_stats.py"""
+import os
+import sys
 
-spec = P.ba_synthetic(seed=20260417)
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from rdis_b200 import Context, problems as P  # noqa: E402
+
+spec = P.ba_synthetic(seed=bench.SEED)
 x0 = spec["x0"]
+pts, cams = P.ba_point_problems(spec), P.ba_camera_problems(spec)
 ctx = Context.from_spec(spec)
-for name, ps in (("points", P.ba_point_problems(spec)), ("cameras", P.ba_camera_problems(spec))):
+for name, ps in (("points", pts), ("cameras", cams)):
     ctx.set_x(x0)
     b = ctx.batch(ps)
-    for _ in range(2):
-        ctx.set_x(x0); b.solve(None, 25, 3e-8); ctx.synchronize()
-    ctx.set_x(x0)
-    t0 = time.perf_counter(); b.solve(None, 25, 3e-8); ctx.synchronize(); dt = time.perf_counter() - t0
+    for _ in range(3):
+        ctx.set_x(x0)
+        b.solve(None, 25, 3e-8)
+    ctx.synchronize()
+    ts = []
+    for _ in range(5):
+        ctx.set_x(x0)
+        ctx.synchronize()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        b.solve(None, 25, 3e-8)
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(e))
     r = b.fetch()
-    nf = np.diff(ps.fac_off)
-    print(name, "n", ps.n, "ms %.3f" % (dt * 1e3), "nf min/med/max", nf.min(), np.median(nf), nf.max())
-    print("  n_feval mean %.1f max %d  n_geval mean %.1f  iters mean %.1f max %d" % (
-        r["n_feval"].mean(), r["n_feval"].max(), r["n_geval"].mean(), r["iters"].mean(), r["iters"].max()))
-    print("  status hist", np.bincount(r["status"], minlength=8))
-    print("  factor-evals total %.3e ; per ms %.3e" % ((r["n_feval"] * nf).sum(), (r["n_feval"] * nf).sum() / (dt * 1e3)))
-    if name == "cameras":
-        print("  per-problem: nf, n_feval", list(zip(nf.tolist(), r["n_feval"].tolist()))[:12])
+    nf, ng = r["n_feval"], r["n_geval"]
+    ms = float(np.median(ts))
+    print("%s: kernel %.3f ms; evals/problem mean %.1f max %d (with slope: mean %.1f max %d); iters mean %.1f max %d; "
+          "=> %.2f us per evaluation on the longest chain; status histogram %s" %
+          (name, ms, nf.mean(), nf.max(), ng.mean(), ng.max(), r["iters"].mean(), r["iters"].max(), ms * 1e3 / nf.max(),
+           np.bincount(r["status"], minlength=8).tolist()))
