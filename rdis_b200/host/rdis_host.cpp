@@ -1,0 +1,454 @@
+// rdis_host.cpp — see rdis_host.h.  Everything that evaluates a factor calls the C-ABI of
+// include/rdis_gpu.h; nothing here computes a factor value on the host.
+#include "rdis_host.h"
+
+#include <algorithm>
+#include <cassert>
+#include <iostream>
+#include <numeric>
+
+#include "../../include/rdis_gpu.h"
+
+namespace rdis {
+
+// ------------------------------------------------------------------------------------------
+// Variable / Factor
+// ------------------------------------------------------------------------------------------
+void Variable::assign(Numeric newval, bool notifyFactors) {  // src/Variable.cpp:66-88
+  if (m_isAssigned) {
+    // The reference skips the cache-invalidation fan-out when |new - old| <= 1e-12 but still stores the
+    // new value (:69-78, :87).  The device keeps no per-factor cache, so only the value matters.
+    if (notifyFactors && newval != m_value)
+      for (Factor* f : m_factors) f->onVarChanged(m_id, m_value, newval);
+  } else {
+    m_isAssigned = true;
+    if (notifyFactors)
+      for (Factor* f : m_factors) f->onVarAssigned(m_id, newval);
+  }
+  m_value = newval;
+  if (m_owner) m_owner->noteAssigned(m_id);  // queued for the next host->device flush
+}
+
+void Variable::unassign() {  // src/Variable.cpp:90-102
+  if (!m_isAssigned) throw std::logic_error("Variable::unassign on an unassigned variable");
+  m_isAssigned = false;
+  for (Factor* f : m_factors) f->onVarUnassigned(m_id, m_value);
+  m_value = 0;
+}
+
+void Factor::assign(Numeric fval, VariableID assignmentKey) {
+  isAssignedConstant = true;
+  vidAssigned = assignmentKey;
+  assignedVal = fval;
+  if (m_owner) m_owner->noteFactorConst(this);
+}
+
+void Factor::unassign(VariableID assignmentKey) {
+  if (!isAssignedConstant || vidAssigned != assignmentKey) throw std::logic_error("Factor::unassign: wrong assignment key");
+  isAssignedConstant = false;
+  vidAssigned = -1;
+  if (m_owner) m_owner->noteFactorConst(this);
+}
+
+// ------------------------------------------------------------------------------------------
+// OptimizableFunction
+// ------------------------------------------------------------------------------------------
+OptimizableFunction::OptimizableFunction() : kind(-1), ncams(0), npts(0), ctx(nullptr) {}
+
+OptimizableFunction::~OptimizableFunction() {
+  if (ctx) rdisgpu_destroy(ctx);
+  for (Factor* f : factors) delete f;
+  for (Variable* v : variables) delete v;
+}
+
+void OptimizableFunction::check(int rc, const char* what) const {
+  if (rc == RDISGPU_OK) return;
+  std::string msg = std::string(what) + ": " + rdisgpu_last_error(ctx);
+  throw std::runtime_error(msg);
+}
+
+Variable* OptimizableFunction::addVariable(Numeric lb, Numeric ub) {
+  if (ctx) throw std::logic_error("addVariable after init");
+  Variable* v = new Variable((VariableID)variables.size(), VariableDomain(lb, ub));
+  v->m_owner = this;
+  variables.push_back(v);
+  return v;
+}
+
+NonlinearProductFactor* OptimizableFunction::addProductFactor(Numeric coefficient) {
+  if (ctx) throw std::logic_error("addProductFactor after init");
+  if (kind == Factor::BUNDLE_ADJUSTMENT) throw std::logic_error("one factor family per function");
+  kind = Factor::NONLINEAR_PRODUCT;
+  NonlinearProductFactor* f = new NonlinearProductFactor((FactorID)factors.size(), coefficient);
+  f->m_owner = this;
+  factors.push_back(f);
+  return f;
+}
+
+void OptimizableFunction::declareBundleAdjustment(int32_t ncams_, int32_t npts_) {
+  if (kind == Factor::NONLINEAR_PRODUCT) throw std::logic_error("one factor family per function");
+  if ((VariableCount)variables.size() != 9LL * ncams_ + 3LL * npts_)
+    throw std::logic_error("declareBundleAdjustment: expected 9*ncams + 3*npts variables");
+  kind = Factor::BUNDLE_ADJUSTMENT;
+  ncams = ncams_;
+  npts = npts_;
+}
+
+BundleAdjustmentFactor* OptimizableFunction::addObservation(int32_t cam, int32_t pt, Numeric obsx, Numeric obsy) {
+  if (ctx) throw std::logic_error("addObservation after init");
+  if (kind != Factor::BUNDLE_ADJUSTMENT) throw std::logic_error("declareBundleAdjustment first");
+  if (cam < 0 || cam >= ncams || pt < 0 || pt >= npts) throw std::out_of_range("addObservation: camera / point id");
+  BundleAdjustmentFactor* f = new BundleAdjustmentFactor((FactorID)factors.size(), cam, pt, obsx, obsy);
+  f->m_owner = this;
+  for (int p = 0; p < 9; ++p) f->addVariable(variables[9LL * cam + p]);                // getCamVID
+  for (int d = 0; d < 3; ++d) f->addVariable(variables[9LL * ncams + 3LL * pt + d]);   // getPointVID
+  factors.push_back(f);
+  return f;
+}
+
+void OptimizableFunction::init(int device) {
+  if (ctx) throw std::logic_error("OptimizableFunction::init called twice");
+  if (variables.empty() || factors.empty() || kind < 0) throw std::logic_error("init: empty function");
+  int rc = rdisgpu_create(&ctx, device);
+  if (rc != RDISGPU_OK) {
+    ctx = nullptr;
+    throw std::runtime_error(std::string("rdisgpu_create: ") + rdisgpu_last_error(nullptr) + " (no CPU fallback)");
+  }
+  const int64_t V = (int64_t)variables.size(), F = (int64_t)factors.size();
+  std::vector<double> lb(V), ub(V);
+  for (int64_t i = 0; i < V; ++i) {
+    lb[i] = variables[i]->getDomain().min();
+    ub[i] = variables[i]->getDomain().max();
+  }
+  check(rdisgpu_set_vars(ctx, V, lb.data(), ub.data()), "rdisgpu_set_vars");
+  if (kind == Factor::NONLINEAR_PRODUCT) {
+    std::vector<int64_t> rowptr(F + 1, 0);
+    std::vector<double> coeff(F);
+    for (int64_t j = 0; j < F; ++j) rowptr[j + 1] = rowptr[j] + (int64_t)factors[j]->numVars();
+    const int64_t E = rowptr[F];
+    std::vector<int32_t> vid(E);
+    std::vector<double> expo(E), konst(E);
+    std::vector<uint8_t> sine(E);
+    for (int64_t j = 0; j < F; ++j) {
+      const NonlinearProductFactor* nf = static_cast<const NonlinearProductFactor*>(factors[j]);
+      coeff[j] = nf->getCoefficient();
+      for (size_t s = 0; s < nf->numVars(); ++s) {
+        const int64_t e = rowptr[j] + (int64_t)s;
+        vid[e] = (int32_t)nf->getVariables()[s]->getID();
+        expo[e] = nf->getTerms()[s].exponent;
+        konst[e] = nf->getTerms()[s].constant;
+        sine[e] = nf->getTerms()[s].useSine ? 1 : 0;
+      }
+    }
+    check(rdisgpu_add_nlpf(ctx, F, rowptr.data(), vid.data(), expo.data(), konst.data(), sine.data(), coeff.data()),
+          "rdisgpu_add_nlpf");
+  } else {
+    std::vector<int32_t> cam(F), pt(F);
+    std::vector<double> obs(2 * F);
+    for (int64_t j = 0; j < F; ++j) {
+      const BundleAdjustmentFactor* bf = static_cast<const BundleAdjustmentFactor*>(factors[j]);
+      cam[j] = bf->getCamera();
+      pt[j] = bf->getPoint();
+      obs[2 * j] = bf->obsX();
+      obs[2 * j + 1] = bf->obsY();
+    }
+    check(rdisgpu_add_ba(ctx, F, cam.data(), pt.data(), obs.data(), ncams, npts), "rdisgpu_add_ba");
+  }
+  check(rdisgpu_finalize(ctx), "rdisgpu_finalize");
+  dirtyFlag.assign((size_t)V, 0);
+  dirtyVids.clear();
+  for (Variable* v : variables)
+    if (v->isAssigned()) noteAssigned(v->getID());
+  for (Factor* f : factors)
+    if (f->isAssigned()) dirtyFactors.push_back(f);
+}
+
+void OptimizableFunction::noteAssigned(VariableID vid) {
+  if (dirtyFlag.empty()) return;  // before init: init() collects every assigned variable
+  if (!dirtyFlag[(size_t)vid]) {
+    dirtyFlag[(size_t)vid] = 1;
+    dirtyVids.push_back((int32_t)vid);
+  }
+}
+
+void OptimizableFunction::noteFactorConst(Factor* f) {
+  if (!ctx) return;
+  dirtyFactors.push_back(f);
+}
+
+void OptimizableFunction::flushAssignments() {
+  if (!ctx) throw std::logic_error("flushAssignments before init");
+  if (!dirtyVids.empty()) {
+    std::vector<double> x(dirtyVids.size());
+    size_t n = 0;
+    for (int32_t vid : dirtyVids) {
+      dirtyFlag[(size_t)vid] = 0;
+      if (!variables[(size_t)vid]->isAssigned()) continue;  // unassigned again since: its value is never read
+      dirtyVids[n] = vid;
+      x[n] = variables[(size_t)vid]->m_value;
+      ++n;
+    }
+    if (n) check(rdisgpu_set_x(ctx, (int64_t)n, dirtyVids.data(), x.data()), "rdisgpu_set_x");
+    dirtyVids.clear();
+  }
+  if (!dirtyFactors.empty()) {
+    std::vector<int64_t> fid;
+    std::vector<double> val;
+    std::vector<uint8_t> on;
+    for (Factor* f : dirtyFactors) {
+      fid.push_back(f->getID());
+      val.push_back(f->assignedVal);
+      on.push_back(f->isAssigned() ? 1 : 0);
+    }
+    check(rdisgpu_set_factor_const(ctx, (int64_t)fid.size(), fid.data(), val.data(), on.data()), "rdisgpu_set_factor_const");
+    dirtyFactors.clear();
+  }
+}
+
+Numeric OptimizableFunction::eval() {
+  Numeric ferr = 0;
+  return evalFactors(factors, ferr);
+}
+
+Numeric OptimizableFunction::evalFactors(const FactorPtrVec& fctrs, Numeric& ferr) {
+  ferr = 0;  // no partial simplification on this path (approxfactors error is tracked by the tree search)
+  if (fctrs.empty()) return 0;
+  flushAssignments();
+  double sum = 0;
+  if (&fctrs == &factors) {
+    check(rdisgpu_eval(ctx, 0, nullptr, &sum, nullptr), "rdisgpu_eval");
+    return sum;
+  }
+  // the reference skips factors that are not fully assigned (src/OptimizableFunction.cpp:108-112)
+  std::vector<int64_t> fid;
+  fid.reserve(fctrs.size());
+  for (const Factor* fp : fctrs)
+    if (fp->areAllVarsAssigned() || fp->isAssigned()) fid.push_back(fp->getID());
+  if (fid.empty()) return 0;
+  check(rdisgpu_eval(ctx, (int64_t)fid.size(), fid.data(), &sum, nullptr), "rdisgpu_eval");
+  return sum;
+}
+
+void OptimizableFunction::computeGradient(const FactorPtrVec& facs, const VariablePtrVec& vars, NumericVec& gradient) {
+  gradient.assign(vars.size(), 0.0);
+  if (vars.empty()) return;
+  flushAssignments();
+  std::vector<int64_t> fid(facs.size());
+  std::vector<int32_t> vid(vars.size());
+  for (size_t i = 0; i < facs.size(); ++i) fid[i] = facs[i]->getID();
+  for (size_t i = 0; i < vars.size(); ++i) vid[i] = (int32_t)vars[i]->getID();
+  // a non-null pointer with nf == 0 means "no factors" (null would mean "all factors")
+  static const int64_t none = 0;
+  check(rdisgpu_grad(ctx, (int64_t)fid.size(), fid.empty() ? &none : fid.data(), (int64_t)vid.size(), vid.data(), gradient.data()),
+        "rdisgpu_grad");
+}
+
+// ------------------------------------------------------------------------------------------
+// SubspaceOptimizer
+// ------------------------------------------------------------------------------------------
+SubspaceOptimizer::SubspaceOptimizer(OptimizableFunction& f_)
+    : f(f_), doAscent(!f_.isMinSum()), maxiters(50), ftol(3.0e-8) {  // src/SubspaceOptimizer.cpp:12-18
+  if (doAscent) throw "only the MinSum semiring is supported";           // src/RDISOptimizer.cpp:57-61
+}
+
+void SubspaceOptimizer::setParameters(const ParameterMap& options) {  // src/SubspaceOptimizer.cpp:22-35
+  if (options.count("SSmaxit")) maxiters = (size_t)options.at("SSmaxit");
+  if (options.count("SSftol")) ftol = options.at("SSftol");
+  if (maxiters == 0) throw std::invalid_argument("SSmaxit must be positive");
+}
+
+void SubspaceOptimizer::quickAssignVals(const VariablePtrVec& vars, const NumericVec& xval, bool sanitizeVals) {
+  assert(vars.size() == xval.size());  // src/SubspaceOptimizer.cpp:38-53
+  for (size_t i = 0; i < vars.size(); ++i) {
+    Numeric val = sanitizeVals ? vars[i]->getDomain().closestVal(xval[i]) : xval[i];
+    if (val != xval[i]) std::cout << "var " << vars[i]->getID() << " xval " << xval[i] << " changed to " << val << std::endl;
+    vars[i]->assign(val);
+    f.onVarAssigned(vars[i]->getID(), val);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CudaSubspaceOptimizer
+// ------------------------------------------------------------------------------------------
+Numeric CudaSubspaceOptimizer::optimize(const VariablePtrVec& vars, const FactorPtrVec& gdfs, NumericVec& xval,
+                                        Numeric& deltaFval, const bool printdbg) {
+  assert(xval.size() == vars.size());
+  if (gdfs.empty()) {  // src/optimizers/CGDSubspaceOptimizer.cpp:26-29
+    deltaFval = 0;
+    return 0;
+  }
+  std::vector<ComponentProblem> one(1);
+  one[0].vars = vars;
+  one[0].factors = gdfs;
+  one[0].xval = xval;
+  optimizeBatch(one, printdbg);
+  xval = one[0].xval;
+  deltaFval = one[0].deltaFval;
+  return one[0].fval;
+}
+
+Numeric CudaSubspaceOptimizer::optimizeBatch(std::vector<ComponentProblem>& problems, const bool printdbg) {
+  const int64_t n = (int64_t)problems.size();
+  if (n == 0) return 0;
+  var_off.assign(1, 0);
+  fac_off.assign(1, 0);
+  vids.clear();
+  fids.clear();
+  x0.clear();
+  for (ComponentProblem& p : problems) {
+    if (p.xval.size() != p.vars.size()) throw std::invalid_argument("optimizeBatch: xval / vars size mismatch");
+    for (size_t i = 0; i < p.vars.size(); ++i) {
+      vids.push_back((int32_t)p.vars[i]->getID());
+      x0.push_back(p.xval[i]);  // the device clamps start values into the domain (quickAssignVals(vars, xval, true), CGD.cpp:33)
+    }
+    for (const Factor* fp : p.factors) fids.push_back(fp->getID());
+    var_off.push_back((int64_t)vids.size());
+    fac_off.push_back((int64_t)fids.size());
+  }
+  // every other variable the factors read must be current on the device
+  f.flushAssignments();
+  xout.resize(vids.size());
+  finit.resize((size_t)n);
+  fend.resize((size_t)n);
+  iters.resize((size_t)n);
+  status.resize((size_t)n);
+  nfe.resize((size_t)n);
+  nge.resize((size_t)n);
+  f.check(rdisgpu_solve_cgd_csr(f.device(), n, var_off.data(), vids.data(), fac_off.data(), fids.data(), x0.data(), (int)maxiters,
+                                ftol, xout.data(), finit.data(), fend.data(), iters.data(), status.data(), nfe.data(), nge.data()),
+          "rdisgpu_solve_cgd_csr");
+  Numeric total = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    ComponentProblem& p = problems[(size_t)k];
+    if (status[(size_t)k] == RDISGPU_DONE_EMPTY) {  // nothing to optimise: xval untouched, returns 0 (CGD.cpp:26-29)
+      p.fval = 0;
+      p.deltaFval = 0;
+      p.iters = 0;
+      p.status = status[(size_t)k];
+      continue;
+    }
+    for (size_t i = 0; i < p.vars.size(); ++i) {
+      const Numeric v = xout[(size_t)var_off[(size_t)k] + i];
+      p.xval[i] = v;
+      Variable* var = p.vars[i];
+      if (!var->isAssigned()) {
+        var->assign(v);  // factor bookkeeping (assigned counts); the queued upload is dropped below
+      }
+      var->setFromDevice(v);  // the solve committed the value on the device (CGD.cpp:61,84-86)
+      f.onVarAssigned(var->getID(), v);
+    }
+    p.fval = fend[(size_t)k];
+    p.deltaFval = fend[(size_t)k] - finit[(size_t)k];
+    p.iters = iters[(size_t)k];
+    p.status = status[(size_t)k];
+    total += p.fval;
+    if (printdbg)
+      std::cout << "CUDA CGD subspace result (steps " << p.iters << "): " << p.fval << ", diff: " << p.deltaFval
+                << ", init: " << finit[(size_t)k] << std::endl;
+  }
+  // values written by the solve are already resident: drop their queued uploads
+  for (int32_t vid : f.dirtyVids) f.dirtyFlag[(size_t)vid] = 0;
+  f.dirtyVids.clear();
+  return total;
+}
+
+// ------------------------------------------------------------------------------------------
+// ComponentBatcher
+// ------------------------------------------------------------------------------------------
+namespace {
+struct DisjointSets {
+  std::vector<int64_t> parent;
+  explicit DisjointSets(size_t n) : parent(n) { std::iota(parent.begin(), parent.end(), (int64_t)0); }
+  int64_t find(int64_t a) {
+    while (parent[(size_t)a] != a) {
+      parent[(size_t)a] = parent[(size_t)parent[(size_t)a]];
+      a = parent[(size_t)a];
+    }
+    return a;
+  }
+  void unite(int64_t a, int64_t b) {
+    a = find(a);
+    b = find(b);
+    if (a != b) parent[(size_t)std::max(a, b)] = std::min(a, b);  // root = smallest vertex: deterministic labels
+  }
+};
+}  // namespace
+
+void ComponentBatcher::createChildren(const OptimizableFunction& func, const VariableIDVec& componentVars,
+                                      std::vector<ChildComponent>& children) {
+  children.clear();
+  OptimizableFunction& fn = const_cast<OptimizableFunction&>(func);
+  const VariablePtrVec& vars = fn.getVariables();
+  const FactorPtrVec& facs = func.getFactors();
+  const int64_t V = (int64_t)vars.size(), F = (int64_t)facs.size();
+  // vertices: variables 0..V-1, factors V..V+F-1 (ConnectivityGraph's vertex numbering)
+  DisjointSets ds((size_t)(V + F));
+  std::vector<uint8_t> inComp((size_t)V, 0);
+  for (VariableID vid : componentVars)
+    if (!vars[(size_t)vid]->isAssigned()) inComp[(size_t)vid] = 1;
+  std::vector<uint8_t> factorSeen((size_t)F, 0);
+  for (VariableID vid : componentVars) {
+    if (!inComp[(size_t)vid]) continue;
+    for (const Factor* fp : vars[(size_t)vid]->getFactors()) {
+      if (fp->isAssigned()) continue;  // an assigned factor has no edges (onFactorAssigned, ConnectivityGraph.cpp:258-271)
+      ds.unite(vid, V + fp->getID());
+      factorSeen[(size_t)fp->getID()] = 1;
+    }
+  }
+  // edges to unassigned variables outside `componentVars` cannot exist for a proper component; a
+  // factor reaching one would make the caller's set not closed — include such variables defensively
+  // is NOT done: the reference asserts closure implicitly through its connectivity graph.
+  std::map<int64_t, size_t> rootToChild;
+  for (VariableID vid : componentVars) {
+    if (!inComp[(size_t)vid]) continue;
+    const int64_t r = ds.find(vid);
+    auto it = rootToChild.find(r);
+    if (it == rootToChild.end()) {
+      it = rootToChild.emplace(r, children.size()).first;
+      children.emplace_back();
+    }
+    children[it->second].vars.push_back(vid);
+  }
+  for (FactorID fid = 0; fid < F; ++fid) {
+    if (!factorSeen[(size_t)fid]) continue;
+    const int64_t r = ds.find(V + fid);
+    children[rootToChild.at(r)].factors.push_back(fid);
+  }
+  for (ChildComponent& c : children) {
+    std::sort(c.vars.begin(), c.vars.end());
+    std::sort(c.factors.begin(), c.factors.end());
+  }
+  std::stable_sort(children.begin(), children.end(), [](const ChildComponent& a, const ChildComponent& b) {
+    if (a.vars.size() != b.vars.size()) return a.vars.size() < b.vars.size();
+    return a.vars.front() < b.vars.front();
+  });
+}
+
+void ComponentBatcher::leafProblem(OptimizableFunction& func, const ChildComponent& child, const NumericVec& fallback,
+                                   ComponentProblem& out) {
+  VariablePtrVec& vars = func.getVariables();
+  const FactorPtrVec& facs = func.getFactors();
+  out.vars.clear();
+  out.factors.clear();
+  out.xval.clear();
+  std::vector<uint8_t> mine;  // membership of the child's variables, by position in a sorted list
+  for (VariableID vid : child.vars) {
+    Variable* v = vars[(size_t)vid];
+    out.vars.push_back(v);
+    out.xval.push_back(v->isAssigned() ? v->eval() : fallback.at((size_t)vid));
+  }
+  for (FactorID fid : child.factors) {
+    const Factor* fp = facs[(size_t)fid];
+    bool ready = true;  // every variable is either assigned or about to be (a variable of this problem)
+    for (const Variable* v : fp->getVariables()) {
+      if (v->isAssigned()) continue;
+      if (!std::binary_search(child.vars.begin(), child.vars.end(), v->getID())) {
+        ready = false;
+        break;
+      }
+    }
+    if (ready) out.factors.push_back(const_cast<Factor*>(fp));
+  }
+}
+
+}  // namespace rdis

@@ -1,0 +1,154 @@
+// host_driver.cpp — native test driver for the C++ host layer (rdis_b200/host/rdis_host.h).
+// Reads a problem written by tests/test_host_adapter.py (flat little-endian arrays), builds the
+// reference-shaped object graph (Variable / Factor / OptimizableFunction), and runs one of:
+//   children <file>            ComponentBatcher::createChildren over the unassigned variables (no GPU needed)
+//   wave <file> <maxiters>     one sibling wave through CudaSubspaceOptimizer::optimizeBatch
+//   single <file> <maxiters>   the same wave, one CudaSubspaceOptimizer::optimize call per child
+//                              (the reference's sibling loop, src/RDISOptimizer.cpp:291-314)
+// Output is plain text with %.17g numbers; the Python side compares it with the ctypes path and the oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+
+#include "rdis_host.h"
+
+using namespace rdis;
+
+namespace {
+template <class T>
+std::vector<T> rd(std::ifstream& in, size_t n) {
+  std::vector<T> v(n);
+  in.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(n * sizeof(T)));
+  if (!in) throw std::runtime_error("short read");
+  return v;
+}
+
+struct Loaded {
+  std::unique_ptr<OptimizableFunction> fn;
+  std::vector<double> x0;
+  std::vector<uint8_t> assigned;
+};
+
+Loaded load(const char* path) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in) throw std::runtime_error("cannot open problem file");
+  auto hdr = rd<int64_t>(in, 6);
+  const int64_t kind = hdr[0], V = hdr[1], F = hdr[2], E = hdr[3], ncams = hdr[4], npts = hdr[5];
+  auto lb = rd<double>(in, (size_t)V), ub = rd<double>(in, (size_t)V);
+  Loaded L;
+  L.fn.reset(new OptimizableFunction());
+  for (int64_t i = 0; i < V; ++i) L.fn->addVariable(lb[(size_t)i], ub[(size_t)i]);
+  if (kind == 0) {
+    auto rowptr = rd<int64_t>(in, (size_t)F + 1);
+    auto vid = rd<int32_t>(in, (size_t)E);
+    auto expo = rd<double>(in, (size_t)E), konst = rd<double>(in, (size_t)E);
+    auto sine = rd<uint8_t>(in, (size_t)E);
+    auto coeff = rd<double>(in, (size_t)F);
+    for (int64_t j = 0; j < F; ++j) {
+      NonlinearProductFactor* f = L.fn->addProductFactor(coeff[(size_t)j]);
+      for (int64_t e = rowptr[(size_t)j]; e < rowptr[(size_t)j + 1]; ++e)
+        f->addVariable(L.fn->getVariables()[(size_t)vid[(size_t)e]], expo[(size_t)e], konst[(size_t)e], sine[(size_t)e] != 0);
+    }
+  } else {
+    auto cam = rd<int32_t>(in, (size_t)F), pt = rd<int32_t>(in, (size_t)F);
+    auto obs = rd<double>(in, 2 * (size_t)F);
+    L.fn->declareBundleAdjustment((int32_t)ncams, (int32_t)npts);
+    for (int64_t j = 0; j < F; ++j) L.fn->addObservation(cam[(size_t)j], pt[(size_t)j], obs[2 * (size_t)j], obs[2 * (size_t)j + 1]);
+  }
+  L.x0 = rd<double>(in, (size_t)V);
+  L.assigned = rd<uint8_t>(in, (size_t)V);
+  return L;
+}
+
+void assign_flagged(Loaded& L) {
+  for (size_t i = 0; i < L.assigned.size(); ++i)
+    if (L.assigned[i]) L.fn->getVariables()[i]->assign(L.x0[i]);
+}
+
+VariableIDVec unassigned(Loaded& L) {
+  VariableIDVec v;
+  for (Variable* var : L.fn->getVariables())
+    if (!var->isAssigned()) v.push_back(var->getID());
+  return v;
+}
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 3) {
+    std::fprintf(stderr, "usage: host_driver children|wave|single <file> [maxiters]\n");
+    return 2;
+  }
+  try {
+    Loaded L = load(argv[2]);
+    const std::string mode = argv[1];
+    assign_flagged(L);
+    std::vector<ChildComponent> kids;
+    ComponentBatcher::createChildren(*L.fn, unassigned(L), kids);
+    if (mode == "children") {
+      std::printf("children %zu\n", kids.size());
+      for (const ChildComponent& c : kids) {
+        std::printf("%zu %zu |", c.vars.size(), c.factors.size());
+        for (VariableID v : c.vars) std::printf(" %lld", v);
+        std::printf(" |");
+        for (FactorID f : c.factors) std::printf(" %lld", f);
+        std::printf("\n");
+      }
+      return 0;
+    }
+    const int maxiters = argc > 3 ? std::atoi(argv[3]) : 25;
+    L.fn->init(0);
+    CudaSubspaceOptimizer ssopt(*L.fn);
+    ParameterMap opts;
+    opts["SSmaxit"] = maxiters;
+    opts["SSftol"] = 3e-8;
+    ssopt.setParameters(opts);
+    std::vector<ComponentProblem> probs(kids.size());
+    for (size_t k = 0; k < kids.size(); ++k) ComponentBatcher::leafProblem(*L.fn, kids[k], L.x0, probs[k]);
+    double total = 0;
+    if (mode == "wave") {
+      total = ssopt.optimizeBatch(probs, false);
+    } else if (mode == "single") {
+      for (ComponentProblem& p : probs) {
+        p.fval = ssopt.optimize(p.vars, p.factors, p.xval, p.deltaFval, false);
+        total += p.fval;
+        // the reference un-assigns the quick-assigned values before the next sibling (quickUnassignSSInitialVal,
+        // src/RDISOptimizer.cpp:1184); siblings share no factor, so leaving them assigned changes nothing
+      }
+    } else {
+      std::fprintf(stderr, "unknown mode\n");
+      return 2;
+    }
+    std::printf("problems %zu total %.17g\n", probs.size(), total);
+    for (const ComponentProblem& p : probs) {
+      std::printf("%.17g %.17g %zu %zu |", p.fval, p.deltaFval, p.vars.size(), p.factors.size());
+      for (size_t i = 0; i < p.vars.size(); ++i) std::printf(" %lld:%.17g", p.vars[i]->getID(), p.xval[i]);
+      std::printf("\n");
+    }
+    // post-conditions: host variables hold the final values; the full objective is consistent
+    for (const ComponentProblem& p : probs)
+      for (size_t i = 0; i < p.vars.size(); ++i)
+        if (!p.vars[i]->isAssigned() || p.vars[i]->eval() != p.xval[i]) {
+          std::printf("POSTCONDITION VIOLATED var %lld\n", p.vars[i]->getID());
+          return 1;
+        }
+    std::printf("eval_all %.17g\n", L.fn->eval());
+    // gradient of everything w.r.t. the first problem's variables, through the plugin surface
+    if (!probs.empty()) {
+      NumericVec g;
+      L.fn->computeGradient(L.fn->getFactors(), probs[0].vars, g);
+      std::printf("grad0");
+      for (double v : g) std::printf(" %.17g", v);
+      std::printf("\n");
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "host_driver: %s\n", e.what());
+    return 1;
+  } catch (const char* s) {
+    std::fprintf(stderr, "host_driver: %s\n", s);
+    return 1;
+  }
+}
