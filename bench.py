@@ -234,6 +234,28 @@ def run_ours(args):
     h2d = 8 * spec["V"] + sum(4 * len(p.vids) + 4 * len(p.fids) + 8 * len(p.vids) + 48 * p.n for p in (pts, cams))
     d2h = sum(8 * len(p.vids) + 32 * p.n for p in (pts, cams))
 
+    # ---- the same wave with the Levenberg-Marquardt subspace solver (BASELINE config 3: per-component LM);
+    #      host buffers through rdisgpu_solve_lm_csr, so this is an end-to-end figure ----
+    def step_lm():
+        ctx.set_x(x0_pin.numpy())
+        ra = ctx.solve_lm(pts, x0_pts_pin, MAXITERS, FTOL)
+        rb = ctx.solve_lm(cams, x0_cams_pin, MAXITERS, FTOL)
+        return float(ra["f_end"].sum() + rb["f_end"].sum()), ra, rb
+
+    for _ in range(2):
+        step_lm()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        obj_lm, lm_a, lm_b = step_lm()
+    torch.cuda.synchronize()
+    t_lm = time.perf_counter() - t0
+    lm_info = {"value": n_solves * e2e_steps / t_lm, "unit": "solves/s (per GPU, host buffers, rdisgpu_solve_lm_csr)",
+               "ms_per_step": t_lm / e2e_steps * 1e3, "objective": obj_lm,
+               "iters_mean": float(np.concatenate([lm_a["iters"], lm_b["iters"]]).mean()),
+               "stop_histogram": np.bincount(np.concatenate([lm_a["stop"], lm_b["stop"]]), minlength=8).tolist(),
+               "parity": "unpinned upstream (levmar not vendored); tested against oracle/lm_oracle.hpp"}
+
     out = None
     if rank == 0:
         peak, peak_src = peaks()
@@ -258,6 +280,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "objective": obj_e2e},
+            "lm_wave": lm_info,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "solve_ba_points_kernel (point components)" if dom_is_pts
                          else "solve_ba_cameras_kernel (camera components)",

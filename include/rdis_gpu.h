@@ -150,6 +150,19 @@ RDISGPU_API int rdisgpu_solve_cgd_csr(rdisgpu_ctx* ctx, int64_t nprobs, const in
                                       double ftol, double* x_out, double* f_init, double* f_end, int32_t* iters,
                                       int32_t* status, int64_t* n_feval, int64_t* n_geval);
 
+/* LMSubspaceOptimizer::optimize (src/optimizers/LMSubspaceOptimizer.cpp:29-171) for nprobs sibling problems,
+ * packed like rdisgpu_solve_cgd_csr: residual sqrt(2 f_j) per factor, dense Jacobian, levmar's dlevmar_der
+ * (x = NULL) with opts4 = {tau, eps1, eps2, eps3} (NULL = the reference's {1e-3, 1e-15, 1e-15, 3e-8}, :83-86),
+ * no domain clamping (:281-297), no revert.  PARITY UNPINNED: levmar is not vendored with the reference and
+ * no reference test runs this optimizer; the arithmetic follows oracle/lm_oracle.hpp.  Components of more
+ * than 32 variables are rejected (RDISGPU_ERR_ARG) in this version.  stop[p] is levmar's termination code:
+ * 1 small gradient, 2 small step, 3 itmax, 4 singular, 5 no further reduction, 6 small ||e||^2, 7 non-finite;
+ * 0 for a problem without factors (returns 0, x untouched).  n_feval / n_jeval count func / jacf calls. */
+RDISGPU_API int rdisgpu_solve_lm_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_off, const int32_t* vids,
+                                     const int64_t* fac_off, const int64_t* fids, const double* x0, int maxiters,
+                                     const double* opts4, double* x_out, double* f_init, double* f_end, int32_t* iters,
+                                     int32_t* stop, int64_t* n_feval, int64_t* n_jeval);
+
 /* The same in three steps, for callers that revisit one component structure many times
  * (alternating minimisation, RDISOptimizer.cpp:1148-1181): index lists stay resident in HBM. */
 RDISGPU_API int rdisgpu_batch_create(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t nprobs,

@@ -12,6 +12,7 @@
 #include <thread>
 
 #include "rdis_oracle.hpp"
+#include "lm_oracle.hpp"
 
 using namespace oracle;
 
@@ -20,7 +21,8 @@ namespace {
 struct Handle {
   std::unique_ptr<OptimizableFunction> fn;
   std::unique_ptr<CGDSubspaceOptimizer> cgd;
-  Handle() : fn(new OptimizableFunction()), cgd(new CGDSubspaceOptimizer(*fn)) {}
+  std::unique_ptr<LMSubspaceOptimizer> lmopt;
+  Handle() : fn(new OptimizableFunction()), cgd(new CGDSubspaceOptimizer(*fn)), lmopt(new LMSubspaceOptimizer(*fn)) {}
 };
 
 Handle* H(void* h) { return static_cast<Handle*>(h); }
@@ -560,6 +562,47 @@ double orc_solve_cgd_batch(void* h, int64_t nprobs, const int64_t* var_off, cons
       th.emplace_back(run_range, replicas[t], lo, hi);
     }
     for (auto& t : th) t.join();
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// One LMSubspaceOptimizer::optimize call (PARITY UNPINNED, see lm_oracle.hpp).  info8 (nullable) receives
+// {||e||^2 at start, ||e||^2 at end, iterations, stop code, #func, #jac, #linear solves, ||J^T e||_inf}.
+double orc_solve_lm(void* h, int64_t nv, const int32_t* vid, int64_t nf, const int64_t* fid, double* x_inout, int maxiters,
+                    double ftol, double* delta, double* info8) {
+  Handle* hd = H(h);
+  OptimizableFunction& fn = *hd->fn;
+  std::vector<Variable*> vars;
+  std::vector<Factor*> fs;
+  for (int64_t i = 0; i < nv; ++i) vars.push_back(fn.variables[vid[i]]);
+  for (int64_t i = 0; i < nf; ++i) fs.push_back(fn.factors[fid[i]]);
+  std::vector<double> xval(x_inout, x_inout + nv);
+  hd->lmopt->setParameters(maxiters, ftol);
+  for (int64_t i = 0; i < nv; ++i) vars[i]->assign(xval[i]);
+  double d = 0;
+  const double fret = hd->lmopt->optimize(vars, fs, xval, d, false);
+  std::memcpy(x_inout, xval.data(), nv * sizeof(double));
+  if (delta) *delta = d;
+  if (info8) {
+    const lm::Info& I = hd->lmopt->lastInfo;
+    const double v[8] = {I.e0, I.e, (double)I.iters, (double)I.stop, (double)I.nfev, (double)I.njev, (double)I.nlss, I.jte_inf};
+    std::memcpy(info8, v, sizeof v);
+  }
+  return fret;
+}
+
+double orc_solve_lm_batch(void* h, int64_t nprobs, const int64_t* var_off, const int32_t* vids, const int64_t* fac_off,
+                          const int64_t* fids, double* x_inout, int maxiters, double ftol, double* f_end, double* f_init,
+                          int32_t* iters, int32_t* stop) {
+  auto t0 = std::chrono::steady_clock::now();
+  for (int64_t p = 0; p < nprobs; ++p) {
+    double d = 0, info[8];
+    const double fe = orc_solve_lm(h, var_off[p + 1] - var_off[p], vids + var_off[p], fac_off[p + 1] - fac_off[p],
+                                   fids + fac_off[p], x_inout + var_off[p], maxiters, ftol, &d, info);
+    if (f_end) f_end[p] = fe;
+    if (f_init) f_init[p] = fe - d;
+    if (iters) iters[p] = (int32_t)info[2];
+    if (stop) stop[p] = (int32_t)info[3];
   }
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }

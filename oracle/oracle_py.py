@@ -25,7 +25,7 @@ def build(force=False):
     """Compile the oracle (and, where /root/reference exists, the _ref variant)."""
     if force or not os.path.exists(LIB_RESTATED) or \
             os.path.getmtime(LIB_RESTATED) < max(os.path.getmtime(os.path.join(_HERE, f))
-                                                  for f in ("oracle_capi.cpp", "rdis_oracle.hpp", "nr_minimize.hpp")):
+                                                  for f in ("oracle_capi.cpp", "rdis_oracle.hpp", "nr_minimize.hpp", "lm_oracle.hpp")):
         subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
     elif not os.path.exists(LIB_REFNRC) and os.path.exists("/root/reference/external/include/minimize_nrc.h"):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
@@ -78,6 +78,9 @@ def _load(path):
     lib.orc_solve_cgd_batch.restype = C.c_double
     lib.orc_solve_cgd_batch.argtypes = [vp, C.c_int64, _i64p, _i32p, _i64p, _i64p, _f64p, C.c_int, C.c_double,
                                         _f64p, _f64p, _i32p, C.c_int, vp]
+    lib.orc_solve_lm_batch.restype = C.c_double
+    lib.orc_solve_lm_batch.argtypes = [vp, C.c_int64, _i64p, _i32p, _i64p, _i64p, _f64p, C.c_int, C.c_double,
+                                       _f64p, _f64p, _i32p, _i32p]
     lib.orc_get_counters.argtypes = [vp, _i64p]
     lib.orc_reset_counters.argtypes = [vp]
     lib.orc_trace_enable.argtypes = [vp, C.c_int]
@@ -265,6 +268,17 @@ class OracleFunction:
             secs = self._lib.orc_solve_cgd_batch(self._h, n, var_off, vids, fac_off, fids, x, maxiters, ftol, fe, fi, it,
                                                  1, None)
         return {"x": x, "f_end": fe, "f_init": fi, "iters": it, "seconds": secs}
+
+    def solve_lm_batch(self, var_off, vids, fac_off, fids, x0, maxiters=25, ftol=3e-8):
+        """Batch of LMSubspaceOptimizer::optimize calls (PARITY UNPINNED: levmar restated, oracle/lm_oracle.hpp).
+        Returns dict(x, f_end, f_init, iters, stop, seconds)."""
+        var_off = np.ascontiguousarray(var_off, np.int64); fac_off = np.ascontiguousarray(fac_off, np.int64)
+        vids = np.ascontiguousarray(vids, np.int32); fids = np.ascontiguousarray(fids, np.int64)
+        n = len(var_off) - 1
+        x = np.array(x0, dtype=np.float64, copy=True)
+        fe = np.empty(n); fi = np.empty(n); it = np.empty(n, np.int32); st = np.empty(n, np.int32)
+        secs = self._lib.orc_solve_lm_batch(self._h, n, var_off, vids, fac_off, fids, x, maxiters, ftol, fe, fi, it, st)
+        return {"x": x, "f_end": fe, "f_init": fi, "iters": it, "stop": st, "seconds": secs}
 
     def trace(self, on=True):
         """Start (and clear) / stop recording every SubfunctionFD evaluation of the next solves."""

@@ -20,7 +20,7 @@ EXPORTS = (
     "rdisgpu_set_vars", "rdisgpu_add_nlpf", "rdisgpu_add_ba", "rdisgpu_finalize",
     "rdisgpu_set_x", "rdisgpu_get_x", "rdisgpu_set_factor_const",
     "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_eval_device", "rdisgpu_grad_device", "rdisgpu_factor_grad",
-    "rdisgpu_solve_cgd", "rdisgpu_solve_cgd_csr", "rdisgpu_batch_create", "rdisgpu_batch_create_csr", "rdisgpu_batch_info", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
+    "rdisgpu_solve_cgd", "rdisgpu_solve_cgd_csr", "rdisgpu_solve_lm_csr", "rdisgpu_batch_create", "rdisgpu_batch_create_csr", "rdisgpu_batch_info", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
     "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches",
     "rdisgpu_num_vars", "rdisgpu_num_factors", "rdisgpu_device_state", "rdisgpu_launch_count", "rdisgpu_version",
 )
@@ -69,6 +69,7 @@ def load_library(path=LIB_PATH):
         "rdisgpu_batch_create": (C.c_int, [vp, C.POINTER(Problem), i64, C.POINTER(vp)]),
         "rdisgpu_batch_create_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, C.POINTER(vp)]),
         "rdisgpu_solve_cgd_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, C.c_int, dbl, vp, vp, vp, vp, vp, vp, vp]),
+        "rdisgpu_solve_lm_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
         "rdisgpu_batch_info": (C.c_int, [vp, vp]),
         "rdisgpu_batch_solve_cgd": (C.c_int, [vp, vp, C.c_int, dbl]),
         "rdisgpu_batch_fetch": (C.c_int, [vp, C.POINTER(Result), C.POINTER(dbl)]),
@@ -286,6 +287,20 @@ class Context:
         self._ck(self._lib.rdisgpu_solve_cgd_csr(self._h, n, _p(ps.var_off), _p(ps.vids), _p(ps.fac_off), _p(ps.fids), _p(x0a),
                                                  maxiters, ftol, _p(out["x"]), _p(out["f_init"]), _p(out["f_end"]),
                                                  _p(out["iters"]), _p(out["status"]), _p(out["n_feval"]), _p(out["n_geval"])))
+        return out
+
+    def solve_lm(self, problems, x0=None, maxiters=25, ftol=3e-8, opts=None):
+        """rdisgpu_solve_lm_csr (Levenberg-Marquardt, parity unpinned).  Returns dict(x, f_init, f_end, iters,
+        stop, n_feval, n_jeval)."""
+        ps = problems
+        x0a = None if x0 is None else _arr(x0, np.float64)
+        o = _arr(opts if opts is not None else [1e-3, 1e-15, 1e-15, ftol], np.float64)
+        n = ps.n
+        out = {"x": np.empty(len(ps.vids)), "f_init": np.empty(n), "f_end": np.empty(n), "iters": np.empty(n, np.int32),
+               "stop": np.empty(n, np.int32), "n_feval": np.empty(n, np.int64), "n_jeval": np.empty(n, np.int64)}
+        self._ck(self._lib.rdisgpu_solve_lm_csr(self._h, n, _p(ps.var_off), _p(ps.vids), _p(ps.fac_off), _p(ps.fids), _p(x0a),
+                                                maxiters, _p(o), _p(out["x"]), _p(out["f_init"]), _p(out["f_end"]),
+                                                _p(out["iters"]), _p(out["stop"]), _p(out["n_feval"]), _p(out["n_jeval"])))
         return out
 
     def solve_cgd_structs(self, problems, x0=None, maxiters=25, ftol=3e-8):

@@ -16,6 +16,7 @@
 #include "solve_kernels.cuh"
 #include "sweep_kernels.cuh"
 #include "nlpf_tile_sweep.cuh"
+#include "lm_kernels.cuh"
 
 using namespace rdisgpu;
 
@@ -109,6 +110,11 @@ struct rdisgpu_ctx {
   DevBuf<int32_t> s_i32a, s_i32b;
   DevBuf<double> s_f64a, s_f64b, s_partials;
   DevBuf<unsigned int> s_counter;
+  // Levenberg-Marquardt path (lm_kernels.cuh)
+  DevBuf<int32_t> lm_vloc;
+  DevBuf<double> lm_scratch;
+  DevBuf<int64_t> lm_off;
+  bool lm_vloc_ready = false;
   DevBuf<double> grid_partials;
   PinnedBuf<char> pin;
 
@@ -1232,6 +1238,78 @@ int rdisgpu_solve_cgd_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_o
     if (status) status[p] = r.status;
     if (n_feval) n_feval[p] = (int64_t)r.n_value + r.n_slope;
     if (n_geval) n_geval[p] = r.n_slope;
+  }
+  return RDISGPU_OK;
+}
+
+int rdisgpu_solve_lm_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_off, const int32_t* vids, const int64_t* fac_off,
+                         const int64_t* fids, const double* x0, int maxiters, const double* opts4, double* x_out,
+                         double* f_init, double* f_end, int32_t* iters, int32_t* stop, int64_t* n_feval, int64_t* n_jeval) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "solve_lm_csr before finalize");
+  if (nprobs <= 0 || !var_off || !fac_off) return ctx->fail(RDISGPU_ERR_ARG, "solve_lm_csr: no problems");
+  if (nprobs >= 0x40000000LL) return ctx->fail(RDISGPU_ERR_ARG, "solve_lm_csr: too many problems");
+  if (maxiters <= 0) return ctx->fail(RDISGPU_ERR_ARG, "solve_lm_csr: maxiters must be positive");
+  CK(cudaSetDevice(ctx->device));
+  rdisgpu_batch* b = scratch_batch(ctx);
+  ProblemsView pv;
+  pv.n = nprobs;
+  pv.var_off = var_off; pv.vids = vids; pv.fac_off = fac_off; pv.fids = fids;
+  int rc = batch_build(b, pv);
+  if (rc) return rc;
+  // dense-Jacobian scratch: per problem jac[n*m] | e[n] | hx[n], n = max(|factors|, m) (LMSubspaceOptimizer.cpp:48-49)
+  std::vector<int64_t> off((size_t)nprobs + 1, 0);
+  for (int64_t p = 0; p < nprobs; ++p) {
+    const int64_t m = b->h_probs[p].nv, nf = b->h_probs[p].nf;
+    if (m > kLmMaxVars) return ctx->fail(RDISGPU_ERR_ARG, "solve_lm_csr: components of more than 32 variables are not supported");
+    const int64_t n = std::max(nf, m);
+    off[(size_t)p + 1] = off[(size_t)p] + n * m + 2 * n;
+  }
+  cudaStream_t s = ctx->stream;
+  CK(ctx->lm_off.ensure(off.size()));
+  CK(ctx->lm_scratch.ensure((size_t)std::max<int64_t>(off.back(), 1)));
+  CK(cudaMemcpyAsync(ctx->lm_off.p, off.data(), off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  if (!ctx->lm_vloc_ready) {
+    CK(ctx->lm_vloc.ensure((size_t)ctx->V));
+    CK(cudaMemsetAsync(ctx->lm_vloc.p, 0xff, (size_t)ctx->V * sizeof(int32_t), s));  // -1
+    ctx->lm_vloc_ready = true;
+  }
+  const bool x0_on_device = is_device_ptr(x0);
+  if (x0 && !x0_on_device && b->total_nv > 0)
+    CK(cudaMemcpyAsync(b->x0.p, x0, (size_t)b->total_nv * sizeof(double), cudaMemcpyHostToDevice, s));
+  BatchView bv;
+  bv.probs = b->d_probs;
+  bv.vids = b->d_vids;
+  bv.fids = b->d_fids;
+  bv.x0 = x0 ? (x0_on_device ? x0 : b->x0.p) : nullptr;
+  bv.xout = b->xout.p;
+  bv.res = b->res.p;
+  LmView lv;
+  lv.vloc = ctx->lm_vloc.p;
+  lv.scratch = ctx->lm_scratch.p;
+  lv.scr_off = ctx->lm_off.p;
+  const double tau = opts4 ? opts4[0] : 1e-3, eps1 = opts4 ? opts4[1] : 1e-15, eps2 = opts4 ? opts4[2] : 1e-15,
+               eps3 = opts4 ? opts4[3] : 3e-8;
+  if (ctx->kind == KIND_NLPF)
+    solve_lm_block_kernel<NlpfOps><<<(unsigned)nprobs, kLmThreads, 0, s>>>(ctx->gv, bv, lv, maxiters, tau, eps1, eps2, eps3);
+  else
+    solve_lm_block_kernel<BaOps><<<(unsigned)nprobs, kLmThreads, 0, s>>>(ctx->gv, bv, lv, maxiters, tau, eps1, eps2, eps3);
+  ++ctx->launches;
+  b->last_launches = 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(b->h_res.p, b->res.p, (size_t)nprobs * sizeof(ResultRec), cudaMemcpyDeviceToHost, s));
+  if (x_out && b->total_nv > 0)
+    CK(cudaMemcpyAsync(b->h_x.p, b->xout.p, (size_t)b->total_nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));  // also keeps `off` alive until the copy is done
+  if (x_out && b->total_nv > 0) std::memcpy(x_out, b->h_x.p, (size_t)b->total_nv * sizeof(double));
+  for (int64_t p = 0; p < nprobs; ++p) {
+    const ResultRec& r = b->h_res.p[p];
+    if (f_init) f_init[p] = r.f_init;
+    if (f_end) f_end[p] = r.f_end;
+    if (iters) iters[p] = r.iters;
+    if (stop) stop[p] = r.status;
+    if (n_feval) n_feval[p] = r.n_value;
+    if (n_jeval) n_jeval[p] = r.n_slope;
   }
   return RDISGPU_OK;
 }

@@ -314,13 +314,20 @@ Numeric CudaSubspaceOptimizer::optimizeBatch(std::vector<ComponentProblem>& prob
   status.resize((size_t)n);
   nfe.resize((size_t)n);
   nge.resize((size_t)n);
-  f.check(rdisgpu_solve_cgd_csr(f.device(), n, var_off.data(), vids.data(), fac_off.data(), fids.data(), x0.data(), (int)maxiters,
-                                ftol, xout.data(), finit.data(), fend.data(), iters.data(), status.data(), nfe.data(), nge.data()),
-          "rdisgpu_solve_cgd_csr");
+  if (useLM) {
+    const double opts[4] = {1e-3, 1e-15, 1e-15, ftol};  // src/optimizers/LMSubspaceOptimizer.cpp:83-86
+    f.check(rdisgpu_solve_lm_csr(f.device(), n, var_off.data(), vids.data(), fac_off.data(), fids.data(), x0.data(), (int)maxiters,
+                                 opts, xout.data(), finit.data(), fend.data(), iters.data(), status.data(), nfe.data(), nge.data()),
+            "rdisgpu_solve_lm_csr");
+  } else {
+    f.check(rdisgpu_solve_cgd_csr(f.device(), n, var_off.data(), vids.data(), fac_off.data(), fids.data(), x0.data(), (int)maxiters,
+                                  ftol, xout.data(), finit.data(), fend.data(), iters.data(), status.data(), nfe.data(), nge.data()),
+            "rdisgpu_solve_cgd_csr");
+  }
   Numeric total = 0;
   for (int64_t k = 0; k < n; ++k) {
     ComponentProblem& p = problems[(size_t)k];
-    if (status[(size_t)k] == RDISGPU_DONE_EMPTY) {  // nothing to optimise: xval untouched, returns 0 (CGD.cpp:26-29)
+    if (p.factors.empty()) {  // nothing to optimise: xval untouched, returns 0 (CGD.cpp:26-29)
       p.fval = 0;
       p.deltaFval = 0;
       p.iters = 0;

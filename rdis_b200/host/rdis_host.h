@@ -283,7 +283,7 @@ struct ComponentProblem {
 
 class CudaSubspaceOptimizer : public SubspaceOptimizer {
  public:
-  explicit CudaSubspaceOptimizer(OptimizableFunction& f_) : SubspaceOptimizer(f_) {}
+  explicit CudaSubspaceOptimizer(OptimizableFunction& f_) : SubspaceOptimizer(f_), useLM(false) {}
   Numeric optimize(const VariablePtrVec& vars, const FactorPtrVec& factors, NumericVec& xval, Numeric& deltaFval,
                    const bool printdbg) override;
   // The sibling-component batch (src/RDISOptimizer.cpp:184-211, 291-314 loop over children one at a
@@ -291,10 +291,22 @@ class CudaSubspaceOptimizer : public SubspaceOptimizer {
   // Returns the sum of the problems' final objective values.
   Numeric optimizeBatch(std::vector<ComponentProblem>& problems, const bool printdbg);
 
+ protected:
+  CudaSubspaceOptimizer(OptimizableFunction& f_, bool lm) : SubspaceOptimizer(f_), useLM(lm) {}
+  const bool useLM;  // false: conjugate gradient (rdisgpu_solve_cgd_csr); true: Levenberg-Marquardt (rdisgpu_solve_lm_csr)
+
  private:
   std::vector<int64_t> var_off, fac_off, fids, nfe, nge;
   std::vector<int32_t> vids, iters, status;
   std::vector<double> x0, xout, finit, fend;
+};
+
+// Replaces src/optimizers/LMSubspaceOptimizer.{h,cpp} (selected by --useCGD 0, src/bundleadjust/optBA.cpp:155-158).
+// Same interface; the solve is levmar's dlevmar_der on the device: no clamping, no revert, stop codes 1..7 in
+// ComponentProblem::status.  PARITY UNPINNED (levmar is not vendored with the reference).
+class CudaLMSubspaceOptimizer : public CudaSubspaceOptimizer {
+ public:
+  explicit CudaLMSubspaceOptimizer(OptimizableFunction& f_) : CudaSubspaceOptimizer(f_, true) {}
 };
 
 // Sibling components of a set of variables: connected components of the bipartite variable / factor

@@ -78,7 +78,7 @@ VariableIDVec unassigned(Loaded& L) {
 
 int main(int argc, char** argv) {
   if (argc < 3) {
-    std::fprintf(stderr, "usage: host_driver children|wave|single <file> [maxiters]\n");
+    std::fprintf(stderr, "usage: host_driver children|wave|single <file> [maxiters] [lm]\n");
     return 2;
   }
   try {
@@ -100,7 +100,10 @@ int main(int argc, char** argv) {
     }
     const int maxiters = argc > 3 ? std::atoi(argv[3]) : 25;
     L.fn->init(0);
-    CudaSubspaceOptimizer ssopt(*L.fn);
+    const bool lm = argc > 4 && std::string(argv[4]) == "lm";
+    CudaSubspaceOptimizer cgd(*L.fn);
+    CudaLMSubspaceOptimizer lmo(*L.fn);
+    CudaSubspaceOptimizer& ssopt = lm ? static_cast<CudaSubspaceOptimizer&>(lmo) : cgd;
     ParameterMap opts;
     opts["SSmaxit"] = maxiters;
     opts["SSftol"] = 3e-8;

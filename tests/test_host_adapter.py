@@ -163,6 +163,13 @@ def test_host_adapter_wave_matches_ctypes_path_and_oracle(driver, oracle_mod, tm
     o = orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[ps.vids], 25, 3e-8)
     rel = np.abs(np.array([p[0] for p in pw]) - o["f_end"]) / np.maximum(np.abs(o["f_end"]), 1e-12)
     assert rel.max() <= 1e-6
+    # the Levenberg-Marquardt adapter (CudaLMSubspaceOptimizer) through the same surface
+    out_l = subprocess.run([driver, "wave", path, "25", "lm"], capture_output=True, text=True, check=True).stdout
+    tot_l, pl, _ = _parse_wave(out_l)
+    orc.set_x(x0)
+    ol = orc.solve_lm_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[ps.vids], 25, 3e-8)
+    rel = np.abs(np.array([p[0] for p in pl]) - ol["f_end"]) / np.maximum(np.abs(ol["f_end"]), 1e-12)
+    assert rel.max() <= 1e-6
 
 
 @pytest.mark.gpu

@@ -221,3 +221,31 @@ def test_ladybug_fixture_shape():
     cdeg = np.bincount(spec["cam"], minlength=49)
     assert (cdeg.min(), int(np.median(cdeg)), cdeg.max()) == (361, 630, 906)
     assert (spec["lb"] <= spec["x0"]).all() and (spec["x0"] <= spec["ub"]).all()
+
+
+def test_lm_restatement_known_answers(oracle_mod):
+    """The LM oracle (levmar restated; PARITY UNPINNED upstream) on problems with known answers:
+    (1) separable quadratics 0.5*(x_i - k_i)^2: residual |x_i - k_i|, minimum 0 at x = k;
+    (2) BA point blocks: never worse than the start, monotone non-increasing with the iteration budget."""
+    from rdis_b200 import problems as P
+    V = 6
+    k = np.array([1.0, -2.0, 0.5, 3.0, -1.5, 2.5])
+    spec = dict(kind="nlpf", V=V, F=V, lb=np.full(V, -50.0), ub=np.full(V, 50.0), rowptr=np.arange(V + 1), vid=np.arange(V, dtype=np.int32),
+                expo=np.full(V, 2.0), konst=k, sine=np.zeros(V, np.uint8), coeff=np.full(V, 0.5))
+    orc = oracle_mod.OracleFunction.from_spec(spec)
+    x0 = np.array([4.0, 4.0, -3.0, 0.0, 1.0, -6.0])
+    orc.set_x(x0)
+    r = orc.solve_lm_batch([0, V], np.arange(V, dtype=np.int32), [0, V], np.arange(V, dtype=np.int64), x0, 50, 1e-20)
+    assert np.allclose(r["x"], k, atol=1e-7) and r["f_end"][0] <= 1e-14
+    assert abs(r["f_init"][0] - 0.5 * np.sum((x0 - k) ** 2)) <= 1e-12
+    spec = P.ba_synthetic(ncams=5, npts=60, nobs=240, seed=2)
+    ps = P.ba_point_problems(spec)
+    x0 = spec["x0"]
+    prev = None
+    for iters in (1, 5, 25):
+        orc = oracle_mod.OracleFunction.from_spec(spec); orc.set_x(x0)
+        r = orc.solve_lm_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[ps.vids], iters, 3e-8)
+        assert (r["f_end"] <= r["f_init"] * (1 + 1e-12)).all()
+        if prev is not None:
+            assert (r["f_end"] <= prev * (1 + 1e-12)).all()
+        prev = r["f_end"]
