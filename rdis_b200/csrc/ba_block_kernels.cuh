@@ -247,6 +247,7 @@ __device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const B
     for (int j = 0; j < 3; ++j) {
       const double val = clamp_to_domain(restore ? xs[j] : p[j], dom[j]);
       Gv.xbd[v0 + j] = make_double2(val, qnan_f64());
+      Gv.xval[v0 + j] = val;
       B.xout[P.var_off + j] = val;
     }
     ResultRec res;
@@ -512,6 +513,7 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
       const int j = threadIdx.x;
       const double val = clamp_to_domain(restore ? sh.xs[j] : sh.p[j], sh.dom[j]);
       Gv.xbd[v0 + j] = make_double2(val, qnan_f64());
+      Gv.xval[v0 + j] = val;
       B.xout[P.var_off + j] = val;
     }
     if (threadIdx.x == 0) {

@@ -1,6 +1,7 @@
 // factors.cuh — device-side factor arithmetic and the HBM layout it reads.
 //
 // HBM layout (all resident for the life of a context; int32 indices, fp64 values):
+//   xval  double[V]    committed value of every variable (mirror of xbd.x outside running solves)
 //   xbd   double2[V]   .x = value of the variable (p of the running solve for its variables)
 //                      .y = search direction xi for variables of a running solve, NaN for
 //                           everything else ("frozen": read as-is, never clamped)
@@ -31,6 +32,7 @@ struct GraphView {
   int kind;
   int64_t V, F, E;
   double2* xbd;
+  double* xval;  // dense mirror of xbd[].x for frozen variables (8 B/variable: what the streaming sweep gathers)
   const double2* dom;
   // NLPF
   const int32_t* rowptr;
@@ -84,6 +86,92 @@ __device__ __forceinline__ double load_var(const GraphView& G, int32_t vid, doub
   return clamp_to_domain(raw, __ldg(&G.dom[vid]));
 }
 
+// ------------------------------------------------------------------------------------------
+// sin / cos for the NonlinearProductFactor terms.
+// Same algorithm, constants and operation order as the CUDA math library's fast path (3-constant
+// Cody-Waite reduction by pi/2, degree-13 / degree-14 minimax kernels), so results are bit-identical
+// to sin() / cos() — tests/native/trig_check.cu demands it — but (a) the kernel coefficients are
+// immediates instead of three 16-byte loads from a global table per call, (b) the body is
+// straight-line, so the two edges a thread owns interleave, and (c) sin and cos of one argument
+// (value term + its derivative) share the reduction.  |x| >= 2^31, inf and NaN take the library call.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double f64_bits(unsigned long long b) { return __longlong_as_double((long long)b); }
+
+__device__ __forceinline__ void rdis_trig_reduce(double x, double& r, int& q) {
+  q = __double2int_rn(x * f64_bits(0x3FE45F306DC9C883ULL));  // x * 2/pi, round to nearest
+  const double j = (double)q;
+  r = __fma_rn(j, f64_bits(0xBFF921FB54442D18ULL), x);
+  r = __fma_rn(j, f64_bits(0xBC91A62633145C00ULL), r);
+  r = __fma_rn(j, f64_bits(0xB97B839A252049C0ULL), r);
+}
+// sin kernel on the reduced argument: r + r * P(r^2)
+__device__ __forceinline__ double rdis_sin_kernel(double r, double z) {
+  double p = f64_bits(0x3DE5DB65F9785EBAULL);
+  p = __fma_rn(p, z, f64_bits(0xBE5AE5F12CB0D246ULL));
+  p = __fma_rn(p, z, f64_bits(0x3EC71DE369ACE392ULL));
+  p = __fma_rn(p, z, f64_bits(0xBF2A01A019DB62A1ULL));
+  p = __fma_rn(p, z, f64_bits(0x3F81111111110818ULL));
+  p = __fma_rn(p, z, f64_bits(0xBFC5555555555554ULL));
+  p = __fma_rn(p, z, 0.0);
+  return __fma_rn(p, r, r);
+}
+// cos kernel: 1 + r^2 * Q(r^2)
+__device__ __forceinline__ double rdis_cos_kernel(double z) {
+  double p = f64_bits(0xBDA8FF8320FD8164ULL);
+  p = __fma_rn(p, z, f64_bits(0x3E21EEA7C1EF8528ULL));
+  p = __fma_rn(p, z, f64_bits(0xBE927E4F8E06E6D9ULL));
+  p = __fma_rn(p, z, f64_bits(0x3EFA01A019DDBCE9ULL));
+  p = __fma_rn(p, z, f64_bits(0xBF56C16C16C15D47ULL));
+  p = __fma_rn(p, z, f64_bits(0x3FA5555555555551ULL));
+  p = __fma_rn(p, z, -0.5);
+  return __fma_rn(p, z, 1.0);
+}
+// one kernel evaluation with the coefficient set chosen by the quadrant parity (what the library does)
+__device__ __forceinline__ double rdis_trig_select(double r, int q) {
+  const bool odd = (q & 1) != 0;
+  const double z = __dmul_rn(r, r);
+  double p = odd ? f64_bits(0xBDA8FF8320FD8164ULL) : f64_bits(0x3DE5DB65F9785EBAULL);
+  p = __fma_rn(p, z, odd ? f64_bits(0x3E21EEA7C1EF8528ULL) : f64_bits(0xBE5AE5F12CB0D246ULL));
+  p = __fma_rn(p, z, odd ? f64_bits(0xBE927E4F8E06E6D9ULL) : f64_bits(0x3EC71DE369ACE392ULL));
+  p = __fma_rn(p, z, odd ? f64_bits(0x3EFA01A019DDBCE9ULL) : f64_bits(0xBF2A01A019DB62A1ULL));
+  p = __fma_rn(p, z, odd ? f64_bits(0xBF56C16C16C15D47ULL) : f64_bits(0x3F81111111110818ULL));
+  p = __fma_rn(p, z, odd ? f64_bits(0x3FA5555555555551ULL) : f64_bits(0xBFC5555555555554ULL));
+  p = __fma_rn(p, z, odd ? -0.5 : 0.0);
+  const double v = odd ? __fma_rn(p, z, 1.0) : __fma_rn(p, r, r);
+  return (q & 2) ? (0.0 - v) : v;
+}
+__device__ __forceinline__ double rdis_sin(double x) {
+  if (!(fabs(x) < 2147483648.0)) return sin(x);
+  double r;
+  int q;
+  rdis_trig_reduce(x, r, q);
+  return rdis_trig_select(r, q);
+}
+__device__ __forceinline__ double rdis_cos(double x) {
+  if (!(fabs(x) < 2147483648.0)) return cos(x);
+  double r;
+  int q;
+  rdis_trig_reduce(x, r, q);
+  return rdis_trig_select(r, q + 1);
+}
+// s = sin(x), c = cos(x), each bit-identical to the separate calls
+__device__ __forceinline__ void rdis_sincos(double x, double& s, double& c) {
+  if (!(fabs(x) < 2147483648.0)) {
+    s = sin(x);
+    c = cos(x);
+    return;
+  }
+  double r;
+  int q;
+  rdis_trig_reduce(x, r, q);
+  const double z = __dmul_rn(r, r);
+  const double sk = rdis_sin_kernel(r, z), ck = rdis_cos_kernel(z);
+  const double sv = (q & 1) ? ck : sk;
+  const double cv = (q & 1) ? sk : ck;
+  s = (q & 2) ? (0.0 - sv) : sv;
+  c = ((q + 1) & 2) ? (0.0 - cv) : cv;
+}
+
 __device__ __forceinline__ double rdis_power(double val, double e) {
   if (e == 0.) return 1.;
   if (e == 1.) return val;
@@ -114,7 +202,7 @@ struct NlpfOps {
         const double ex = __ldg(&G.expo[e]);
         if (k != 0) val -= k;
         if (ex != 1) val = rdis_power(val, ex);
-        if (__ldg(&G.sine[e])) val = sin(val);
+        if (__ldg(&G.sine[e])) val = rdis_sin(val);
         prod *= val;
       }
       slope = 0.0;
@@ -256,8 +344,12 @@ struct NlpfOps {
     double dv = rdis_power(inner, ex - 1.0);
     dv *= ex;
     if (sn) {
-      dv *= cos(innerexp);
-      t = sin(val);  // same call as the value-only path, so a point has one value
+      // val and innerexp are the same number (k == 0: x and x - 0; else x - k both times), so one
+      // argument reduction serves both; each result is bit-identical to the separate call
+      double sv, cv;
+      rdis_sincos(val, sv, cv);
+      dv *= (innerexp == val) ? cv : rdis_cos(innerexp);
+      t = sv;  // same value as the value-only path, so a point has one value
     } else {
       t = val;
     }

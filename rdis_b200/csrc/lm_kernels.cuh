@@ -181,7 +181,10 @@ __global__ void __launch_bounds__(kLmThreads) solve_lm_block_kernel(GraphView G,
 
   // func: assign q (no clamping), hx_j = sqrt(2 f_j), returns sum f_j and sum hx_j^2 to every thread
   auto func = [&](const double* q, double& sumf, double& e2) {
-    for (int i = tid; i < m; i += kLmThreads) G.xbd[sh.vids[i]] = make_double2(q[i], qnan);
+    for (int i = tid; i < m; i += kLmThreads) {
+      G.xbd[sh.vids[i]] = make_double2(q[i], qnan);
+      G.xval[sh.vids[i]] = q[i];
+    }
     __syncthreads();
     double sf = 0.0, s2 = 0.0;
     for (int k = tid; k < n; k += kLmThreads) {

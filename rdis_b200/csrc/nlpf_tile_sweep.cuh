@@ -38,7 +38,7 @@ namespace rdisgpu {
 #define RDIS_TILE_FACTORS 512
 #endif
 #ifndef RDIS_TILE_STAGES
-#define RDIS_TILE_STAGES 4
+#define RDIS_TILE_STAGES 3
 #endif
 #ifndef RDIS_TILE_CTAS
 #define RDIS_TILE_CTAS 3
@@ -65,6 +65,7 @@ struct TileStage {
   double coeff[kTileFactors + 8];
   int32_t evid[kTileEdges + 32];
   int32_t rowptr[kTileFactors + 8];
+  double xs[kTileEdges + 32];   // gathered variable values (cp.async by the producer warp)
   uint8_t sine[kTileEdges + 32];
   TileDesc desc;  // written by the producer before it arms the barrier: consumers never touch the descriptor array
 };
@@ -73,6 +74,7 @@ static_assert(sizeof(TileStage) % 16 == 0, "stages must keep 16-byte alignment")
 struct TileSmem {
   TileStage stage[kTileStages];
   unsigned long long full[kTileStages];   // producer -> consumers: the stage's bytes have landed
+  unsigned long long xready[kTileStages]; // producer -> consumers: ... and the gathered variable values too
   unsigned long long empty[kTileStages];  // consumers -> producer: every consumer warp is done with the stage
 };
 
@@ -142,10 +144,14 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ double2 gather_var_pair(const double2* p, uint64_t policy) {
-  double2 v;
-  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy));
-  return v;
+// asynchronous 8-byte gather global -> shared (LDGSTS), L2 evict-last; completion is reported to an mbarrier
+__device__ __forceinline__ void cp_async_gather8(double* dst_smem, const double* src_gmem, uint64_t policy) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(smem_addr_u32(dst_smem)), "l"(src_gmem),
+               "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
 }
 
 // value term exactly as NlpfOps::value (no-slope path) computes it
@@ -154,7 +160,7 @@ __device__ __forceinline__ double nlpf_term_value(double xv, double k, double ex
   if (k != 0) val -= k;
   if (ex != 1) val = rdis_power(val, ex);
 #ifndef RDIS_EXP_NOSIN
-  if (sn) val = sin(val);
+  if (sn) val = rdis_sin(val);
 #endif
   return val;
 }
@@ -175,8 +181,10 @@ __device__ __forceinline__ void nlpf_term_grad(double xv, double k, double ex, b
   double dv = rdis_power(inner, ex - 1.0);
   dv *= ex;
   if (sn) {
-    dv *= cos(innerexp);
-    t = sin(val);
+    double sv, cv;
+    rdis_sincos(val, sv, cv);
+    dv *= (innerexp == val) ? cv : rdis_cos(innerexp);
+    t = sv;
   } else {
     t = val;
   }
@@ -208,17 +216,22 @@ __device__ __forceinline__ void tile_issue(const GraphView& G, const TileDesc d,
 // Named barrier over the consumer warps only (the producer warp never joins it).
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTileThreads) : "memory"); }
 
-// Value of a gathered variable: frozen variables (direction slot NaN — every variable outside a
-// running solve) are used as stored; the others are clamped (load_var<false>).  Out of line on
-// purpose: the sweep never takes this path in steady state and it must not cost issue slots.
-__device__ __noinline__ double clamp_live_var(const GraphView& G, int32_t vid, double xv) {
-  return clamp_to_domain(xv, __ldg(&G.dom[vid]));
-}
+// Block layout: warps 0..kTileThreads/32-1 = consumers, one more warp = producer.
+// The producer warp runs two software-pipelined jobs per tile: lane 0 launches the six TMA bulk copies
+// (kTileStages - kGatherLag tiles ahead of the consumers), and — kGatherLag tiles later, once the slice
+// has landed — all 32 lanes gather the tile's variable values into the stage with 8-byte cp.async
+// copies from the dense value mirror (xval).  Consumers therefore find everything in shared memory:
+// no register staging, no exposed gather latency.  Terms are written IN PLACE over the stage's
+// exponent slots (derivatives over the constant slots): the thread that consumes expo[e] / konst[e] is
+// the one that produces term[e], so a tile needs exactly one CTA-wide barrier.
+// Precondition (holds for every stream-ordered caller): no subspace solve is running on this context,
+// i.e. every variable is frozen and xval mirrors xbd.x.
+#ifndef RDIS_TILE_GATHER_LAG
+#define RDIS_TILE_GATHER_LAG 1
+#endif
+constexpr int kGatherLag = RDIS_TILE_GATHER_LAG;
+static_assert(kGatherLag >= 1 && kGatherLag < kTileStages, "the gather trails the bulk copy by fewer tiles than there are stages");
 
-// Block layout: warps 0..kTileThreads/32-1 = consumers, one more warp = producer (one elected lane).
-// Terms are written IN PLACE over the stage's exponent slots (derivatives over the constant slots):
-// the thread that consumes expo[e] / konst[e] is the one that produces term[e], so the stage ring
-// doubles as the term buffer and a tile needs exactly one CTA-wide barrier.
 template <bool kGrad>
 __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? 2 : kTileCtasPerSm)
     nlpf_tile_sweep_kernel(GraphView G, const TileDesc* __restrict__ tiles, int ntiles, double* __restrict__ per_factor,
@@ -232,6 +245,7 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? 2 : kTileCtasPerSm)
   if (tid == 0) {
     for (int s = 0; s < kTileStages; ++s) {
       mbar_init(&S.full[s], 1);
+      mbar_init(&S.xready[s], 32);                // one arrival per producer lane
       mbar_init(&S.empty[s], kTileThreads / 32);  // one arrival per consumer warp
     }
     mbar_fence_init();
@@ -240,9 +254,9 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? 2 : kTileCtasPerSm)
 
   double acc = 0.0;
   if (tid >= kTileThreads) {
-    // ---- producer warp: keeps kTileStages tiles in flight ahead of the consumers ----
+    // ---- producer warp ----
     // Descriptors are fetched 32 at a time (one per lane, the next batch already in flight), so the
-    // issue loop never waits on HBM for a descriptor; lane 0 issues the copies.
+    // issue loop never waits on HBM for a descriptor.
     const int lane = tid & 31;
     auto fetch = [&](int batch) {
       const int i = batch * 32 + lane;
@@ -250,66 +264,52 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? 2 : kTileCtasPerSm)
     };
     TileDesc mine = fetch(0), ahead = fetch(1);
     const uint64_t pol = l2_policy_evict_first();
-    for (int it = 0; it < my_tiles; ++it) {
-      if (it > 0 && (it & 31) == 0) {
-        mine = ahead;
-        ahead = fetch((it >> 5) + 1);
+    const uint64_t keep = l2_policy_evict_last();
+    for (int j = 0; j < my_tiles + kGatherLag; ++j) {
+      if (j < my_tiles) {
+        if (j > 0 && (j & 31) == 0) {
+          mine = ahead;
+          ahead = fetch((j >> 5) + 1);
+        }
+        TileDesc d;
+        d.f0 = __shfl_sync(0xffffffffu, mine.f0, j & 31);
+        d.f1 = __shfl_sync(0xffffffffu, mine.f1, j & 31);
+        d.e0 = __shfl_sync(0xffffffffu, mine.e0, j & 31);
+        d.e1 = __shfl_sync(0xffffffffu, mine.e1, j & 31);
+        if (lane == 0) {
+          const int s = j % kTileStages;
+          if (j >= kTileStages) mbar_wait_backoff(&S.empty[s], (uint32_t)(j / kTileStages - 1) & 1u);  // stage released
+          S.stage[s].desc = d;
+          tile_issue(G, d, S.stage[s], &S.full[s], pol);
+        }
+        __syncwarp();
       }
-      TileDesc d;
-      d.f0 = __shfl_sync(0xffffffffu, mine.f0, it & 31);
-      d.f1 = __shfl_sync(0xffffffffu, mine.f1, it & 31);
-      d.e0 = __shfl_sync(0xffffffffu, mine.e0, it & 31);
-      d.e1 = __shfl_sync(0xffffffffu, mine.e1, it & 31);
-      if (lane == 0) {
-        const int s = it % kTileStages;
-        if (it >= kTileStages) mbar_wait_backoff(&S.empty[s], (uint32_t)(it / kTileStages - 1) & 1u);  // stage released
-        S.stage[s].desc = d;
-        tile_issue(G, d, S.stage[s], &S.full[s], pol);
+      const int g = j - kGatherLag;  // the tile whose slice should have landed by now: gather its variables
+      if (g >= 0) {
+        const int sg = g % kTileStages;
+        TileStage& st = S.stage[sg];
+        mbar_wait(&S.full[sg], (uint32_t)(g / kTileStages) & 1u);
+        const TileDesc dg = st.desc;
+        const int ne = dg.e1 - dg.e0, eo = dg.e0 & 15;
+        if (ne <= kTileEdges) {
+#ifndef RDIS_EXP_NOGATHER
+          for (int le = lane; le < ne; le += 32) cp_async_gather8(&st.xs[eo + le], G.xval + st.evid[eo + le], keep);
+#endif
+        }
+        cp_async_arrive_noinc(&S.xready[sg]);  // fires when this lane's copies have landed
       }
-      __syncwarp();
     }
   } else {
     // ---- consumers ----
     const int lane = tid & 31;
-    int32_t vid[kEdgeBatch];
-    double2 xb[kEdgeBatch];
-    const uint64_t keep = l2_policy_evict_last();
-    // put the gathers of tile `j` (stage already landed) in flight
-    auto gather = [&](const TileStage& stg, const TileDesc& dd, int32_t (&v)[kEdgeBatch], double2 (&x)[kEdgeBatch]) {
-      const int n = dd.e1 - dd.e0, o = dd.e0 & 15;
-      if (n <= kTileEdges) {
-#pragma unroll
-        for (int i = 0; i < kEdgeBatch; ++i) {
-          const int le = i * kTileThreads + tid;
-          if (le < n) {
-            v[i] = stg.evid[o + le];
-#ifdef RDIS_EXP_NOGATHER
-            x[i] = make_double2((double)v[i], __longlong_as_double(0x7ff8000000000000LL));
-#else
-            x[i] = gather_var_pair(&G.xbd[v[i]], keep);
-#endif
-          }
-        }
-      }
-    };
-    mbar_wait(&S.full[0], 0u);
-    TileDesc d = S.stage[0].desc;
-    gather(S.stage[0], d, vid, xb);
-
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % kTileStages;
+      const uint32_t parity = (uint32_t)(it / kTileStages) & 1u;
       TileStage& st = S.stage[s];
+      mbar_wait(&S.xready[s], parity);
+      mbar_wait(&S.full[s], parity);  // already complete (the producer waited on it); makes the TMA writes visible here
+      const TileDesc d = st.desc;
       const int ne = d.e1 - d.e0;
-      // ---- the next tile: wait for its stage and put its gathers in flight (hidden behind this tile's math) ----
-      TileDesc dn = d;
-      int32_t vid_n[kEdgeBatch];
-      double2 xb_n[kEdgeBatch];
-      if (it + 1 < my_tiles) {
-        const int sn = (it + 1) % kTileStages;
-        mbar_wait(&S.full[sn], (uint32_t)((it + 1) / kTileStages) & 1u);
-        dn = S.stage[sn].desc;
-        gather(S.stage[sn], dn, vid_n, xb_n);
-      }
 
       if (ne > kTileEdges) {  // one over-wide factor, folded serially from global memory
         if (tid == 0) {
@@ -328,13 +328,17 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? 2 : kTileCtasPerSm)
         // ---- phase 1: staged edge slices -> terms (in place) ----
         double* term = st.expo + (d.e0 & 15);   // term[le] overwrites expo[le]
         double* dterm = st.konst + (d.e0 & 15);  // dterm[le] overwrites konst[le]
+        const double* xs = st.xs + (d.e0 & 15);
         const uint8_t* sine = st.sine + (d.e0 & 15);
 #pragma unroll
         for (int i = 0; i < kEdgeBatch; ++i) {
           const int le = i * kTileThreads + tid;
           if (le < ne) {
-            double xv = xb[i].x;
-            if (xb[i].y == xb[i].y) xv = clamp_live_var(G, vid[i], xv);  // variable of a running solve
+#ifdef RDIS_EXP_NOGATHER
+            const double xv = (double)st.evid[(d.e0 & 15) + le];
+#else
+            const double xv = xs[le];
+#endif
             const double ex = term[le], kk = dterm[le];
             const bool sn = sine[le] != 0;
             if (kGrad) {
@@ -389,12 +393,6 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? 2 : kTileCtasPerSm)
       // this warp is done with stage s: release it to the producer
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.empty[s]);
-      d = dn;
-#pragma unroll
-      for (int i = 0; i < kEdgeBatch; ++i) {
-        vid[i] = vid_n[i];
-        xb[i] = xb_n[i];
-      }
     }
   }
   block_then_grid_sum(acc, partials, counter, sum_out);

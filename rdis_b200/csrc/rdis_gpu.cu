@@ -96,7 +96,7 @@ struct rdisgpu_ctx {
   DevBuf<int32_t> rowptr, evid, vrow, vedge, efac, cam, pt, crow, cfac, prow, pfac, fstamp;
   DevBuf<TileDesc> tiles;  // NLPF: factor tiles of the streaming sweep (nlpf_tile_sweep.cuh)
   int ntiles = 0, tile_grid[2] = {0, 0};  // persistent grid size of the eval / grad instantiation
-  DevBuf<double> expo, konst, coeff, gedge, gvec, hvec, xsave, fconst_val;
+  DevBuf<double> expo, konst, coeff, gedge, gvec, hvec, xsave, fconst_val, xval;
   DevBuf<uint8_t> sine, fconst_on;
   DevBuf<double2> obs;
   bool has_fconst = false;
@@ -188,7 +188,7 @@ void fill_view(rdisgpu_ctx* c) {
   std::memset(&g, 0, sizeof g);
   g.kind = c->kind;
   g.V = c->V; g.F = c->F; g.E = c->E;
-  g.xbd = c->xbd.p; g.dom = c->dom.p;
+  g.xbd = c->xbd.p; g.xval = c->xval.p; g.dom = c->dom.p;
   g.rowptr = c->rowptr.p; g.evid = c->evid.p; g.expo = c->expo.p; g.konst = c->konst.p;
   g.sine = c->sine.p; g.coeff = c->coeff.p; g.vrow = c->vrow.p; g.vedge = c->vedge.p; g.efac = c->efac.p;
   g.cam = c->cam.p; g.pt = c->pt.p; g.obs = c->obs.p; g.ncams = c->ncams; g.npts = c->npts;
@@ -377,6 +377,8 @@ int rdisgpu_finalize(rdisgpu_ctx* ctx) {
   }
   CK(upload(ctx->dom, dom.data(), (size_t)V, s));
   CK(upload(ctx->xbd, xbd.data(), (size_t)V, s));
+  CK(ctx->xval.ensure((size_t)V));
+  CK(cudaMemsetAsync(ctx->xval.p, 0, (size_t)V * sizeof(double), s));
   CK(cudaStreamSynchronize(s));
 
   if (ctx->kind == KIND_NLPF) {

@@ -347,6 +347,7 @@ __device__ void solve_problem(const GraphView& G, Grp& grp, const BatchView& B, 
     const double raw = restore ? G.xsave[vid] : G.xbd[vid].x;
     const double val = clamp_to_domain(raw, G.dom[vid]);
     G.xbd[vid] = make_double2(val, __longlong_as_double(0x7ff8000000000000LL));  // freeze again
+    G.xval[vid] = val;
     B.xout[P.var_off + j] = val;
   }
   for (int k = grp.rank(); k < nf; k += grp.size()) G.fstamp[fids[k]] = -1;

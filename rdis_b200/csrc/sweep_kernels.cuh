@@ -15,6 +15,7 @@ __global__ void scatter_x_kernel(GraphView G, int64_t n, const int32_t* vid, con
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = vid ? vid[i] : i;
     G.xbd[v] = make_double2(x[i], qnan);
+    G.xval[v] = x[i];
   }
 }
 

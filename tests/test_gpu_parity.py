@@ -7,6 +7,8 @@ Tolerances (written here as the contract):
   final objective of a subspace solve     1e-6 relative (north_star), typically observed ~1e-12
   index bookkeeping (which variables moved, statuses of empty problems)   bit-exact
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -493,3 +495,15 @@ def test_solve_lm_blocks(gpu, oracle_mod):
     ctx.set_x(x0)
     r = ctx.solve_lm(emp, x0[emp.vids], 5, 3e-8)
     assert r["f_end"][0] == 0 and np.array_equal(r["x"], x0[emp.vids])
+
+
+@pytest.mark.gpu
+def test_inline_trig_is_bit_identical(built_lib):
+    """rdis_sin / rdis_cos / rdis_sincos (the inline kernels the NLPF terms use) == the CUDA library's
+    sin / cos to the bit on 8 M values incl. the slow-path threshold and the special values."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "rdis_b200", "host"), "all"], stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(root, "tests", "native", "trig_check")], capture_output=True, text=True)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
