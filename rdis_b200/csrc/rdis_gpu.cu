@@ -591,13 +591,14 @@ static int upload_fids(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, DevBuf<
 
 // Enqueues one residual sweep: fid_dev (device, nullable = all factors), per_factor_dev (device, nullable);
 // the total lands in *dsum_out (device scratch of the context).  No copies, no waiting.
-static int enqueue_eval(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, double* per_factor_dev, double** dsum_out) {
+static int enqueue_eval(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, double* per_factor_dev, double** dsum_out,
+                        double* sum_dst = nullptr /* device: write the total here instead of the context scratch */) {
   cudaStream_t s = ctx->stream;
   const int threads = 256;
   const bool tiled = (ctx->kind == KIND_NLPF && fid_dev == nullptr);
   const int blocks = tiled ? ctx->tile_grid[0] : (int)std::min<int64_t>((nf + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
   CK(ctx->s_partials.ensure((size_t)blocks + 1));
-  double* dsum = ctx->s_partials.p + blocks;
+  double* dsum = sum_dst ? sum_dst : ctx->s_partials.p + blocks;
   if (tiled)
     nlpf_tile_sweep_kernel<false><<<blocks, kTileThreads + 32, sizeof(TileSmem), s>>>(
         ctx->gv, ctx->tiles.p, ctx->ntiles, per_factor_dev, ctx->s_partials.p, ctx->s_counter.p, dsum);
@@ -650,10 +651,7 @@ int rdisgpu_eval_device(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, do
     return ctx->fail(RDISGPU_ERR_ARG, "eval_device: every pointer must be device memory");
   CK(cudaSetDevice(ctx->device));
   double* dsum = nullptr;
-  int rc = enqueue_eval(ctx, nf, fid_dev, per_factor_dev, &dsum);
-  if (rc) return rc;
-  if (sum_dev) CK(cudaMemcpyAsync(sum_dev, dsum, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  return RDISGPU_OK;
+  return enqueue_eval(ctx, nf, fid_dev, per_factor_dev, &dsum, sum_dev);  // the kernel writes the total straight to sum_dev
 }
 
 // Enqueues computeGradient over a factor list: phase A writes every listed factor's partials to gedge

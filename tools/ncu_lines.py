@@ -4,17 +4,22 @@ import csv
 import sys
 
 top = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 1  # 1-based index of the kernel in the report
 rows = list(csv.reader(sys.stdin))
-cur, hdr, agg, kernels = None, None, [], 0
+cur, hdr, agg, kernels, last_fn = None, None, [], 0, None
 for r in rows:
     if not r:
         continue
     if r[0] == 'Function Name':
-        kernels += 1
+        if len(r) > 1 and r[1] != last_fn:
+            kernels += 1
+            last_fn = r[1]
     if r[0] == 'File Path':
-        if kernels > 1:
+        if kernels > which:
             break
         cur = r[1].split('/')[-1]
+        continue
+    if kernels != which:
         continue
     if r[0] == 'Line No':
         hdr = r
