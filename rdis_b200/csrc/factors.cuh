@@ -457,9 +457,14 @@ struct BaOps {
     const double J00 = m.dist + t1 * pp00, J01 = t1 * pp01, J10 = t1 * pp01, J11 = m.dist + t1 * pp11;
     const double omc = (1 - c);
 
+    // The reference divides by P_z^2, P_z and |r| 24 times per observation (chain() is called six times);
+    // here each denominator is inverted once and multiplied: <= 1 ulp away per quotient, 21 fewer fp64
+    // division sequences on the evaluation's dependency chain.  (The VALUE path, project(), keeps the
+    // reference's divisions.)
+    const double iP22 = 1.0 / P22, iP2 = 1.0 / P[2], ivn = 1.0 / vnorm;
     auto chain = [&](double dP0, double dP1, double dP2) -> double {
-      const double dppx = (P[0] * dP2 - P[2] * dP0) / P22;
-      const double dppy = (P[1] * dP2 - P[2] * dP1) / P22;
+      const double dppx = (P[0] * dP2 - P[2] * dP0) * iP22;
+      const double dppy = (P[1] * dP2 - P[2] * dP1) * iP22;
       const double drx = m.res0 * (J00 * dppx + J01 * dppy);
       const double dry = m.res1 * (J10 * dppx + J11 * dppy);
       return f * (drx + dry);
@@ -481,33 +486,33 @@ struct BaOps {
 
     // rotation vector, component x
     {
-      const double d0 = (a[1] * a[1] + a[2] * a[2]) / vnorm;
-      const double d1 = -a[0] * a[1] / vnorm;
-      const double d2 = -a[0] * a[2] / vnorm;
+      const double d0 = (a[1] * a[1] + a[2] * a[2]) * ivn;
+      const double d1 = -a[0] * a[1] * ivn;
+      const double d2 = -a[0] * a[2] * ivn;
       g[0] = chain(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[0], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[0],
                      A20 * d0 + A21 * d1 + A22 * d2 + T2 * a[0]);
     }
     {
-      const double d0 = -a[0] * a[1] / vnorm;
-      const double d1 = (a[0] * a[0] + a[2] * a[2]) / vnorm;
-      const double d2 = -a[1] * a[2] / vnorm;
+      const double d0 = -a[0] * a[1] * ivn;
+      const double d1 = (a[0] * a[0] + a[2] * a[2]) * ivn;
+      const double d2 = -a[1] * a[2] * ivn;
       g[1] = chain(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[1], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[1],
                      A20 * d0 + A21 * d1 + A22 * d2 + T2 * a[1]);
     }
     {
-      const double d0 = -a[0] * a[2] / vnorm;
-      const double d1 = -a[1] * a[2] / vnorm;
-      const double d2 = (a[0] * a[0] + a[1] * a[1]) / vnorm;
+      const double d0 = -a[0] * a[2] * ivn;
+      const double d1 = -a[1] * a[2] * ivn;
+      const double d2 = (a[0] * a[0] + a[1] * a[1]) * ivn;
       g[2] = chain(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[2], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[2],
                      A20 * d0 + A21 * d1 + A22 * d2 + T2 * a[2]);
     }
     // translation
-    g[3] = (m.res0 * J00 + m.res1 * J10) * -f / P[2];
-    g[4] = (m.res0 * J01 + m.res1 * J11) * -f / P[2];
+    g[3] = (m.res0 * J00 + m.res1 * J10) * -f * iP2;
+    g[4] = (m.res0 * J01 + m.res1 * J11) * -f * iP2;
     {
       const double dpx = J00 * P[0] + J01 * P[1];
       const double dpy = J10 * P[0] + J11 * P[1];
-      g[5] = (m.res0 * dpx + m.res1 * dpy) * f / P22;
+      g[5] = (m.res0 * dpx + m.res1 * dpy) * f * iP22;
     }
     // intrinsics
     g[6] = m.res0 * (m.dist * m.pp0) + m.res1 * (m.dist * m.pp1);
