@@ -296,14 +296,54 @@ struct CamShared {
   double p[9], xi[9], g[9], h[9], xs[9];
   double2 dom[9];
   double red[2][kCamMaxCluster * kCamMaxWarps][kCamRedWidth];
+  unsigned long long mbar[2];  // one transaction barrier per reduction buffer (remote st.async completes on it)
 };
 
-// All-reduce of `n` doubles per thread over the whole cluster, fixed order: warp butterfly, lane 0
-// stores the warp's partial into slot (cta*nw + warp) of EVERY CTA's buffer (distributed shared
-// memory), one cluster barrier, then every thread folds the C*nw partials in slot order.
+// ---- PTX wrappers: transaction barriers + asynchronous stores into a peer CTA's shared memory ----
+__device__ __forceinline__ uint32_t cam_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cam_map_to_cta(uint32_t local_addr, uint32_t cta_rank) {  // shared::cta -> shared::cluster of a peer
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void cam_st_async_v2(uint32_t remote_addr, double a, double b, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
+               "d"(a), "d"(b), "r"(remote_mbar)
+               : "memory");
+}
+__device__ __forceinline__ void cam_mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cam_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cam_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cam_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cam_mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t a = cam_smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+
+// All-reduce of N doubles per thread over the whole cluster, fixed order: warp butterfly, then lane d of
+// every warp pushes the warp's partial into slot (cta*nw + warp) of CTA d's buffer with ASYNCHRONOUS
+// stores over distributed shared memory that complete a transaction barrier in the receiving CTA
+// (st.async ... mbarrier::complete_tx).  A CTA just waits for its own barrier to have received
+// C*nw*N*8 bytes: one one-way trip per evaluation instead of remote stores + a two-phase cluster
+// barrier.  The buffers (and their barriers) alternate; re-use two rounds later is safe because a warp
+// can only send round r+1 after all its lanes folded round r, and nobody finishes round r+1 before every
+// warp of the cluster has sent it.  `phase` holds the two barriers' parities.
 template <int N>
-__device__ __forceinline__ void cluster_allreduce(cooperative_groups::cluster_group& cluster, CamShared& sh, int& flip,
-                                                  double (&v)[N], int C, int cta) {
+__device__ __forceinline__ void cluster_allreduce(CamShared& sh, int& flip, uint32_t& phase, double (&v)[N], int C, int cta) {
+  static_assert(N % 2 == 0, "partials travel as 16-byte pairs");
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -318,12 +358,15 @@ __device__ __forceinline__ void cluster_allreduce(cooperative_groups::cluster_gr
     }
     __syncthreads();
   } else {
+    if (threadIdx.x == 0) cam_mbar_expect_tx(&sh.mbar[flip], (uint32_t)(C * nw * N * 8));
     if (lane < C) {  // lane d delivers this warp's partial to CTA d
-      double* remote = cluster.map_shared_rank(&sh.red[flip][slot][0], lane);
+      const uint32_t dst = cam_map_to_cta(cam_smem_u32(&sh.red[flip][slot][0]), (uint32_t)lane);
+      const uint32_t bar = cam_map_to_cta(cam_smem_u32(&sh.mbar[flip]), (uint32_t)lane);
 #pragma unroll
-      for (int i = 0; i < N; ++i) remote[i] = v[i];
+      for (int i = 0; i < N; i += 2) cam_st_async_v2(dst + 8u * i, v[i], v[i + 1], bar);
     }
-    cluster.sync();
+    cam_mbar_wait(&sh.mbar[flip], (phase >> flip) & 1u);
+    phase ^= (1u << flip);
   }
   const int total = C * nw;
 #pragma unroll
@@ -351,6 +394,12 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
   const int rank = cta * T + threadIdx.x;
   const int size = C * T;
   int flip = 0;
+  uint32_t phase = 0;
+  if (threadIdx.x == 0) {
+    cam_mbar_init(&sh.mbar[0], 1);
+    cam_mbar_init(&sh.mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   if (threadIdx.x < 9) {
     const int j = threadIdx.x;
@@ -376,6 +425,7 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
     }
   }
   __syncthreads();
+  if (C > 1) cluster.sync();  // every CTA's barriers are initialised before a peer's st.async can reach them
   (void)cam;
 
   CgdMachine mc;
@@ -433,7 +483,7 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
         if (fc_on) fv = fc_val;
         v2[0] += fv;
       }
-      cluster_allreduce<2>(cluster, sh, flip, v2, C, cta);
+      cluster_allreduce<2>(sh, flip, phase, v2, C, cta);
       mc.on_eval(v2[0], v2[1]);
       if (mc.req == REQ_MOVE) {
         const double step = mc.alpha;
@@ -463,7 +513,7 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
         if (fc_on) fv = fc_val;
         acc[0] += fv;
       }
-      cluster_allreduce<kCamRedWidth>(cluster, sh, flip, acc, C, cta);
+      cluster_allreduce<kCamRedWidth>(sh, flip, phase, acc, C, cta);
       if (kind == REQ_INIT_GRAD) {
         if (threadIdx.x < 9) {
           const int j = threadIdx.x;
