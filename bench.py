@@ -20,8 +20,8 @@ accumulate the global objective, which is all-reduced across ranks (the path's o
                   per sweep — larger than L2): the HBM-roofline evidence for the sweep kernel
   cpu_baseline    the CPU oracle (reference-semantics port, 1 core) on a bounded sample of the wave
 
-Multi-GPU (weak scaling): every rank owns one ladybug-shaped component set (seed + rank); no data
-path collective besides the objective all-reduce.
+Multi-GPU (weak scaling): every rank owns one copy of the ladybug-shaped component set (same seed, equal
+work per GPU); no data path collective besides the objective all-reduce.
 """
 import argparse
 import json
@@ -137,8 +137,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- workload: one ladybug-shaped component set per rank ----
-    spec = P.ba_synthetic(seed=SEED + rank)
+    # ---- workload: one ladybug-shaped component set per rank.  Every rank generates the SAME set (same seed):
+    #      weak scaling with exactly equal work per GPU, so that the per-N numbers measure the system (launch,
+    #      NCCL all-reduce, host contention) and not the luck of a rank's longest line-search chain ----
+    spec = P.ba_synthetic(seed=SEED)
     x0 = spec["x0"]
     pts, cams = P.ba_point_problems(spec), P.ba_camera_problems(spec)
     n_solves = pts.n + cams.n
@@ -277,7 +279,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "ladybug-49-7776-shaped BA graph (49 cams, 7776 pts, 31843 obs) per GPU: "
                                    "7776 point-component + 49 camera-component CGD solves per step",
-                       "ssmaxit": MAXITERS, "ssftol": FTOL, "parallelism": "component-shard x%d" % world,
+                       "ssmaxit": MAXITERS, "ssftol": FTOL, "parallelism": "component-shard x%d (one copy of the component set per rank, objective all-reduced)" % world,
                        "l2": "flushed between steps (256 MiB memset + read pass, untimed)", "seed": SEED,
                        "mapping": {"points": b_pts.info(), "cameras": b_cams.info()}},
             "residual_evals_per_sec": resid_evals_per_s,

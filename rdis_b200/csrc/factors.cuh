@@ -310,9 +310,29 @@ struct NlpfOps {
     double acc = 0.0;
     bool first = true;
     const int32_t r0 = __ldg(&G.vrow[vid]), r1 = __ldg(&G.vrow[vid + 1]);
+    if (!filter) {
+      // all factors contribute: fetch the partials eight at a time (independent loads in flight),
+      // fold them in the same ascending order
+      for (int32_t r = r0; r < r1; r += 8) {
+        int32_t e[8];
+        double ge[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = (r + i < r1) ? __ldg(&G.vedge[r + i]) : -1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ge[i] = (e[i] >= 0) ? G.gedge[e[i]] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (e[i] >= 0) {
+            acc = first ? ge[i] : acc + ge[i];
+            first = false;
+          }
+        }
+      }
+      return acc;
+    }
     for (int32_t r = r0; r < r1; ++r) {
       const int32_t e = __ldg(&G.vedge[r]);
-      if (filter && G.fstamp[__ldg(&G.efac[e])] != stamp) continue;
+      if (G.fstamp[__ldg(&G.efac[e])] != stamp) continue;
       const double ge = G.gedge[e];
       acc = first ? ge : acc + ge;
       first = false;
