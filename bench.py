@@ -111,6 +111,16 @@ def algorithmic_bytes(spec, ps, res):
     return float(np.sum(n_f * (32.0 * nf + 8.0 * touched) + n_g * 8.0 * touched))
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel, {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -292,7 +302,8 @@ def run_ours(args):
                     "steps": e2e_steps, "objective": obj_e2e},
             "lm_wave": lm_info,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "solve_ba_points_kernel (point components)" if dom_is_pts
+                         "traffic": measured_traffic("solve_ba_points_kernel" if dom_is_pts else "solve_ba_cameras_kernel"),
+                         "kernel": "solve_ba_points_kernel (point components)" if dom_is_pts
                          else "solve_ba_cameras_kernel (camera components)",
                          "algorithmic_bytes_per_launch": abytes, "launch_ms": float(dom_ms), "peak_source": peak_src,
                          "note": "working set 1.4 MB: L2-resident, FP64/latency bound; see roofline_sweep for the HBM-bound kernel"},
@@ -360,7 +371,8 @@ def sweep_roofline(device, stream):
     abytes = 20.0 * F + 21.0 * E + 8.0 * V
     ach = abytes / (ms * 1e-3) / 1e9
     out = {"bound": "hbm", "kernel": "nlpf_tile_sweep_kernel<false>", "workload": "sinusoid h=19 k=2 arity=4: V=%d F=%d E=%d" % (V, F, E),
-           "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+           "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+           "traffic": measured_traffic("nlpf_tile_sweep_kernel<false>"),
            "algorithmic_bytes_per_launch": abytes, "launch_ms": ms, "launch_ms_single_flushed": ms_flushed,
            "frac_single_flushed": abytes / (ms_flushed * 1e-3) / 1e9 / peak, "launch_ms_min": ms_min,
            "factor_evals_per_sec": F / (ms * 1e-3), "sum": s, "peak_source": peak_src,
