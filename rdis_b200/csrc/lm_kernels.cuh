@@ -21,6 +21,7 @@
 //   control flow  thread 0, decisions broadcast through shared memory
 #pragma once
 #include "factors.cuh"
+#include "ba_block_kernels.cuh"
 #include "solve_kernels.cuh"
 
 namespace rdisgpu {
@@ -147,10 +148,10 @@ __device__ inline bool lm_ax_eq_b_lu(LmShared& sh, int m) {
 enum LmDecision : int { LM_CONTINUE = 0, LM_STOP = 1, LM_TRY = 2, LM_ACCEPT = 3, LM_REJECT = 4 };
 
 template <class Ops>
-__global__ void __launch_bounds__(kLmThreads) solve_lm_block_kernel(GraphView G, BatchView B, LmView L, int itmax, double tau,
-                                                                    double eps1, double eps2, double eps3) {
+__global__ void __launch_bounds__(kLmThreads) solve_lm_block_kernel(GraphView G, BatchView B, LmView L, const int32_t* order,
+                                                                    int itmax, double tau, double eps1, double eps2, double eps3) {
   __shared__ LmShared sh;
-  const int pidx = blockIdx.x;
+  const int pidx = order ? order[blockIdx.x] : (int)blockIdx.x;
   const ProblemDesc P = B.probs[pidx];
   const int m = P.nv, nf = P.nf;
   const int n = (nf > m) ? nf : m;
@@ -382,6 +383,247 @@ __global__ void __launch_bounds__(kLmThreads) solve_lm_block_kernel(GraphView G,
     r.n_value = nfev;
     r.n_slope = njev;
     B.res[pidx] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bundle-adjustment point blocks (3 variables, <= 32 observations): the same Levenberg-Marquardt
+// iteration in registers, one lane per observation, 32/G problems per warp — the LM counterpart of
+// solve_ba_points_kernel.  Every pass of the loop is ONE evaluation (value + the three point partials)
+// of every unfinished problem of the warp, executed converged; the 3 x 3 normal equations are reduced
+// with tile shuffles and solved redundantly by every lane (LDL^T: J^T J + mu I is positive definite).
+// Same control flow, stop codes and counters as solve_lm_block_kernel; sums are folded in shuffle-tree
+// order instead of row order, so results agree with it (and with the oracle) to rounding.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool lm_solve_spd3(const double (&A)[6], double mu, const double (&b)[3], double (&x)[3]) {
+  // A = [a00 a10 a11 a20 a21 a22] (lower triangle), solve (A + mu I) x = b
+  const double a00 = A[0] + mu, a10 = A[1], a11 = A[2] + mu, a20 = A[3], a21 = A[4], a22 = A[5] + mu;
+  const double d0 = a00;
+  if (!(d0 > 0.0)) return false;
+  const double l10 = a10 / d0, l20 = a20 / d0;
+  const double d1 = a11 - l10 * a10;
+  if (!(d1 > 0.0)) return false;
+  const double l21 = (a21 - l20 * a10) / d1;
+  const double d2 = a22 - l20 * a20 - l21 * (a21 - l20 * a10);
+  if (!(d2 > 0.0)) return false;
+  const double y0 = b[0];
+  const double y1 = b[1] - l10 * y0;
+  const double y2 = b[2] - l20 * y0 - l21 * y1;
+  const double z2 = y2 / d2;
+  const double z1 = y1 / d1 - l21 * z2;
+  const double z0 = y0 / d0 - l10 * z1 - l20 * z2;
+  x[0] = z0; x[1] = z1; x[2] = z2;
+  return true;
+}
+
+__global__ void __launch_bounds__(32) solve_lm_ba_points_kernel(GraphView Gv, BatchView B, const int32_t* order,
+                                                                const PointWarpTask* tasks, int itmax, double tau, double eps1,
+                                                                double eps2, double eps3) {
+  const PointWarpTask t = tasks[blockIdx.x];
+  const int lg = t.lg;
+  const int G = 1 << lg;
+  const int lane = threadIdx.x & 31;
+  const int r = lane & (G - 1);
+  const int slot = lane >> lg;
+  const int pidx = (slot < t.count) ? order[t.first + slot] : -1;
+  const bool run = (pidx >= 0);
+  ProblemDesc P;
+  P.var_off = 0; P.fac_off = 0; P.nv = 0; P.nf = 0;
+  if (run) P = B.probs[pidx];
+  const int nf = P.nf;
+  const int32_t v0 = run ? B.vids[P.var_off] : 0;
+  const unsigned kFull = 0xffffffffu;
+
+  double p[3], q[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    p[j] = 0.0;
+    if (run) p[j] = (B.x0 != nullptr) ? B.x0[P.var_off + j] : Gv.xbd[v0 + j].x;
+    q[j] = p[j];
+  }
+  const bool have = run && (r < nf);
+  double x[12];
+  double2 ob = make_double2(0.0, 0.0);
+  BaOps::Fwd m;
+  bool fc_on = false;
+  double fc_val = 0.0;
+#pragma unroll
+  for (int s = 0; s < 12; ++s) x[s] = 0.0;
+  m.a0 = m.a1 = m.a2 = m.theta = m.s = 0.0; m.c = 1.0;
+  if (have) {
+    const int32_t fid = B.fids[P.fac_off + r];
+    const int32_t cam = __ldg(&Gv.cam[fid]);
+    ob = __ldg(&Gv.obs[fid]);
+#pragma unroll
+    for (int s = 0; s < 9; ++s) x[s] = Gv.xbd[9 * cam + s].x;
+    BaOps::rotation(x[0], x[1], x[2], m);
+    if (Gv.fconst_on != nullptr && Gv.fconst_on[fid]) {
+      fc_on = true;
+      fc_val = Gv.fconst_val[fid];
+    }
+  }
+
+  // levmar state (replicated in every lane of the tile)
+  double A[6] = {0, 0, 0, 0, 0, 0}, Jte[3] = {0, 0, 0}, Dp[3] = {0, 0, 0};
+  double mu = 0.0, p_eL2 = 0.0, ival = 0.0, fval = 0.0, p_L2 = 0.0;
+  int nu = 2, stop = 0, nfev = 0, njev = 0, k_it = 0;
+  bool fin = !run, first = true, at_commit = false;
+
+  while (true) {
+    if (__all_sync(kFull, fin)) break;
+    // ---- one evaluation at q: value, residual, the three point partials ----
+    double fv = 0.0, h = 0.0, j0 = 0.0, j1 = 0.0, j2 = 0.0;
+    if (have && !fin) {
+      x[9] = q[0]; x[10] = q[1]; x[11] = q[2];  // no clamping (LMSubspaceOptimizer.cpp:281-297)
+      fv = BaOps::project(x, ob, m);
+      double gq[12];
+      BaOps::partials(x, m, gq);
+      if (fc_on) fv = fc_val;
+      h = sqrt(fv * 2.0);
+      j0 = gq[9] / h; j1 = gq[10] / h; j2 = gq[11] / h;
+    }
+    // tile reductions: sum f, ||hx||^2, J^T J (lower), J^T e with e = -hx
+    double red[11] = {fv, h * h, j0 * j0, j1 * j0, j1 * j1, j2 * j0, j2 * j1, j2 * j2, j0 * (-h), j1 * (-h), j2 * (-h)};
+    for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 11; ++i) red[i] += __shfl_xor_sync(kFull, red[i], o);
+    }
+    if (fin) continue;
+
+    // ---- the scalar part of levmar's loop (diverges between the tiles of a warp) ----
+    const double e2 = red[1];
+    bool new_point = false;  // q became the current point p: redo the top of the outer loop
+    if (at_commit) {         // final evalFactors at the returned point (LMSubspaceOptimizer.cpp:110)
+      fval = red[0];
+      fin = true;
+    } else if (first) {
+      first = false;
+      ival = red[0];
+      p_eL2 = e2;
+      nfev = 1;
+      if (!(fabs(p_eL2) <= 1.7976931348623157e308)) stop = 7;
+      new_point = true;
+    } else {
+      ++nfev;
+      const double pDp_eL2 = e2;
+      bool accepted = false;
+      if (!(fabs(pDp_eL2) <= 1.7976931348623157e308)) {
+        stop = 7;
+      } else {
+        double dL = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) dL += Dp[i] * (mu * Dp[i] + Jte[i]);
+        const double dF = p_eL2 - pDp_eL2;
+        if (dL > 0.0 && dF > 0.0) {
+          double tt = (2.0 * dF / dL - 1.0);
+          tt = 1.0 - tt * tt * tt;
+          mu = mu * ((tt >= 0.3333333334) ? tt : 0.3333333334);
+          nu = 2;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) p[i] = q[i];
+          p_eL2 = pDp_eL2;
+          accepted = true;
+        }
+      }
+      if (stop) {
+        ++k_it;  // the for-loop's increment after the inner break
+      } else if (accepted) {
+        ++k_it;
+        new_point = true;
+      } else {
+        mu *= nu;
+        const int nu2 = nu << 1;
+        if (nu2 <= nu) {
+          stop = 5;
+          ++k_it;
+        }
+        nu = nu2;
+      }
+    }
+    // top of the outer loop at a (new) current point: stop tests, normal equations of THIS evaluation
+    if (!fin && !stop && new_point) {
+      if (k_it >= itmax) {
+        stop = 3;
+      } else if (p_eL2 <= eps3) {
+        stop = 6;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) A[i] = red[2 + i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Jte[i] = red[8 + i];
+        ++njev;
+        double jinf = 0.0;
+        p_L2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double a = fabs(Jte[i]);
+          if (jinf < a) jinf = a;
+          p_L2 += p[i] * p[i];
+        }
+        if (jinf <= eps1) {
+          stop = 1;
+        } else if (k_it == 0) {
+          double mx = A[0];
+          if (A[2] > mx) mx = A[2];
+          if (A[5] > mx) mx = A[5];
+          mu = tau * mx;
+        }
+      }
+    }
+    // next trial point (also after a rejection): solve, step tests
+    if (!fin && !stop) {
+      while (true) {
+        if (lm_solve_spd3(A, mu, Jte, Dp)) {
+          double d2 = 0.0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            q[i] = p[i] + Dp[i];
+            d2 += Dp[i] * Dp[i];
+          }
+          if (d2 <= eps2 * eps2 * p_L2) {
+            stop = 2;
+            ++k_it;
+          } else if (d2 >= (p_L2 + eps2) / (1e-12 * 1e-12)) {
+            stop = 4;
+            ++k_it;
+          }
+          break;
+        }
+        mu *= nu;  // the linear system could not be solved: reject without an evaluation
+        const int nu2 = nu << 1;
+        if (nu2 <= nu) {
+          stop = 5;
+          ++k_it;
+          break;
+        }
+        nu = nu2;
+      }
+    }
+    if (!fin && stop) {  // leave the loop: one more evaluation at the returned point p
+      if (k_it >= itmax) stop = 3;
+      at_commit = true;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) q[i] = p[i];
+    }
+  }
+
+  if (!run) return;
+  if (r == 0) {
+    const double qn = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      Gv.xbd[v0 + j] = make_double2(p[j], qn);
+      Gv.xval[v0 + j] = p[j];
+      B.xout[P.var_off + j] = p[j];
+    }
+    ResultRec res;
+    res.f_init = ival;
+    res.f_end = fval;
+    res.iters = k_it;
+    res.status = stop;
+    res.n_value = nfev;
+    res.n_slope = njev;
+    B.res[pidx] = res;
   }
 }
 

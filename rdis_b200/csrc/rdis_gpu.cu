@@ -1290,13 +1290,27 @@ int rdisgpu_solve_lm_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_of
   lv.scr_off = ctx->lm_off.p;
   const double tau = opts4 ? opts4[0] : 1e-3, eps1 = opts4 ? opts4[1] : 1e-15, eps2 = opts4 ? opts4[2] : 1e-15,
                eps3 = opts4 ? opts4[3] : 3e-8;
-  if (ctx->kind == KIND_NLPF)
-    solve_lm_block_kernel<NlpfOps><<<(unsigned)nprobs, kLmThreads, 0, s>>>(ctx->gv, bv, lv, maxiters, tau, eps1, eps2, eps3);
-  else
-    solve_lm_block_kernel<BaOps><<<(unsigned)nprobs, kLmThreads, 0, s>>>(ctx->gv, bv, lv, maxiters, tau, eps1, eps2, eps3);
-  ++ctx->launches;
-  b->last_launches = 1;
-  CK(cudaGetLastError());
+  // bundle-adjustment point blocks run register-resident (one lane per observation); camera blocks and
+  // every other shape take the generic one-CTA-per-component kernel
+  int launches = 0;
+  if (b->n_pt_warps > 0) {
+    solve_lm_ba_points_kernel<<<b->n_pt_warps, 32, 0, s>>>(ctx->gv, bv, b->d_pt_order, b->d_pt_tasks, maxiters, tau, eps1, eps2, eps3);
+    ++launches;
+    CK(cudaGetLastError());
+  }
+  auto launch_generic = [&](const int32_t* order, int count) -> cudaError_t {
+    if (count <= 0) return cudaSuccess;
+    if (ctx->kind == KIND_NLPF)
+      solve_lm_block_kernel<NlpfOps><<<(unsigned)count, kLmThreads, 0, s>>>(ctx->gv, bv, lv, order, maxiters, tau, eps1, eps2, eps3);
+    else
+      solve_lm_block_kernel<BaOps><<<(unsigned)count, kLmThreads, 0, s>>>(ctx->gv, bv, lv, order, maxiters, tau, eps1, eps2, eps3);
+    ++launches;
+    return cudaGetLastError();
+  };
+  CK(launch_generic(b->d_cam_order, b->n_cam));
+  CK(launch_generic(b->d_order, (int)b->h_order.size()));
+  ctx->launches += launches;
+  b->last_launches = launches;
   CK(cudaMemcpyAsync(b->h_res.p, b->res.p, (size_t)nprobs * sizeof(ResultRec), cudaMemcpyDeviceToHost, s));
   if (x_out && b->total_nv > 0)
     CK(cudaMemcpyAsync(b->h_x.p, b->xout.p, (size_t)b->total_nv * sizeof(double), cudaMemcpyDeviceToHost, s));
