@@ -13,6 +13,7 @@
 #include <iostream>
 #include <memory>
 
+#include "rdis_builders.h"
 #include "rdis_host.h"
 
 using namespace rdis;
@@ -82,6 +83,80 @@ int main(int argc, char** argv) {
     return 2;
   }
   try {
+    if (std::string(argv[1]) == "loadbal") {  // loadbal <bal file> [ncams npts]: the BAL loader's view of the file
+      BundleAdjustmentFunction fn;
+      const long long nc = argc > 3 ? std::atoll(argv[3]) : -1, np = argc > 4 ? std::atoll(argv[4]) : -1;
+      if (!fn.load(argv[2], nc, np)) {
+        std::printf("load failed\n");
+        return 1;
+      }
+      std::printf("V %lld F %zu ncams %lld npts %lld blocks %lld\n", fn.getNumVars(), fn.getFactors().size(), fn.getNumCameras(),
+                  fn.getNumPoints(), fn.getNumBlocks());
+      for (const Factor* f : fn.getFactors()) {
+        const BundleAdjustmentFactor* b = static_cast<const BundleAdjustmentFactor*>(f);
+        std::printf("f %d %d %.17g %.17g %lld %lld\n", b->getCamera(), b->getPoint(), b->obsX(), b->obsY(),
+                    b->getVariables()[0]->getID(), b->getVariables()[9]->getID());
+      }
+      for (Variable* v : fn.getVariables())
+        std::printf("v %.17g %.17g %.17g %.17g %.17g %lld\n", fn.getInitialState()[(size_t)v->getID()], v->getDomain().min(),
+                    v->getDomain().max(), v->getDomain().samplingMin(), v->getDomain().samplingMax(), fn.getBlockID(v->getID()));
+      return 0;
+    }
+    if (std::string(argv[1]) == "bawaves") {  // bawaves <bal file> <rounds> [lm]: alternating point / camera waves from the file state
+      BundleAdjustmentFunction fn;
+      if (!fn.load(argv[2])) return 1;
+      const int rounds = argc > 3 ? std::atoi(argv[3]) : 2;
+      const bool lm = argc > 4 && std::string(argv[4]) == "lm";
+      fn.init(0);
+      CudaSubspaceOptimizer cgd(fn);
+      CudaLMSubspaceOptimizer lmo(fn);
+      CudaSubspaceOptimizer& ssopt = lm ? static_cast<CudaSubspaceOptimizer&>(lmo) : cgd;
+      ParameterMap opts;
+      opts["SSmaxit"] = 25;  // the optBA default (src/RDISOptimizer.cpp:107)
+      ssopt.setParameters(opts);
+      const NumericVec& x0 = fn.getInitialState();
+      VariablePtrVec& vars = fn.getVariables();
+      for (Variable* v : vars) v->assign(x0[(size_t)v->getID()]);
+      std::printf("objective %.17g\n", fn.eval());
+      const VariableID npv = 9 * fn.getNumCameras();
+      for (int rd = 0; rd < 2 * rounds; ++rd) {
+        // un-assign one side (points on even half-rounds, cameras on odd): its blocks become the sibling components
+        const bool points = (rd % 2 == 0);
+        NumericVec cur((size_t)fn.getNumVars());
+        for (Variable* v : vars) cur[(size_t)v->getID()] = v->eval();
+        VariableIDVec open;
+        for (Variable* v : vars)
+          if ((v->getID() >= npv) == points) {
+            v->unassign();
+            open.push_back(v->getID());
+          }
+        std::vector<ChildComponent> kids;
+        ComponentBatcher::createChildren(fn, open, kids);
+        std::vector<ComponentProblem> probs(kids.size());
+        for (size_t k = 0; k < kids.size(); ++k) ComponentBatcher::leafProblem(fn, kids[k], cur, probs[k]);
+        const double total = ssopt.optimizeBatch(probs, false);
+        std::printf("wave %d %s components %zu sum %.17g objective %.17g\n", rd, points ? "points" : "cameras", kids.size(), total,
+                    fn.eval());
+      }
+      return 0;
+    }
+    if (std::string(argv[1]) == "sinusoid") {  // sinusoid <height> <branches> <maxArity> <odd>
+      if (argc < 6) return 2;
+      std::unique_ptr<OptimizableFunction> fn(makeHighDimSinusoid(std::atoll(argv[2]), std::atoll(argv[3]), std::atoll(argv[4]),
+                                                                  std::atoi(argv[5]) != 0));
+      std::printf("V %lld F %zu dom %.17g %.17g samp %.17g %.17g\n", fn->getNumVars(), fn->getFactors().size(),
+                  fn->getVariables()[0]->getDomain().min(), fn->getVariables()[0]->getDomain().max(),
+                  fn->getVariables()[0]->getDomain().samplingMin(), fn->getVariables()[0]->getDomain().samplingMax());
+      for (const Factor* f : fn->getFactors()) {
+        const NonlinearProductFactor* n = static_cast<const NonlinearProductFactor*>(f);
+        std::printf("f %.17g %zu", n->getCoefficient(), n->numVars());
+        for (size_t i = 0; i < n->numVars(); ++i)
+          std::printf(" %lld %.17g %.17g %d", n->getVariables()[i]->getID(), n->getTerms()[i].exponent, n->getTerms()[i].constant,
+                      n->getTerms()[i].useSine ? 1 : 0);
+        std::printf("\n");
+      }
+      return 0;
+    }
     Loaded L = load(argv[2]);
     const std::string mode = argv[1];
     assign_flagged(L);

@@ -190,3 +190,101 @@ def test_host_adapter_nlpf_subtrees(driver, oracle_mod, tmp_path):
     rel = np.abs(got - o["f_end"]) / np.maximum(np.abs(o["f_end"]), 1e-12)
     print("nlpf subtrees through the C++ adapter: worst rel diff", rel.max())
     assert rel.max() <= 1e-6
+
+
+def _write_bal(path, spec, x0):
+    nc, npnt = spec["ncams"], spec["npts"]
+    with open(path, "w") as fh:
+        fh.write("%d %d %d\n" % (nc, npnt, spec["F"]))
+        for c, p, (ox, oy) in zip(spec["cam"], spec["pt"], np.asarray(spec["obs"]).reshape(-1, 2)):
+            fh.write("%d %d     %s %s\n" % (c, p, repr(float(ox)), repr(float(oy))))
+        for v in x0:
+            fh.write("%s\n" % repr(float(v)))
+
+
+def _parse_loadbal(text):
+    lines = text.strip().splitlines()
+    head = dict(zip(lines[0].split()[0::2], [int(t) for t in lines[0].split()[1::2]]))
+    fac = np.array([[float(t) for t in ln.split()[1:]] for ln in lines[1:] if ln.startswith("f ")])
+    var = np.array([[float(t) for t in ln.split()[1:]] for ln in lines[1:] if ln.startswith("v ")])
+    return head, fac, var
+
+
+def test_bal_loader_and_sinusoid_generator_cpu(driver, oracle_mod, tmp_path):
+    """The host layer's problem builders (rdis_builders.h) against (a) the generators bench.py / the tests use,
+    (b) the oracle's restatement of the reference loader on a BAL file, incl. the ncams / npts truncation, and
+    (c) where the reference tree is mounted, its own ladybug file vs the committed fixture — all to the bit."""
+    from rdis_b200 import problems as P
+    spec = P.ba_synthetic(ncams=5, npts=40, nobs=150, seed=3)
+    x0 = spec["x0"]
+    bal = str(tmp_path / "small.bal")
+    _write_bal(bal, spec, x0)
+    head, fac, var = _parse_loadbal(subprocess.run([driver, "loadbal", bal], capture_output=True, text=True, check=True).stdout)
+    assert head == {"V": spec["V"], "F": spec["F"], "ncams": 5, "npts": 40, "blocks": 45}
+    assert np.array_equal(fac[:, 0], spec["cam"]) and np.array_equal(fac[:, 1], spec["pt"])
+    assert np.array_equal(fac[:, 2:4], np.asarray(spec["obs"]).reshape(-1, 2))
+    assert np.array_equal(fac[:, 4], 9 * spec["cam"]) and np.array_equal(fac[:, 5], 9 * 5 + 3 * spec["pt"])
+    lb, ub, slo, shi = P.ba_domains(x0, 5)
+    assert np.array_equal(var[:, 0], x0) and np.array_equal(var[:, 1], lb) and np.array_equal(var[:, 2], ub)
+    assert np.array_equal(var[:, 3], slo) and np.array_equal(var[:, 4], shi)
+    assert np.array_equal(var[:, 5], np.concatenate([np.repeat(np.arange(5), 9), 5 + np.repeat(np.arange(40), 3)]))
+    # truncated load (optBA --ncams 3 --npts 25): the oracle's restatement of the reference loader agrees
+    head, fac, var = _parse_loadbal(subprocess.run([driver, "loadbal", bal, "3", "25"], capture_output=True, text=True, check=True).stdout)
+    o = oracle_mod.OracleFunction.load_bal(bal, 3, 25).export()
+    assert head["V"] == o["V"] and head["F"] == o["F"]
+    assert np.array_equal(fac[:, 0], o["cam"]) and np.array_equal(fac[:, 1], o["pt"])
+    assert np.array_equal(fac[:, 2:4], o["obs"].reshape(-1, 2))
+    assert np.array_equal(var[:, 0], o["x0"]) and np.array_equal(var[:, 1], o["lb"]) and np.array_equal(var[:, 2], o["ub"])
+    # the reference's own data file, where mounted
+    ref = "/root/reference/data/ladybug-problem-49-7776-pre.txt"
+    if os.path.exists(ref):
+        head, fac, var = _parse_loadbal(subprocess.run([driver, "loadbal", ref], capture_output=True, text=True, check=True).stdout)
+        g = P.load_golden_ba()
+        assert head["V"] == 23769 and head["F"] == 31843
+        assert np.array_equal(fac[:, 0], g["cam"]) and np.array_equal(fac[:, 1], g["pt"]) and np.array_equal(fac[:, 2:4], g["obs"])
+        assert np.array_equal(var[:, 0], g["x0"]) and np.array_equal(var[:, 1], g["lb"]) and np.array_equal(var[:, 2], g["ub"])
+    # sinusoid generator
+    for (h, k, ar, odd) in ((6, 3, 4, 0), (5, 2, 4, 1), (9, 1, 3, 0)):
+        out = subprocess.run([driver, "sinusoid", str(h), str(k), str(ar), str(odd)], capture_output=True, text=True, check=True).stdout
+        lines = out.strip().splitlines()
+        sp = P.sinusoid(h, k, ar, odd=bool(odd))
+        t = lines[0].split()
+        assert int(t[1]) == sp["V"] and int(t[3]) == sp["F"]
+        assert float(t[5]) == sp["lb"][0] and float(t[6]) == sp["ub"][0] and float(t[8]) == sp["samp_lo"][0] and float(t[9]) == sp["samp_hi"][0]
+        vid, expo, konst, sine, coeff, lens = [], [], [], [], [], []
+        for ln in lines[1:]:
+            tk = ln.split()
+            coeff.append(float(tk[1])); n = int(tk[2]); lens.append(n)
+            for i in range(n):
+                vid.append(int(tk[3 + 4 * i])); expo.append(float(tk[4 + 4 * i])); konst.append(float(tk[5 + 4 * i])); sine.append(int(tk[6 + 4 * i]))
+        assert np.array_equal(np.concatenate([[0], np.cumsum(lens)]), sp["rowptr"])
+        assert np.array_equal(vid, sp["vid"]) and np.array_equal(expo, sp["expo"]) and np.array_equal(konst, sp["konst"])
+        assert np.array_equal(sine, sp["sine"]) and np.array_equal(coeff, sp["coeff"])
+
+
+@pytest.mark.gpu
+def test_cpp_end_to_end_waves_from_a_bal_file(driver, tmp_path):
+    """BAL file -> rdis::BundleAdjustmentFunction::load -> init -> alternating point / camera sibling waves through
+    ComponentBatcher + CudaSubspaceOptimizer::optimizeBatch, entirely in C++; the objective trajectory must equal
+    the ctypes path's doing the same waves (same library: to the bit), and must not increase."""
+    from rdis_b200 import Context, problems as P
+    spec = P.ba_synthetic(ncams=6, npts=90, nobs=400, seed=31)
+    x0 = spec["x0"]
+    bal = str(tmp_path / "waves.bal")
+    _write_bal(bal, spec, x0)
+    out = subprocess.run([driver, "bawaves", bal, "2"], capture_output=True, text=True, check=True).stdout
+    lines = out.strip().splitlines()
+    objs = [float(lines[0].split()[1])] + [float(ln.split()[-1]) for ln in lines[1:]]
+    sums = [float(ln.split()[6]) for ln in lines[1:]]
+    assert len(objs) == 5 and all(b <= a * (1 + 1e-12) for a, b in zip(objs, objs[1:]))
+    ctx = Context.from_spec(spec); ctx.set_x(x0)
+    ref = [ctx.eval()]
+    rsum = []
+    for rd in range(4):
+        ps = P.ba_point_problems(spec) if rd % 2 == 0 else P.ba_camera_problems(spec)
+        x = ctx.get_x()
+        r = ctx.solve_cgd(ps, x[ps.vids], 25, 3e-8)
+        rsum.append(float(np.sum(r["f_end"])))
+        ref.append(ctx.eval())
+    assert objs == ref
+    assert np.allclose(sums, rsum, rtol=1e-14, atol=0)
