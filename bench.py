@@ -308,6 +308,11 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": abytes, "launch_ms": float(dom_ms), "peak_source": peak_src,
                          "note": "working set 1.4 MB: L2-resident, FP64/latency bound; see roofline_sweep for the HBM-bound kernel"},
         }
+    # ---- BASELINE config 4: sibling-component shard of the 1e6-variable / 4e6-factor graph (all ranks) ----
+    if not args.no_sweep:
+        c4 = cfg4_sibling_wave(local_rank, stream, rank, world, dist if world > 1 else None, dev)
+        if rank == 0:
+            out["cfg4_sibling_wave"] = c4
     # ---- the HBM-bound kernel: residual sweep on the cfg4 graph (rank 0) ----
     if rank == 0 and not args.no_sweep:
         out["roofline_sweep"] = sweep_roofline(local_rank, stream)
@@ -319,6 +324,49 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
+
+
+def cfg4_sibling_wave(device, stream, rank, world, dist, dev):
+    """Synthetic factor graph of BASELINE config 4 (sinusoid tree h=19 k=2 arity 4: 1,048,575 variables, 4,194,292
+    NonlinearProductFactors).  With the top 10 tree levels assigned the graph falls apart into 1024 sibling
+    components (1023 variables / 4092 factors each); they are dealt to the ranks (LPT shard, static CSR replicated),
+    every rank solves its share as ONE batch, the objective is all-reduced.  STRONG scaling: total work fixed."""
+    import torch
+    from rdis_b200 import Context, problems as P
+    spec = P.sinusoid(19, 2, 4)
+    x0 = P.random_start(spec, 1)
+    ps = P.sinusoid_subtree_problems(spec, 10)
+    mine = ps.subset(P.shard_problems(ps, rank, world)) if world > 1 else ps
+    ctx = Context.from_spec(spec, device=device, stream=stream.cuda_stream)
+    x0_dev = torch.from_numpy(x0).to(dev)
+    obj = torch.zeros(1, dtype=torch.float64, device=dev)
+    b = ctx.batch(mine)
+    times = []
+    for it in range(3):
+        ctx.set_x_device(x0_dev.data_ptr(), spec["V"])
+        obj.zero_()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        b.solve(None, MAXITERS, FTOL)
+        b.objective_device(obj.data_ptr())
+        if dist is not None:
+            dist.all_reduce(obj)
+        e.record(stream)
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(e))
+    ms = float(np.min(times[1:]))
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    r = b.fetch(want_x=False)
+    return {"workload": "sinusoid h=19 k=2 arity=4 (V=%d, F=%d): %d sibling components of %d variables / %d factors after assigning "
+                        "the top 10 tree levels, %d per rank" % (spec["V"], spec["F"], ps.n, ps.var_off[1], ps.fac_off[1], mine.n),
+            "scaling": "strong", "n_gpus": world, "ms": ms, "solves_per_sec": ps.n / (ms * 1e-3),
+            "objective_sum_f_end": float(obj.item()), "mapping": b.info()}
 
 
 def sweep_roofline(device, stream):
