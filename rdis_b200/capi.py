@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("RDIS_B200_LIB", os.path.join(_HERE, "librdis_b200.so"))  # override: kernel experiments only
+LIB_PATH = os.environ.get("RDIS_B200_LIB") or os.path.join(_HERE, "librdis_b200.so")  # override: kernel experiments only
 
 DONE_NAMES = ("ftol", "gtol", "gg_zero", "maxiters", "dbrent_itmax", "empty", "nonfinite", "bracket_cap")
 

@@ -183,7 +183,7 @@ __device__ __forceinline__ double rdis_power(double val, double e) {
 // NonlinearProductFactor
 // ------------------------------------------------------------------------------------------
 struct NlpfOps {
-  static constexpr int kMaxArityFast = 8;  // arities above this take the O(arity^2) recompute path
+  static constexpr int kMaxArityFast = 4;  // arities above this take the O(arity^2) recompute path (the generators stop at 4; 8 cost 242 registers)
 
   // f_j at abscissa alpha; if kSlope also d f_j / d alpha = sum_i (d f_j/d x_i) * xi_i.
   template <bool kAlongLine>

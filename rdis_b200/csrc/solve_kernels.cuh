@@ -393,9 +393,12 @@ __global__ void sum_f_end_kernel(const ResultRec* res, int64_t n, double* out) {
   }
 }
 
+#ifndef RDIS_BLOCK_MIN_CTAS
+#define RDIS_BLOCK_MIN_CTAS 1
+#endif
 template <class Ops>
-__global__ void solve_block_kernel(GraphView Gv, BatchView B, const int32_t* order, int count, int maxiters,
-                                   double ftol) {
+__global__ void __launch_bounds__(256, RDIS_BLOCK_MIN_CTAS) solve_block_kernel(GraphView Gv, BatchView B, const int32_t* order, int count,
+                                                             int maxiters, double ftol) {
   __shared__ double scratch[260];
   if ((int)blockIdx.x >= count) return;
   Block grp(scratch);
