@@ -213,6 +213,19 @@ def ba_synthetic(ncams=49, npts=7776, nobs=31843, seed=20260417, noise_px=0.5, p
             "cam": cam_idx, "pt": pt_idx, "obs": obs, "lb": lb, "ub": ub, "samp_lo": slo, "samp_hi": shi, "x0": x0}
 
 
+def ba_replicate(spec, K):
+    """K independent copies of a bundle-adjustment problem in one graph (the K restarts of `optBA --nsamples`,
+    src/bundleadjust/optBA.cpp:184-211, as one function): cameras of copy k are cameras k*ncams.., points likewise."""
+    nc, npnt = spec["ncams"], spec["npts"]
+    cam = np.concatenate([spec["cam"] + k * nc for k in range(K)]).astype(np.int32)
+    pt = np.concatenate([spec["pt"] + k * npnt for k in range(K)]).astype(np.int32)
+    obs = np.concatenate([np.asarray(spec["obs"]).reshape(-1, 2)] * K)
+    x0 = np.concatenate([np.tile(spec["x0"][:9 * nc], K), np.tile(spec["x0"][9 * nc:], K)])
+    lb, ub, slo, shi = ba_domains(x0, nc * K)
+    return {"kind": "ba", "V": len(x0), "F": spec["F"] * K, "ncams": nc * K, "npts": npnt * K, "cam": cam, "pt": pt, "obs": obs,
+            "lb": lb, "ub": ub, "samp_lo": slo, "samp_hi": shi, "x0": x0}
+
+
 def load_golden_ba(name="ladybug_49_7776.npz"):
     """The reference's own data/ladybug-problem-49-7776-pre.txt as parsed by the oracle's BAL
     loader (tests/golden/make_golden.py wrote it)."""
