@@ -507,3 +507,64 @@ def test_inline_trig_is_bit_identical(built_lib):
     r = subprocess.run([os.path.join(root, "tests", "native", "trig_check")], capture_output=True, text=True)
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_more_edge_cases(gpu, oracle_mod):
+    """Clamping active inside the line search, a stationary start, a ragged batch that mixes block shapes, and
+    the error paths of the C-ABI (bad ids, wrong call order) — against the oracle where there is a number."""
+    from rdis_b200 import Context, problems as P, RdisGpuError
+    from rdis_b200.capi import ProblemSet
+    # (1) optimum outside the domain: 0.5*(x-1)^2 + 0.5*(y+3)^2 on [2,5] x [-2,2]  ->  clamps to (2, -2)
+    V = 2
+    spec = dict(kind="nlpf", V=V, F=2, lb=np.array([2.0, -2.0]), ub=np.array([5.0, 2.0]), rowptr=np.array([0, 1, 2]),
+                vid=np.array([0, 1], np.int32), expo=np.array([2.0, 2.0]), konst=np.array([1.0, -3.0]),
+                sine=np.zeros(2, np.uint8), coeff=np.array([0.5, 0.5]))
+    ctx = Context.from_spec(spec)
+    orc = oracle_mod.OracleFunction.from_spec(spec)
+    ps = ProblemSet.from_lists([(np.array([0, 1], np.int32), np.array([0, 1], np.int64))])
+    for start in (np.array([3.0, 0.5]), np.array([2.0, -2.0]), np.array([4.9, 1.9])):
+        ctx.set_x(start); orc.set_x(start)
+        r = ctx.solve_cgd(ps, start, 25, 3e-8)
+        o = orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, start, 25, 3e-8)
+        assert np.allclose(r["x"], o["x"], rtol=0, atol=1e-12) and abs(r["f_end"][0] - o["f_end"][0]) <= 1e-12 * abs(o["f_end"][0])
+        assert r["iters"][0] == o["iters"][0]
+        assert np.allclose(r["x"], [2.0, -2.0], atol=1e-9)
+    # (2) a stationary start: the gradient test returns at once, nothing moves
+    spec2 = dict(spec); spec2["lb"] = np.array([-9.0, -9.0]); spec2["ub"] = np.array([9.0, 9.0])
+    ctx2 = Context.from_spec(spec2); orc2 = oracle_mod.OracleFunction.from_spec(spec2)
+    start = np.array([1.0, -3.0])
+    ctx2.set_x(start); orc2.set_x(start)
+    r = ctx2.solve_cgd(ps, start, 25, 3e-8)
+    o = orc2.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, start, 25, 3e-8)
+    assert r["f_end"][0] == 0.0 == o["f_end"][0] and np.array_equal(r["x"], start) and r["iters"][0] == o["iters"][0]
+    # (3) ragged batch: two camera blocks + the point blocks those cameras do not observe, in ONE call
+    sp = P.ba_synthetic(ncams=6, npts=80, nobs=300, seed=17)
+    x0 = sp["x0"]
+    cams, pts = P.ba_camera_problems(sp), P.ba_point_problems(sp)
+    seen = set(sp["pt"][(sp["cam"] == 0) | (sp["cam"] == 1)].tolist())
+    free_pts = [i for i in range(80) if i not in seen]
+    assert len(free_pts) >= 5
+    probs = [(cams.vids[cams.var_off[c]:cams.var_off[c + 1]], cams.fids[cams.fac_off[c]:cams.fac_off[c + 1]]) for c in (0, 1)]
+    probs += [(pts.vids[pts.var_off[i]:pts.var_off[i + 1]], pts.fids[pts.fac_off[i]:pts.fac_off[i + 1]]) for i in free_pts]
+    mixed = ProblemSet.from_lists(probs)
+    c3 = Context.from_spec(sp); o3 = oracle_mod.OracleFunction.from_spec(sp)
+    c3.set_x(x0); o3.set_x(x0)
+    r = c3.solve_cgd(mixed, x0[mixed.vids], 1, 3e-8)      # one CG iteration: stable for the camera blocks too
+    o = o3.solve_cgd_batch(mixed.var_off, mixed.vids, mixed.fac_off, mixed.fids, x0[mixed.vids], 1, 3e-8)
+    assert _relerr(r["f_init"], o["f_init"], 1e-12).max() <= 1e-12
+    assert _relerr(r["f_end"], o["f_end"], 1e-12).max() <= 1e-6
+    # (4) error paths: loud, with a message, and the context stays usable
+    with pytest.raises(RdisGpuError):
+        c3.solve_cgd(ProblemSet.from_lists([(np.array([sp["V"]], np.int32), np.array([0], np.int64))]), np.zeros(1))
+    with pytest.raises(RdisGpuError):
+        c3.solve_cgd(ProblemSet.from_lists([(np.array([0], np.int32), np.array([sp["F"]], np.int64))]), np.zeros(1))
+    with pytest.raises(RdisGpuError):
+        c3.set_x(np.zeros(3), vid=np.array([0, 1, sp["V"] + 5], np.int32))
+    with pytest.raises(RdisGpuError):
+        c3.solve_cgd(mixed, x0[mixed.vids], 0, 3e-8)       # maxiters must be positive
+    fresh = Context()
+    with pytest.raises(RdisGpuError):
+        fresh.eval()                                        # before finalize
+    c3.set_x(x0); o3.set_x(x0)
+    assert abs(c3.eval() - o3.eval()) <= 1e-12 * abs(o3.eval())
