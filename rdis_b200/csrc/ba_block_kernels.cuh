@@ -295,7 +295,8 @@ constexpr int kCamRedWidth = 10;  // f + 9 partials (gradient mode); f + slope u
 struct CamShared {
   double p[9], xi[9], g[9], h[9], xs[9];
   double2 dom[9];
-  double red[2][kCamMaxCluster * kCamMaxWarps][kCamRedWidth];
+  double wred[kCamMaxWarps][kCamRedWidth];          // warp partials of this CTA (first reduction level)
+  double red[2][kCamMaxCluster][kCamRedWidth];      // CTA partials of the whole cluster (second level, double-buffered)
   unsigned long long mbar[2];  // one transaction barrier per reduction buffer (remote st.async completes on it)
 };
 
@@ -333,14 +334,15 @@ __device__ __forceinline__ void cam_mbar_wait(unsigned long long* bar, uint32_t 
   }
 }
 
-// All-reduce of N doubles per thread over the whole cluster, fixed order: warp butterfly, then lane d of
-// every warp pushes the warp's partial into slot (cta*nw + warp) of CTA d's buffer with ASYNCHRONOUS
-// stores over distributed shared memory that complete a transaction barrier in the receiving CTA
-// (st.async ... mbarrier::complete_tx).  A CTA just waits for its own barrier to have received
-// C*nw*N*8 bytes: one one-way trip per evaluation instead of remote stores + a two-phase cluster
-// barrier.  The buffers (and their barriers) alternate; re-use two rounds later is safe because a warp
-// can only send round r+1 after all its lanes folded round r, and nobody finishes round r+1 before every
-// warp of the cluster has sent it.  `phase` holds the two barriers' parities.
+// All-reduce of N doubles per thread over the whole cluster, fixed order, two levels:
+//   (1) warp butterfly, warp partials folded per CTA through shared memory (one __syncthreads);
+//   (2) thread d of warp 0 pushes the CTA's partial into slot `cta` of CTA d's buffer with an ASYNCHRONOUS
+//       store over distributed shared memory that completes a transaction barrier in the receiving CTA
+//       (st.async ... mbarrier::complete_tx); a CTA just waits for its own barrier to have received C*N*8
+//       bytes and folds the C partials in CTA order: one one-way trip per evaluation, no cluster barrier.
+// The cluster buffers (and their barriers) alternate; re-use two rounds later is safe because a CTA can only
+// send round r+1 after its warp 0 folded round r's warp partials, and nobody finishes round r+1 before every
+// CTA of the cluster has sent it.  `phase` holds the two barriers' parities.
 template <int N>
 __device__ __forceinline__ void cluster_allreduce(CamShared& sh, int& flip, uint32_t& phase, double (&v)[N], int C, int cta) {
   static_assert(N % 2 == 0, "partials travel as 16-byte pairs");
@@ -350,28 +352,42 @@ __device__ __forceinline__ void cluster_allreduce(CamShared& sh, int& flip, uint
     for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-  const int slot = cta * nw + warp;
-  if (C == 1) {
-    if (lane == 0) {
+  if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) sh.red[flip][slot][i] = v[i];
+    for (int i = 0; i < N; ++i) sh.wred[warp][i] = v[i];
+  }
+  __syncthreads();
+  if (C == 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = sh.wred[0][i];
+    for (int w = 1; w < nw; ++w) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] += sh.wred[w][i];
     }
-    __syncthreads();
-  } else {
-    if (threadIdx.x == 0) cam_mbar_expect_tx(&sh.mbar[flip], (uint32_t)(C * nw * N * 8));
-    if (lane < C) {  // lane d delivers this warp's partial to CTA d
-      const uint32_t dst = cam_map_to_cta(cam_smem_u32(&sh.red[flip][slot][0]), (uint32_t)lane);
+    __syncthreads();  // wred is rewritten by the next evaluation
+    return;
+  }
+  if (warp == 0) {
+    if (lane == 0) cam_mbar_expect_tx(&sh.mbar[flip], (uint32_t)(C * N * 8));
+    if (lane < C) {  // lane d delivers this CTA's partial to CTA d
+      double c[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) c[i] = sh.wred[0][i];
+      for (int w = 1; w < nw; ++w) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) c[i] += sh.wred[w][i];
+      }
+      const uint32_t dst = cam_map_to_cta(cam_smem_u32(&sh.red[flip][cta][0]), (uint32_t)lane);
       const uint32_t bar = cam_map_to_cta(cam_smem_u32(&sh.mbar[flip]), (uint32_t)lane);
 #pragma unroll
-      for (int i = 0; i < N; i += 2) cam_st_async_v2(dst + 8u * i, v[i], v[i + 1], bar);
+      for (int i = 0; i < N; i += 2) cam_st_async_v2(dst + 8u * i, c[i], c[i + 1], bar);
     }
-    cam_mbar_wait(&sh.mbar[flip], (phase >> flip) & 1u);
-    phase ^= (1u << flip);
   }
-  const int total = C * nw;
+  cam_mbar_wait(&sh.mbar[flip], (phase >> flip) & 1u);
+  phase ^= (1u << flip);
 #pragma unroll
   for (int i = 0; i < N; ++i) v[i] = sh.red[flip][0][i];
-  for (int s = 1; s < total; ++s) {
+  for (int s = 1; s < C; ++s) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] += sh.red[flip][s][i];
   }
