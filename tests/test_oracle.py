@@ -249,3 +249,63 @@ def test_lm_restatement_known_answers(oracle_mod):
         if prev is not None:
             assert (r["f_end"] <= prev * (1 + 1e-12)).all()
         prev = r["f_end"]
+
+
+def test_ba_forward_model_matches_an_independent_bal_implementation(oracle_mod):
+    """The reference has no golden values for bundle adjustment, so the oracle's BA arithmetic is pinned by its own
+    restatement + finite differences only.  One more, independent, check: the BAL camera model written from its
+    published definition in numpy (rdis_b200.problems._project: Rodrigues rotation, p = -P/P.z, radial distortion
+    1 + k1 r^2 + k2 r^4, focal scaling) must give the oracle's factor values: observations generated WITHOUT noise
+    from a state make every factor vanish at that state, and with known pixel offsets f_j = |offset_j|^2 / 2."""
+    from rdis_b200 import problems as P
+    spec = P.ba_synthetic(ncams=7, npts=60, nobs=260, seed=4, noise_px=0.0, perturb=0.0)
+    orc = oracle_mod.OracleFunction.from_spec(spec)
+    orc.set_x(spec["x0"])                       # perturb = 0: x0 is the generating state
+    s, pf = orc.eval(per_factor=True)
+    assert np.all(pf >= 0) and pf.max() <= 1e-20, pf.max()
+    rng = np.random.default_rng(0)
+    off = rng.normal(0, 2.0, size=(spec["F"], 2))
+    spec2 = dict(spec); spec2["obs"] = np.asarray(spec["obs"]).reshape(-1, 2) + off
+    orc2 = oracle_mod.OracleFunction.from_spec(spec2)
+    orc2.set_x(spec["x0"])
+    s2, pf2 = orc2.eval(per_factor=True)
+    want = 0.5 * np.sum(off * off, axis=1)
+    assert np.allclose(pf2, want, rtol=1e-9, atol=0)
+    assert abs(s2 - want.sum()) <= 1e-9 * want.sum()
+
+
+def test_nlpf_values_match_a_direct_numpy_evaluation(oracle_mod):
+    """Independent check of the NonlinearProductFactor arithmetic: c * prod [sin]((x - k)^e) evaluated with numpy
+    from the flat arrays, on the sinusoid tree and on a graph with general exponents / constants / mixed sine flags."""
+    from rdis_b200 import problems as P
+
+    def numpy_eval(spec, x):
+        t = x[spec["vid"]] - spec["konst"]
+        t = np.where(spec["expo"] == 1.0, t, np.power(t, spec["expo"]))
+        t = np.where(spec["sine"] != 0, np.sin(t), t)
+        lens = np.diff(spec["rowptr"])
+        prod = np.ones(spec["F"])
+        pos = spec["rowptr"][:-1].copy()
+        for step in range(int(lens.max())):
+            live = lens > step
+            prod[live] *= t[pos[live] + step]
+        return spec["coeff"] * prod
+
+    spec = P.sinusoid(6, 3, 4, odd=True)
+    x = P.random_start(spec, 11)
+    orc = oracle_mod.OracleFunction.from_spec(spec); orc.set_x(x)
+    s, pf = orc.eval(per_factor=True)
+    want = numpy_eval(spec, x)
+    assert np.allclose(pf, want, rtol=1e-13, atol=1e-300) and abs(s - want.sum()) <= 1e-11 * np.abs(want).sum()
+    rng = np.random.default_rng(8)
+    V, F = 30, 150
+    ar = rng.integers(1, 7, size=F)
+    spec2 = dict(kind="nlpf", V=V, F=F, lb=np.full(V, 2.0), ub=np.full(V, 5.0), rowptr=np.concatenate([[0], np.cumsum(ar)]),
+                 vid=np.concatenate([rng.choice(V, size=a, replace=False) for a in ar]).astype(np.int32),
+                 expo=rng.choice([1.0, 2.0, 3.0, 0.5], size=int(ar.sum())), konst=rng.choice([0.0, 0.7, -1.3], size=int(ar.sum())),
+                 sine=rng.integers(0, 2, size=int(ar.sum())).astype(np.uint8), coeff=rng.normal(0, 2, size=F))
+    x2 = rng.uniform(2.0, 5.0, size=V)
+    orc2 = oracle_mod.OracleFunction.from_spec(spec2); orc2.set_x(x2)
+    s2, pf2 = orc2.eval(per_factor=True)
+    want2 = numpy_eval(spec2, x2)
+    assert np.allclose(pf2, want2, rtol=1e-12, atol=1e-300)
