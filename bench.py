@@ -308,6 +308,10 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": abytes, "launch_ms": float(dom_ms), "peak_source": peak_src,
                          "note": "working set 1.4 MB: L2-resident, FP64/latency bound; see roofline_sweep for the HBM-bound kernel"},
         }
+    # ---- residual-evals/sec of the all-factor BA sweep (evalFactors over the whole graph): at ladybug size it is
+    #      launch-bound (1.2 MB); 100 copies of the graph (122 MB algorithmic > L2) show the streaming regime ----
+    if rank == 0 and not args.no_sweep:
+        out["ba_residual_sweep"] = ba_sweep_rates(spec, local_rank, stream, dev)
     # ---- throughput regime: 8 independent copies of the problem (optBA's --nsamples restarts) in ONE batch ----
     if rank == 0 and not args.no_sweep:
         K = 8
@@ -348,6 +352,37 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
+
+
+def ba_sweep_rates(spec, device, stream, dev):
+    import torch
+    from rdis_b200 import Context, problems as P
+    peak, _ = peaks()
+    res = {}
+    for name, K in (("ladybug_shaped", 1), ("x100_points_same_49_cameras", 100), ("x100_independent_copies_4900_cameras", -100)):
+        sp = spec if K == 1 else (P.ba_replicate_points(spec, K) if K > 0 else P.ba_replicate(spec, -K))
+        ctx = Context.from_spec(sp, device=device, stream=stream.cuda_stream)
+        ctx.set_x(sp["x0"])
+        pf = torch.empty(sp["F"], dtype=torch.float64, device=dev)
+        tot = torch.zeros(1, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            ctx.eval_device(tot.data_ptr(), pf.data_ptr())
+        reps = 20
+        torch.cuda.synchronize()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            ctx.eval_device(tot.data_ptr(), pf.data_ptr())
+        e.record(stream)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(e) / reps
+        abytes = 32.0 * sp["F"] + 8.0 * sp["V"]
+        res[name] = {"factors": int(sp["F"]), "variables": int(sp["V"]), "ms_per_sweep": ms, "residual_evals_per_sec": sp["F"] / (ms * 1e-3),
+                     "algorithmic_bytes": abytes, "achieved_GBps": abytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": abytes / (ms * 1e-3) / 1e9 / peak,
+                     "sum": float(tot.item())}
+        del ctx
+    res["kernels"] = "ba_camera_table_kernel + ba_sweep_kernel (back-to-back launches, per-factor values written)"
+    return res
 
 
 def cfg4_sibling_wave(device, stream, rank, world, dist, dev):

@@ -17,6 +17,7 @@
 #include "sweep_kernels.cuh"
 #include "nlpf_tile_sweep.cuh"
 #include "lm_kernels.cuh"
+#include "ba_sweep.cuh"
 
 using namespace rdisgpu;
 
@@ -94,6 +95,7 @@ struct rdisgpu_ctx {
   // device residency
   DevBuf<double2> xbd, dom;
   DevBuf<int32_t> rowptr, evid, vrow, vedge, efac, cam, pt, crow, cfac, prow, pfac, fstamp;
+  DevBuf<CameraRow> cam_table;  // BA: per-camera part of the forward model for the all-factor sweep (ba_sweep.cuh)
   DevBuf<TileDesc> tiles;  // NLPF: factor tiles of the streaming sweep (nlpf_tile_sweep.cuh)
   int ntiles = 0, tile_grid[2] = {0, 0};  // persistent grid size of the eval / grad instantiation
   DevBuf<double> expo, konst, coeff, gedge, gvec, hvec, xsave, fconst_val, xval;
@@ -115,6 +117,7 @@ struct rdisgpu_ctx {
   DevBuf<double> lm_scratch;
   DevBuf<int64_t> lm_off;
   bool lm_vloc_ready = false;
+  bool ba_smem_optin = false;
   DevBuf<double> grid_partials;
   PinnedBuf<char> pin;
 
@@ -596,13 +599,30 @@ static int enqueue_eval(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, do
   cudaStream_t s = ctx->stream;
   const int threads = 256;
   const bool tiled = (ctx->kind == KIND_NLPF && fid_dev == nullptr);
-  const int blocks = tiled ? ctx->tile_grid[0] : (int)std::min<int64_t>((nf + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
+  const bool ba_all = (ctx->kind == KIND_BA && fid_dev == nullptr);
+  const int blocks = tiled ? ctx->tile_grid[0]
+                           : (int)std::min<int64_t>(((ba_all ? (nf + kBaSweepUnroll - 1) / kBaSweepUnroll : nf) + threads - 1) / threads,
+                                                    (int64_t)ctx->sm_count * (ba_all ? RDIS_BA_SWEEP_CTAS : 8));
   CK(ctx->s_partials.ensure((size_t)blocks + 1));
   double* dsum = sum_dst ? sum_dst : ctx->s_partials.p + blocks;
   if (tiled)
     nlpf_tile_sweep_kernel<false><<<blocks, kTileThreads + 32, sizeof(TileSmem), s>>>(
         ctx->gv, ctx->tiles.p, ctx->ntiles, per_factor_dev, ctx->s_partials.p, ctx->s_counter.p, dsum);
-  else if (ctx->kind == KIND_NLPF)
+  else if (ba_all) {
+    CK(ctx->cam_table.ensure((size_t)ctx->ncams));
+    ba_camera_table_kernel<<<(ctx->ncams + 127) / 128, 128, 0, s>>>(ctx->gv, ctx->cam_table.p);
+    ++ctx->launches;
+    if (ctx->ncams <= kBaSmemCams) {
+      const size_t smem = (size_t)ctx->ncams * sizeof(CameraRow);
+      if (smem > 48 * 1024 && !ctx->ba_smem_optin) {
+        CK(cudaFuncSetAttribute(ba_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBaSmemCams * sizeof(CameraRow))));
+        ctx->ba_smem_optin = true;
+      }
+      ba_sweep_kernel<true><<<blocks, threads, smem, s>>>(ctx->gv, ctx->cam_table.p, per_factor_dev, ctx->s_partials.p, ctx->s_counter.p, dsum);
+    } else {
+      ba_sweep_kernel<false><<<blocks, threads, 0, s>>>(ctx->gv, ctx->cam_table.p, per_factor_dev, ctx->s_partials.p, ctx->s_counter.p, dsum);
+    }
+  } else if (ctx->kind == KIND_NLPF)
     eval_sweep_kernel<NlpfOps><<<blocks, threads, 0, s>>>(ctx->gv, fid_dev, nf, per_factor_dev, ctx->s_partials.p,
                                                           ctx->s_counter.p, dsum);
   else

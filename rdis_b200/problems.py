@@ -226,6 +226,19 @@ def ba_replicate(spec, K):
             "lb": lb, "ub": ub, "samp_lo": slo, "samp_hi": shi, "x0": x0}
 
 
+def ba_replicate_points(spec, K):
+    """The same cameras observing K copies of the point cloud: ncams cameras, K*npts points, K*F observations
+    (a long sequence from few cameras; used to put the BA sweep into its streaming regime)."""
+    nc, npnt = spec["ncams"], spec["npts"]
+    cam = np.tile(spec["cam"], K).astype(np.int32)
+    pt = np.concatenate([spec["pt"] + k * npnt for k in range(K)]).astype(np.int32)
+    obs = np.concatenate([np.asarray(spec["obs"]).reshape(-1, 2)] * K)
+    x0 = np.concatenate([spec["x0"][:9 * nc], np.tile(spec["x0"][9 * nc:], K)])
+    lb, ub, slo, shi = ba_domains(x0, nc)
+    return {"kind": "ba", "V": len(x0), "F": spec["F"] * K, "ncams": nc, "npts": npnt * K, "cam": cam, "pt": pt, "obs": obs,
+            "lb": lb, "ub": ub, "samp_lo": slo, "samp_hi": shi, "x0": x0}
+
+
 def load_golden_ba(name="ladybug_49_7776.npz"):
     """The reference's own data/ladybug-problem-49-7776-pre.txt as parsed by the oracle's BAL
     loader (tests/golden/make_golden.py wrote it)."""

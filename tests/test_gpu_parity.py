@@ -568,3 +568,33 @@ def test_more_edge_cases(gpu, oracle_mod):
         fresh.eval()                                        # before finalize
     c3.set_x(x0); o3.set_x(x0)
     assert abs(c3.eval() - o3.eval()) <= 1e-12 * abs(o3.eval())
+
+
+@pytest.mark.gpu
+def test_ba_table_sweep_equals_list_sweep(gpu, oracle_mod):
+    """The all-factor BA sweep (per-camera table + streaming kernel, ba_sweep.cuh) against the thread-per-factor
+    list sweep: per-factor values to the BIT, incl. assigned-constant factors, a zero rotation vector (the theta == 0
+    branch), after solves have moved the state, and through the device-pointer entry; and against the oracle."""
+    import torch
+    from rdis_b200 import Context, problems as P
+    spec = P.ba_synthetic(ncams=9, npts=400, nobs=1900, seed=23)
+    x0 = spec["x0"].copy()
+    x0[0:3] = 0.0                                   # camera 0: theta == 0
+    ctx = Context.from_spec(spec); ctx.set_x(x0)
+    allf = np.arange(spec["F"])
+    s_tab, pf_tab = ctx.eval(per_factor=True)
+    s_lst, pf_lst = ctx.eval(allf, per_factor=True)
+    assert np.array_equal(pf_tab, pf_lst) and abs(s_tab - s_lst) <= 1e-12 * abs(s_lst)
+    orc = oracle_mod.OracleFunction.from_spec(spec); orc.set_x(x0)
+    so, po = orc.eval(per_factor=True)
+    assert (np.abs(pf_tab - po) <= 1e-12 * np.maximum(np.abs(po), 1e-300)).all()
+    ctx.set_factor_const(np.array([7, 1000]), np.array([0.25, 3.0]), np.ones(2, np.uint8))
+    assert np.array_equal(ctx.eval(per_factor=True)[1], ctx.eval(allf, per_factor=True)[1])
+    pts = P.ba_point_problems(spec)
+    ctx.solve_cgd(pts, x0[pts.vids], 5, 3e-8)       # commits new point values: the value mirror must follow
+    pf_a = ctx.eval(per_factor=True)[1]; pf_b = ctx.eval(allf, per_factor=True)[1]
+    assert np.array_equal(pf_a, pf_b)
+    dev = torch.device("cuda", 0)
+    pf_d = torch.empty(spec["F"], dtype=torch.float64, device=dev); tot = torch.zeros(1, dtype=torch.float64, device=dev)
+    ctx.eval_device(tot.data_ptr(), pf_d.data_ptr()); ctx.synchronize()
+    assert np.array_equal(pf_d.cpu().numpy(), pf_a)
