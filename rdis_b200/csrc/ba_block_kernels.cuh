@@ -31,6 +31,7 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include "ptx_async.cuh"
 #include "solve_kernels.cuh"
 
 namespace rdisgpu {
@@ -300,40 +301,6 @@ struct CamShared {
   unsigned long long mbar[2];  // one transaction barrier per reduction buffer (remote st.async completes on it)
 };
 
-// ---- PTX wrappers: transaction barriers + asynchronous stores into a peer CTA's shared memory ----
-__device__ __forceinline__ uint32_t cam_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t cam_map_to_cta(uint32_t local_addr, uint32_t cta_rank) {  // shared::cta -> shared::cluster of a peer
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
-  return r;
-}
-__device__ __forceinline__ void cam_st_async_v2(uint32_t remote_addr, double a, double b, uint32_t remote_mbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
-               "d"(a), "d"(b), "r"(remote_mbar)
-               : "memory");
-}
-__device__ __forceinline__ void cam_mbar_init(unsigned long long* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cam_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void cam_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cam_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cam_mbar_wait(unsigned long long* bar, uint32_t parity) {
-  uint32_t done = 0;
-  const uint32_t a = cam_smem_u32(bar);
-  while (!done) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-  }
-}
-
 // All-reduce of N doubles per thread over the whole cluster, fixed order, two levels:
 //   (1) warp butterfly, warp partials folded per CTA through shared memory (one __syncthreads);
 //   (2) thread d of warp 0 pushes the CTA's partial into slot `cta` of CTA d's buffer with an ASYNCHRONOUS
@@ -368,7 +335,7 @@ __device__ __forceinline__ void cluster_allreduce(CamShared& sh, int& flip, uint
     return;
   }
   if (warp == 0) {
-    if (lane == 0) cam_mbar_expect_tx(&sh.mbar[flip], (uint32_t)(C * N * 8));
+    if (lane == 0) mbar_arrive_expect_tx(&sh.mbar[flip], (uint32_t)(C * N * 8));
     if (lane < C) {  // lane d delivers this CTA's partial to CTA d
       double c[N];
 #pragma unroll
@@ -377,13 +344,13 @@ __device__ __forceinline__ void cluster_allreduce(CamShared& sh, int& flip, uint
 #pragma unroll
         for (int i = 0; i < N; ++i) c[i] += sh.wred[w][i];
       }
-      const uint32_t dst = cam_map_to_cta(cam_smem_u32(&sh.red[flip][cta][0]), (uint32_t)lane);
-      const uint32_t bar = cam_map_to_cta(cam_smem_u32(&sh.mbar[flip]), (uint32_t)lane);
+      const uint32_t dst = map_to_cta(smem_addr_u32(&sh.red[flip][cta][0]), (uint32_t)lane);
+      const uint32_t bar = map_to_cta(smem_addr_u32(&sh.mbar[flip]), (uint32_t)lane);
 #pragma unroll
-      for (int i = 0; i < N; i += 2) cam_st_async_v2(dst + 8u * i, c[i], c[i + 1], bar);
+      for (int i = 0; i < N; i += 2) st_async_v2(dst + 8u * i, c[i], c[i + 1], bar);
     }
   }
-  cam_mbar_wait(&sh.mbar[flip], (phase >> flip) & 1u);
+  mbar_wait_cluster(&sh.mbar[flip], (phase >> flip) & 1u);
   phase ^= (1u << flip);
 #pragma unroll
   for (int i = 0; i < N; ++i) v[i] = sh.red[flip][0][i];
@@ -412,9 +379,9 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
   int flip = 0;
   uint32_t phase = 0;
   if (threadIdx.x == 0) {
-    cam_mbar_init(&sh.mbar[0], 1);
-    cam_mbar_init(&sh.mbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_init(&sh.mbar[0], 1);
+    mbar_init(&sh.mbar[1], 1);
+    mbar_fence_init();
   }
 
   if (threadIdx.x < 9) {

@@ -23,6 +23,7 @@
 // the grand total is folded in a fixed order (reproducible run to run on one device).
 #pragma once
 #include "factors.cuh"
+#include "ptx_async.cuh"
 #include "sweep_kernels.cuh"
 
 namespace rdisgpu {
@@ -77,82 +78,6 @@ struct TileSmem {
   unsigned long long xready[kTileStages]; // producer -> consumers: ... and the gathered variable values too
   unsigned long long empty[kTileStages];  // consumers -> producer: every consumer warp is done with the stage
 };
-
-// ---- PTX wrappers (mbarrier + TMA bulk copy) ----------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-  uint32_t done = 0;
-  const uint32_t a = smem_addr_u32(bar);
-  while (!done) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-  }
-}
-// producer-side wait: it is one thread with nothing else to do, so it sleeps between probes instead
-// of competing with the consumer warps for issue slots
-__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, uint32_t parity) {
-  uint32_t done = 0;
-  const uint32_t a = smem_addr_u32(bar);
-  while (true) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-    if (done) break;
-    __nanosleep(100);
-  }
-}
-// L2 policy of the streamed slices: evict-first, so that 268 MB of single-use stream does not push the
-// 17 MB of gathered variable values (re-used ~8 times each, loaded evict-last below) out of the 126 MB L2.
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar,
-                                             uint64_t policy) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                   smem_addr_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_addr_u32(bar)), "l"(policy)
-               : "memory");
-}
-// the variable gather: 16 B {value, direction slot}, kept in L2 with evict-last priority
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-// asynchronous 8-byte gather global -> shared (LDGSTS), L2 evict-last; completion is reported to an mbarrier
-__device__ __forceinline__ void cp_async_gather8(double* dst_smem, const double* src_gmem, uint64_t policy) {
-  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(smem_addr_u32(dst_smem)), "l"(src_gmem),
-               "l"(policy)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(unsigned long long* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
-}
 
 // value term exactly as NlpfOps::value (no-slope path) computes it
 __device__ __forceinline__ double nlpf_term_value(double xv, double k, double ex, bool sn) {
