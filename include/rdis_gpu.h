@@ -185,6 +185,17 @@ RDISGPU_API int rdisgpu_batch_info(const rdisgpu_batch* b, int32_t out[8]);
 /* Kernel launches the last rdisgpu_batch_solve_cgd enqueued (bench.py's gpu_launches). */
 RDISGPU_API int rdisgpu_batch_last_launches(const rdisgpu_batch* b);
 
+/* ---- component membership ------------------------------------------------- */
+/* Sibling components as Component::createChildren produces them (src/Component.cpp:508-549; connectivity rule
+ * src/ConnectivityGraph.cpp:211-285): connected components of the bipartite variable / factor graph with an edge
+ * (v, f) iff variable v is unassigned (assigned[v] == 0) and factor f is not an assigned constant
+ * (rdisgpu_set_factor_const).  var_label[v] = smallest variable id of v's component, -1 for assigned variables;
+ * fac_label[f] (nullable) = the label of the component f belongs to, -1 if it has none.  Exact integer bookkeeping
+ * (min-label propagation with pointer jumping on the device); host buffers in and out.  n_components / n_rounds
+ * (nullable) receive the number of components and of propagation rounds. */
+RDISGPU_API int rdisgpu_components(rdisgpu_ctx* ctx, const uint8_t* assigned, int32_t* var_label, int32_t* fac_label,
+                                   int32_t* n_components, int32_t* n_rounds);
+
 /* ---- introspection (tests / bench) ------------------------------------------------------ */
 RDISGPU_API int64_t rdisgpu_num_vars(const rdisgpu_ctx* ctx);
 RDISGPU_API int64_t rdisgpu_num_factors(const rdisgpu_ctx* ctx);

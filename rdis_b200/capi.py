@@ -21,7 +21,7 @@ EXPORTS = (
     "rdisgpu_set_x", "rdisgpu_get_x", "rdisgpu_set_factor_const",
     "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_eval_device", "rdisgpu_grad_device", "rdisgpu_factor_grad",
     "rdisgpu_solve_cgd", "rdisgpu_solve_cgd_csr", "rdisgpu_solve_lm_csr", "rdisgpu_batch_create", "rdisgpu_batch_create_csr", "rdisgpu_batch_info", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
-    "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches",
+    "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches", "rdisgpu_components",
     "rdisgpu_num_vars", "rdisgpu_num_factors", "rdisgpu_device_state", "rdisgpu_launch_count", "rdisgpu_version",
 )
 
@@ -70,6 +70,7 @@ def load_library(path=LIB_PATH):
         "rdisgpu_batch_create_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, C.POINTER(vp)]),
         "rdisgpu_solve_cgd_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, C.c_int, dbl, vp, vp, vp, vp, vp, vp, vp]),
         "rdisgpu_solve_lm_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "rdisgpu_components": (C.c_int, [vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]),
         "rdisgpu_batch_info": (C.c_int, [vp, vp]),
         "rdisgpu_batch_solve_cgd": (C.c_int, [vp, vp, C.c_int, dbl]),
         "rdisgpu_batch_fetch": (C.c_int, [vp, C.POINTER(Result), C.POINTER(dbl)]),
@@ -273,6 +274,33 @@ class Context:
         rows = np.zeros((len(f), arity_max))
         self._ck(self._lib.rdisgpu_factor_grad(self._h, len(f), _p(f), arity_max, _p(rows)))
         return rows
+
+    # ---- component membership ----------------------------------------------------------
+    def components(self, assigned):
+        """rdisgpu_components: (var_label[V], fac_label[F], n_components, rounds)."""
+        a = _arr(assigned, np.uint8)
+        assert len(a) == self.V
+        vl = np.empty(self.V, np.int32); fl = np.empty(self.F, np.int32)
+        n = C.c_int32(0); r = C.c_int32(0)
+        self._ck(self._lib.rdisgpu_components(self._h, _p(a), _p(vl), _p(fl), C.byref(n), C.byref(r)))
+        return vl, fl, n.value, r.value
+
+    def component_problems(self, assigned):
+        """Sibling components as a ProblemSet, ordered like Component::createChildren's children (fewest variables
+        first, ties by smallest variable id), variables and factors of a component ascending."""
+        vl, fl, n, _ = self.components(assigned)
+        vs = np.nonzero(vl >= 0)[0]
+        fs = np.nonzero(fl >= 0)[0]
+        vorder = vs[np.argsort(vl[vs], kind="stable")]
+        forder = fs[np.argsort(fl[fs], kind="stable")]
+        labels, vcount = np.unique(vl[vs], return_counts=True)
+        fcount = np.zeros(len(labels), np.int64)
+        flab, fc = np.unique(fl[fs], return_counts=True)
+        fcount[np.searchsorted(labels, flab)] = fc
+        voff = np.concatenate([[0], np.cumsum(vcount)]); foff = np.concatenate([[0], np.cumsum(fcount)])
+        order = np.lexsort((labels, vcount))   # by size, then by smallest variable id (= the label)
+        probs = [(vorder[voff[k]:voff[k + 1]].astype(np.int32), forder[foff[k]:foff[k + 1]].astype(np.int64)) for k in order]
+        return ProblemSet.from_lists(probs)
 
     # ---- solves ----------------------------------------------------------------------
     def solve_cgd(self, problems, x0=None, maxiters=25, ftol=3e-8):

@@ -18,6 +18,7 @@
 #include "nlpf_tile_sweep.cuh"
 #include "lm_kernels.cuh"
 #include "ba_sweep.cuh"
+#include "components.cuh"
 
 using namespace rdisgpu;
 
@@ -118,6 +119,8 @@ struct rdisgpu_ctx {
   DevBuf<int64_t> lm_off;
   bool lm_vloc_ready = false;
   bool ba_smem_optin = false;
+  DevBuf<uint8_t> cc_assigned;
+  DevBuf<int32_t> cc_vlabel, cc_flabel, cc_flag;
   DevBuf<double> grid_partials;
   PinnedBuf<char> pin;
 
@@ -1345,6 +1348,57 @@ int rdisgpu_solve_lm_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_of
     if (n_feval) n_feval[p] = r.n_value;
     if (n_jeval) n_jeval[p] = r.n_slope;
   }
+  return RDISGPU_OK;
+}
+
+int rdisgpu_components(rdisgpu_ctx* ctx, const uint8_t* assigned, int32_t* var_label, int32_t* fac_label, int32_t* n_components,
+                       int32_t* n_rounds) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "components before finalize");
+  if (!assigned || !var_label) return ctx->fail(RDISGPU_ERR_ARG, "components: null argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int64_t V = ctx->V, F = ctx->F;
+  CK(ctx->cc_assigned.ensure((size_t)V));
+  CK(ctx->cc_vlabel.ensure((size_t)V));
+  CK(ctx->cc_flabel.ensure((size_t)F));
+  CK(ctx->cc_flag.ensure(1));
+  CK(cudaMemcpyAsync(ctx->cc_assigned.p, assigned, (size_t)V, cudaMemcpyHostToDevice, s));
+  ComponentsView cv;
+  cv.assigned = ctx->cc_assigned.p;
+  cv.vlabel = ctx->cc_vlabel.p;
+  cv.flabel = ctx->cc_flabel.p;
+  cv.changed = ctx->cc_flag.p;
+  const int threads = 256;
+  const int vb = (int)std::min<int64_t>((V + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
+  const int fb = (int)std::min<int64_t>((F + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
+  cc_init_kernel<<<vb, threads, 0, s>>>(ctx->gv, cv);
+  ++ctx->launches;
+  int rounds = 0;
+  for (;; ++rounds) {
+    if (rounds > (1 << 20)) return ctx->fail(RDISGPU_ERR_CUDA, "components: label propagation did not converge");
+    CK(cudaMemsetAsync(ctx->cc_flag.p, 0, sizeof(int32_t), s));
+    cc_hook_kernel<<<fb, threads, 0, s>>>(ctx->gv, cv);
+    cc_jump_kernel<<<vb, threads, 0, s>>>(ctx->gv, cv);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    int32_t changed = 0;
+    CK(cudaMemcpyAsync(&changed, ctx->cc_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (!changed) break;
+  }
+  cc_factor_labels_kernel<<<fb, threads, 0, s>>>(ctx->gv, cv);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(var_label, ctx->cc_vlabel.p, (size_t)V * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (fac_label) CK(cudaMemcpyAsync(fac_label, ctx->cc_flabel.p, (size_t)F * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (n_components) {
+    int32_t n = 0;
+    for (int64_t v = 0; v < V; ++v) n += (var_label[v] == (int32_t)v);
+    *n_components = n;
+  }
+  if (n_rounds) *n_rounds = rounds + 1;
   return RDISGPU_OK;
 }
 

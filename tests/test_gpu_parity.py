@@ -598,3 +598,71 @@ def test_ba_table_sweep_equals_list_sweep(gpu, oracle_mod):
     pf_d = torch.empty(spec["F"], dtype=torch.float64, device=dev); tot = torch.zeros(1, dtype=torch.float64, device=dev)
     ctx.eval_device(tot.data_ptr(), pf_d.data_ptr()); ctx.synchronize()
     assert np.array_equal(pf_d.cpu().numpy(), pf_a)
+
+
+def _scipy_labels(spec, assigned, fconst=()):
+    """Canonical (min variable id) component labels of the reference's connectivity rule, computed independently."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    V, F = spec["V"], spec["F"]
+    if spec["kind"] == "nlpf":
+        lens = np.diff(spec["rowptr"]); fe = np.repeat(np.arange(F), lens); ve = spec["vid"].astype(np.int64)
+    else:
+        nc = spec["ncams"]
+        fe = np.repeat(np.arange(F), 12)
+        ve = np.concatenate([9 * spec["cam"].astype(np.int64)[:, None] + np.arange(9), 9 * nc + 3 * spec["pt"].astype(np.int64)[:, None] + np.arange(3)], axis=1).ravel()
+    dead = np.zeros(F, bool); dead[list(fconst)] = True
+    keep = (~assigned.astype(bool)[ve]) & (~dead[fe])
+    g = coo_matrix((np.ones(keep.sum()), (ve[keep], V + fe[keep])), shape=(V + F, V + F))
+    _, lab = connected_components(g, directed=False)
+    vl = np.full(V, -1, np.int64)
+    un = np.nonzero(assigned == 0)[0]
+    first = {}
+    for v in un:                       # ascending: the first variable seen in a component is its smallest id
+        first.setdefault(lab[v], v)
+        vl[v] = first[lab[v]]
+    fl = np.full(F, -1, np.int64)
+    has = np.zeros(F, bool); np.logical_or.at(has, fe[keep], True)
+    fl[has] = np.array([first[lab[V + f]] for f in np.nonzero(has)[0]])
+    return vl, fl
+
+
+@pytest.mark.gpu
+def test_device_components_membership_is_exact(gpu, oracle_mod):
+    """rdisgpu_components (min-label propagation on the device) against an independent scipy labelling of the same
+    connectivity rule — integer bookkeeping: exact — on BA cuts, the sinusoid tree and chain (diameter 1000), random
+    assignments and assigned-constant factors; and the packed ProblemSet against the generators the bench uses."""
+    from rdis_b200 import Context, problems as P
+    rng = np.random.default_rng(3)
+    ba = P.ba_synthetic(ncams=7, npts=300, nobs=1300, seed=41)
+    tree = P.sinusoid(9, 2, 4)
+    chain = P.sinusoid(999, 1, 3)
+    cases = []
+    a = np.zeros(ba["V"], np.uint8); a[:63] = 1; cases.append((ba, a, ()))
+    a = np.zeros(ba["V"], np.uint8); a[63:] = 1; cases.append((ba, a, ()))
+    a = (rng.random(ba["V"]) < 0.5).astype(np.uint8); cases.append((ba, a, (5, 77, 900)))
+    a = np.zeros(tree["V"], np.uint8); a[:15] = 1; cases.append((tree, a, ()))
+    a = (rng.random(tree["V"]) < 0.3).astype(np.uint8); cases.append((tree, a, (0, 100, 2000)))
+    a = np.zeros(chain["V"], np.uint8); cases.append((chain, a, ()))
+    a = np.zeros(chain["V"], np.uint8); a[::97] = 1; cases.append((chain, a, ()))
+    ctxs = {}
+    for sp, a, fc in cases:
+        ctx = Context.from_spec(sp)
+        ctx.set_x(np.zeros(sp["V"]))
+        if fc:
+            ctx.set_factor_const(np.array(fc), np.zeros(len(fc)), np.ones(len(fc), np.uint8))
+        vl, fl, n, rounds = ctx.components(a)
+        wv, wf = _scipy_labels(sp, a, fc)
+        assert np.array_equal(vl, wv) and np.array_equal(fl, wf)
+        assert n == len(np.unique(wv[wv >= 0]))
+        print("components: V=%d F=%d -> %d components in %d rounds" % (sp["V"], sp["F"], n, rounds))
+    # the packed problem set == what the generators produce for the same cut
+    ctx = Context.from_spec(ba)
+    a = np.zeros(ba["V"], np.uint8); a[:63] = 1
+    got = ctx.component_problems(a); want = P.ba_point_problems(ba)
+    assert np.array_equal(got.var_off, want.var_off) and np.array_equal(got.vids, want.vids)
+    assert np.array_equal(got.fac_off, want.fac_off) and np.array_equal(got.fids, want.fids)
+    ctx = Context.from_spec(tree)
+    a = np.zeros(tree["V"], np.uint8); a[:7] = 1
+    got = ctx.component_problems(a); want = P.sinusoid_subtree_problems(tree, 3)
+    assert np.array_equal(got.vids, want.vids) and np.array_equal(got.fids, want.fids) and np.array_equal(got.fac_off, want.fac_off)
