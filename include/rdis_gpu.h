@@ -182,6 +182,11 @@ RDISGPU_API void rdisgpu_batch_destroy(rdisgpu_batch* b);
  * CTA of the camera kernel, problems on the generic kernels, max observations of a camera block,
  * launches of the last solve}. */
 RDISGPU_API int rdisgpu_batch_info(const rdisgpu_batch* b, int32_t out[8]);
+/* NonlinearProductFactor components solved by the shared-memory resident kernel (a component of more than 32
+ * factors whose flattened form — variables, distinct terms, edges, factors — fits one CTA's shared memory):
+ * out = {number of such problems in the batch, dynamic shared memory bytes of the launch}.  They are not counted
+ * in rdisgpu_batch_info's "problems on the generic kernels". */
+RDISGPU_API int rdisgpu_batch_resident_info(const rdisgpu_batch* b, int32_t out[2]);
 /* Kernel launches the last rdisgpu_batch_solve_cgd enqueued (bench.py's gpu_launches). */
 RDISGPU_API int rdisgpu_batch_last_launches(const rdisgpu_batch* b);
 

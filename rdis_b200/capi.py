@@ -21,7 +21,7 @@ EXPORTS = (
     "rdisgpu_set_x", "rdisgpu_get_x", "rdisgpu_set_factor_const",
     "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_eval_device", "rdisgpu_grad_device", "rdisgpu_factor_grad",
     "rdisgpu_solve_cgd", "rdisgpu_solve_cgd_csr", "rdisgpu_solve_lm_csr", "rdisgpu_batch_create", "rdisgpu_batch_create_csr", "rdisgpu_batch_info", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
-    "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches", "rdisgpu_components",
+    "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches", "rdisgpu_batch_resident_info", "rdisgpu_components",
     "rdisgpu_num_vars", "rdisgpu_num_factors", "rdisgpu_device_state", "rdisgpu_launch_count", "rdisgpu_version",
 )
 
@@ -72,6 +72,7 @@ def load_library(path=LIB_PATH):
         "rdisgpu_solve_lm_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
         "rdisgpu_components": (C.c_int, [vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]),
         "rdisgpu_batch_info": (C.c_int, [vp, vp]),
+        "rdisgpu_batch_resident_info": (C.c_int, [vp, vp]),
         "rdisgpu_batch_solve_cgd": (C.c_int, [vp, vp, C.c_int, dbl]),
         "rdisgpu_batch_fetch": (C.c_int, [vp, C.POINTER(Result), C.POINTER(dbl)]),
         "rdisgpu_batch_objective_device": (C.c_int, [vp, vp]),
@@ -401,8 +402,12 @@ class Batch:
     def info(self):
         out = np.zeros(8, np.int32)
         self.ctx._ck(self._lib.rdisgpu_batch_info(self._h, _p(out)))
-        return dict(zip(("nprobs", "point_warps", "camera_blocks", "cluster_size", "camera_threads", "generic_problems",
-                         "camera_nf_max", "last_launches"), out.tolist()))
+        d = dict(zip(("nprobs", "point_warps", "camera_blocks", "cluster_size", "camera_threads", "generic_problems",
+                      "camera_nf_max", "last_launches"), out.tolist()))
+        r = np.zeros(2, np.int32)
+        self.ctx._ck(self._lib.rdisgpu_batch_resident_info(self._h, _p(r)))
+        d["resident_problems"] = int(r[0]); d["resident_smem_bytes"] = int(r[1])
+        return d
 
     @property
     def last_launches(self):

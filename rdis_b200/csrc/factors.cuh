@@ -44,6 +44,13 @@ struct GraphView {
   const int32_t* vrow;
   const int32_t* vedge;
   const int32_t* efac;
+  // NLPF term table (nlpf_resident.cuh): the distinct (k, e, sine) expressions of each variable, variable-major
+  const int32_t* tvrow;   // i32[V+1]
+  const int32_t* eterm;   // i32[E]: edge -> its term (global term id)
+  const double* t_expo;   // f64[U]
+  const double* t_konst;  // f64[U]
+  const uint8_t* t_sine;  // u8[U]
+  int32_t* vloc;          // i32[V] scratch: variable -> slot inside the component that owns it
   // BA
   const int32_t* cam;
   const int32_t* pt;

@@ -19,6 +19,7 @@
 #include "lm_kernels.cuh"
 #include "ba_sweep.cuh"
 #include "components.cuh"
+#include "nlpf_resident.cuh"
 
 using namespace rdisgpu;
 
@@ -119,6 +120,12 @@ struct rdisgpu_ctx {
   DevBuf<int64_t> lm_off;
   bool lm_vloc_ready = false;
   bool ba_smem_optin = false;
+  // resident NonlinearProductFactor components (nlpf_resident.cuh): term table + host copies for classification
+  DevBuf<int32_t> tvrow, eterm, vloc;
+  DevBuf<double> t_expo, t_konst;
+  DevBuf<uint8_t> t_sine;
+  std::vector<int32_t> h_rp32, h_evid32, h_tvrow, vowner;
+  int res_smem_cap = -1;  // dynamic shared memory a resident CTA may ask for (queried at the first NLPF batch)
   DevBuf<uint8_t> cc_assigned;
   DevBuf<int32_t> cc_vlabel, cc_flabel, cc_flag;
   DevBuf<double> grid_partials;
@@ -163,6 +170,7 @@ struct rdisgpu_batch {
   // bundle-adjustment block fast paths (ba_block_kernels.cuh)
   int n_pt_warps = 0, n_cam = 0, cam_nf_max = 0;
   int cam_C = 0, cam_T = 0;  // chosen at the first solve (needs the occupancy query)
+  int res_smem = 0;  // dynamic shared memory of the resident NLPF class (largest layout in the batch)
   int last_launches = 0;
   bool solved = false;
 };
@@ -197,6 +205,8 @@ void fill_view(rdisgpu_ctx* c) {
   g.xbd = c->xbd.p; g.xval = c->xval.p; g.dom = c->dom.p;
   g.rowptr = c->rowptr.p; g.evid = c->evid.p; g.expo = c->expo.p; g.konst = c->konst.p;
   g.sine = c->sine.p; g.coeff = c->coeff.p; g.vrow = c->vrow.p; g.vedge = c->vedge.p; g.efac = c->efac.p;
+  g.tvrow = c->tvrow.p; g.eterm = c->eterm.p; g.t_expo = c->t_expo.p; g.t_konst = c->t_konst.p; g.t_sine = c->t_sine.p;
+  g.vloc = c->vloc.p;
   g.cam = c->cam.p; g.pt = c->pt.p; g.obs = c->obs.p; g.ncams = c->ncams; g.npts = c->npts;
   g.crow = c->crow.p; g.cfac = c->cfac.p; g.prow = c->prow.p; g.pfac = c->pfac.p;
   g.fconst_on = c->has_fconst ? c->fconst_on.p : nullptr;
@@ -416,6 +426,44 @@ int rdisgpu_finalize(rdisgpu_ctx* ctx) {
     CK(upload(ctx->vrow, vrow.data(), vrow.size(), s));
     CK(upload(ctx->vedge, vedge.data(), vedge.size(), s));
     CK(upload(ctx->efac, efac.data(), efac.size(), s));
+    // term table: the distinct (k, e, sine) expressions each variable enters factors through, variable-major, in
+    // order of first appearance (ascending factor id); compared bit for bit, so a shared term is the same number
+    {
+      std::vector<int32_t> tvrow((size_t)V + 1, 0), eterm((size_t)E, 0);
+      std::vector<double> t_expo, t_konst;
+      std::vector<uint8_t> t_sine;
+      t_expo.reserve((size_t)V * 2); t_konst.reserve((size_t)V * 2); t_sine.reserve((size_t)V * 2);
+      auto bits = [](double d) { uint64_t u; std::memcpy(&u, &d, 8); return u; };
+      for (int64_t v = 0; v < V; ++v) {
+        const size_t base = t_expo.size();
+        tvrow[v] = (int32_t)base;
+        for (int32_t r = vrow[v]; r < vrow[v + 1]; ++r) {
+          const int32_t e = vedge[r];
+          const uint64_t kb = bits(ctx->h_konst[e]), eb = bits(ctx->h_expo[e]);
+          const uint8_t sn = ctx->h_sine[e] ? 1 : 0;
+          size_t u = base;
+          for (; u < t_expo.size(); ++u)
+            if (bits(t_konst[u]) == kb && bits(t_expo[u]) == eb && t_sine[u] == sn) break;
+          if (u == t_expo.size()) {
+            if (u >= 0x7fffffffULL) return ctx->fail(RDISGPU_ERR_ARG, "finalize: too many terms");
+            t_expo.push_back(ctx->h_expo[e]); t_konst.push_back(ctx->h_konst[e]); t_sine.push_back(sn);
+          }
+          eterm[e] = (int32_t)u;
+        }
+      }
+      tvrow[V] = (int32_t)t_expo.size();
+      if (t_expo.empty()) { t_expo.push_back(0.0); t_konst.push_back(0.0); t_sine.push_back(0); }
+      CK(upload(ctx->tvrow, tvrow.data(), tvrow.size(), s));
+      CK(upload(ctx->eterm, eterm.data(), eterm.size(), s));
+      CK(upload(ctx->t_expo, t_expo.data(), t_expo.size(), s));
+      CK(upload(ctx->t_konst, t_konst.data(), t_konst.size(), s));
+      CK(upload(ctx->t_sine, t_sine.data(), t_sine.size(), s));
+      CK(ctx->vloc.ensure((size_t)V));
+      CK(cudaStreamSynchronize(s));  // the staging vectors die with this scope
+      ctx->h_tvrow.swap(tvrow);
+      ctx->h_rp32 = rp;
+      ctx->h_evid32 = ctx->h_evid;
+    }
     // factor tiles of the streaming sweep: consecutive factors, <= kTileFactors of them, <= kTileEdges edges
     std::vector<TileDesc> tiles;
     for (int64_t f = 0; f < F;) {
@@ -809,7 +857,7 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
     const int64_t nv = pv.nv(p), nf = pv.nf(p);
     if (nv < 0 || nf < 0 || (nv > 0 && !pv.vid(p)) || (nf > 0 && !pv.fid(p)) || nv > 0x7fffffffLL || nf > 0x7fffffffLL)
       return ctx->fail(RDISGPU_ERR_ARG, "batch: malformed problem");
-    b->h_probs[p] = ProblemDesc{tv, tf, (int32_t)nv, (int32_t)nf};
+    b->h_probs[p] = ProblemDesc{tv, tf, (int32_t)nv, (int32_t)nf, 0, 0, 0, 0};
     tv += nv;
     tf += nf;
   }
@@ -843,6 +891,7 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
   // sibling check: no variable and no factor may belong to two problems of one batch
   if ((int64_t)ctx->vmark.size() != ctx->V) ctx->vmark.assign((size_t)ctx->V, 0);
   if ((int64_t)ctx->fmark.size() != ctx->F) ctx->fmark.assign((size_t)ctx->F, 0);
+  if ((int64_t)ctx->vowner.size() != ctx->V) ctx->vowner.assign((size_t)ctx->V, 0);
   if (++ctx->mark_epoch == 0x7fffffff) {
     std::fill(ctx->vmark.begin(), ctx->vmark.end(), 0);
     std::fill(ctx->fmark.begin(), ctx->fmark.end(), 0);
@@ -858,6 +907,7 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
       if (v < 0 || v >= ctx->V) return ctx->fail(RDISGPU_ERR_ARG, "batch: variable id out of range");
       if (ctx->vmark[v] == epoch) return ctx->fail(RDISGPU_ERR_OVERLAP, "batch: a variable appears twice in the batch");
       ctx->vmark[v] = epoch;
+      ctx->vowner[v] = (int32_t)p;
       vids[D.var_off + j] = v;
     }
     for (int64_t k = 0; k < D.nf; ++k) {
@@ -918,6 +968,44 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
       for (int32_t o = 0; o < cnt; o += per_warp) h_tasks[b->n_pt_warps++] = PointWarpTask{lg, base + o, std::min(per_warp, cnt - o)};
     }
   }
+  // NonlinearProductFactor components that fit one CTA's shared memory: the resident kernel (nlpf_resident.cuh)
+  std::vector<int32_t> res_list;
+  b->res_smem = 0;
+  if (ctx->kind == KIND_NLPF && !ctx->generic_only) {
+    if (ctx->res_smem_cap < 0) {
+      int optin = 0;
+      cudaFuncAttributes fa;
+      CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+      CK(cudaFuncGetAttributes(&fa, solve_nlpf_resident_kernel));
+      ctx->res_smem_cap = std::max(0, optin - (int)fa.sharedSizeBytes);
+      CK(cudaFuncSetAttribute(solve_nlpf_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_smem_cap));
+    }
+    for (int64_t p = 0; p < nprobs; ++p) {
+      ProblemDesc& D = b->h_probs[p];
+      if (D.nf <= kTileMax || D.nv > 0xffff) continue;
+      const int32_t* pvv = vids + D.var_off;
+      const int32_t* pf = fids + D.fac_off;
+      int64_t nE = 0, nT = 0, nFz = 0;
+      bool ok = true;
+      for (int j = 0; j < D.nv; ++j) nT += ctx->h_tvrow[pvv[j] + 1] - ctx->h_tvrow[pvv[j]];
+      for (int k = 0; k < D.nf && ok; ++k) {
+        for (int32_t e = ctx->h_rp32[pf[k]]; e < ctx->h_rp32[pf[k] + 1]; ++e) {
+          const int32_t v = ctx->h_evid32[e];
+          if (ctx->vmark[v] != epoch) ++nFz;                       // frozen variable: a constant term
+          else if (ctx->vowner[v] != (int32_t)p) ok = false;        // not a sibling set: leave it to the generic path
+          ++nE;
+        }
+      }
+      if (!ok || nT + nFz > 0xffff || nE > 0x3fffffff) continue;
+      const ResLayout L = res_layout(D.nv, D.nf, (int)nE, (int)nT, (int)nFz);
+      if (L.total > ctx->res_smem_cap) continue;
+      D.nE = (int32_t)nE; D.nT = (int32_t)nT; D.nFz = (int32_t)nFz;
+      h_probs[p] = D;
+      b->res_smem = std::max(b->res_smem, L.total);
+      res_list.push_back((int32_t)p);
+      fast[p] = 3;
+    }
+  }
   for (int64_t p = 0; p < nprobs; ++p) {
     if (fast[p]) continue;
     const int nf = b->h_probs[p].nf;
@@ -941,6 +1029,10 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
     if (block_lists[t].empty()) continue;
     b->classes.push_back({1, 64 << t, (int64_t)b->h_order.size(), (int64_t)block_lists[t].size()});
     b->h_order.insert(b->h_order.end(), block_lists[t].begin(), block_lists[t].end());
+  }
+  if (!res_list.empty()) {
+    b->classes.push_back({3, kResThreads, (int64_t)b->h_order.size(), (int64_t)res_list.size()});
+    b->h_order.insert(b->h_order.end(), res_list.begin(), res_list.end());
   }
   if (!grid_list.empty()) {
     b->classes.push_back({2, 256, (int64_t)b->h_order.size(), (int64_t)grid_list.size()});
@@ -1103,6 +1195,9 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
         solve_block_kernel<NlpfOps><<<cnt, c.param, 0, s>>>(gv, bv, ord, cnt, maxiters, ftol);
       else
         solve_block_kernel<BaOps><<<cnt, c.param, 0, s>>>(gv, bv, ord, cnt, maxiters, ftol);
+      ++launches;
+    } else if (c.kind == 3) {
+      solve_nlpf_resident_kernel<<<cnt, c.param, (size_t)b->res_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
       ++launches;
     } else {
       const int threads = 256;
@@ -1405,7 +1500,8 @@ int rdisgpu_components(rdisgpu_ctx* ctx, const uint8_t* assigned, int32_t* var_l
 int rdisgpu_batch_info(const rdisgpu_batch* b, int32_t out[8]) {
   if (!b || !out) return RDISGPU_ERR_ARG;
   int n_generic = 0;
-  for (const auto& c : b->classes) n_generic += (int)c.count;
+  for (const auto& c : b->classes)
+    if (c.kind != 3) n_generic += (int)c.count;
   out[0] = (int32_t)b->nprobs;
   out[1] = b->n_pt_warps;
   out[2] = b->n_cam;
@@ -1414,6 +1510,15 @@ int rdisgpu_batch_info(const rdisgpu_batch* b, int32_t out[8]) {
   out[5] = n_generic;
   out[6] = b->cam_nf_max;
   out[7] = b->last_launches;
+  return RDISGPU_OK;
+}
+
+int rdisgpu_batch_resident_info(const rdisgpu_batch* b, int32_t out[2]) {
+  if (!b || !out) return RDISGPU_ERR_ARG;
+  out[0] = 0;
+  for (const auto& c : b->classes)
+    if (c.kind == 3) out[0] += (int32_t)c.count;
+  out[1] = b->res_smem;
   return RDISGPU_OK;
 }
 

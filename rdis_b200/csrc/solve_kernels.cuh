@@ -30,6 +30,9 @@ struct ProblemDesc {
   int64_t fac_off;  // into fids
   int32_t nv;
   int32_t nf;
+  // resident NonlinearProductFactor class only (nlpf_resident.cuh), 0 otherwise: edges, distinct terms of the
+  // problem's own variables, edges on frozen variables
+  int32_t nE, nT, nFz, pad_;
 };
 
 struct ResultRec {

@@ -666,3 +666,76 @@ def test_device_components_membership_is_exact(gpu, oracle_mod):
     a = np.zeros(tree["V"], np.uint8); a[:7] = 1
     got = ctx.component_problems(a); want = P.sinusoid_subtree_problems(tree, 3)
     assert np.array_equal(got.vids, want.vids) and np.array_equal(got.fids, want.fids) and np.array_equal(got.fac_off, want.fac_off)
+
+
+def _two_group_nlpf(seed, V=60, F=260, own=20):
+    """Random NonlinearProductFactor graph with two sibling components (variables [0, own) and [own, 2*own)) over a
+    pool of frozen variables [2*own, V): mixed exponents / constants / sine flags, repeated (k, e, sine) expressions
+    on one variable (shared terms), arities up to 7 (above the register fast path)."""
+    rng = np.random.default_rng(seed)
+    rows, groups = [], []
+    for j in range(F):
+        g = int(rng.integers(0, 2))
+        a = int(rng.integers(1, 8))
+        n_own = int(rng.integers(1, a + 1))
+        vs = list(rng.choice(np.arange(g * own, (g + 1) * own), size=min(n_own, own), replace=False))
+        vs += list(rng.choice(np.arange(2 * own, V), size=a - len(vs), replace=False))
+        rng.shuffle(vs)
+        rows.append(np.array(vs, np.int32)); groups.append(g)
+    rowptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])])
+    vid = np.concatenate(rows).astype(np.int32)
+    E = len(vid)
+    expo = rng.choice([1.0, 1.0, 2.0, 3.0], size=E)
+    konst = rng.choice([0.0, 0.0, 0.7, -1.3], size=E)
+    sine = rng.integers(0, 2, size=E).astype(np.uint8)
+    coeff = rng.normal(0, 0.5, size=F)
+    spec = dict(kind="nlpf", V=V, F=F, lb=np.full(V, -3.0), ub=np.full(V, 3.0), rowptr=rowptr, vid=vid, expo=expo,
+                konst=konst, sine=sine, coeff=coeff)
+    groups = np.array(groups)
+    probs = [(np.arange(g * own, (g + 1) * own, dtype=np.int32), np.nonzero(groups == g)[0].astype(np.int64)) for g in (0, 1)]
+    return spec, probs, rng.uniform(-2.5, 2.5, size=V)
+
+
+@pytest.mark.gpu
+def test_nlpf_resident_kernel_matches_generic_path(gpu, oracle_mod):
+    """The shared-memory resident NonlinearProductFactor component kernel (distinct terms evaluated once per line
+    point) against the generic CTA kernel (`generic_only`): it folds the same per-factor expressions over the same
+    factor -> thread mapping and reduction tree, so the whole result is demanded EQUAL (objective, iterations,
+    status, evaluation counts, committed state), and both within 1e-6 of the CPU oracle."""
+    from rdis_b200 import Context, problems as P
+    from rdis_b200.capi import ProblemSet
+    cases = []
+    tree = P.sinusoid(9, 2, 4)
+    cases.append(("sinusoid h=9 subtrees", tree, P.sinusoid_subtree_problems(tree, 3), P.random_start(tree, 11), ()))
+    spec, probs, x0 = _two_group_nlpf(17)
+    cases.append(("two-group general terms", spec, ProblemSet.from_lists(probs), x0, ()))
+    cases.append(("two-group + assigned constants", spec, ProblemSet.from_lists(probs), x0, (3, 40, 41, 200)))
+    for name, sp, ps, x0, fconst in cases:
+        fast = Context.from_spec(sp); slow = Context.from_spec(sp)
+        slow.set_option("generic_only", 1)
+        orc = oracle_mod.OracleFunction.from_spec(sp)
+        if fconst:
+            fid = np.array(fconst); val = np.linspace(-1.0, 2.0, len(fid)); on = np.ones(len(fid), np.uint8)
+            fast.set_factor_const(fid, val, on); slow.set_factor_const(fid, val, on); orc.set_factor_const(fid, val, on)
+        fast.set_x(x0); slow.set_x(x0); orc.set_x(x0)
+        x0c = x0[ps.vids]
+        bf = fast.batch(ps); info = bf.info(); bf.close()
+        assert info["resident_problems"] == ps.n and info["generic_problems"] == 0, info
+        a = fast.solve_cgd(ps, x0c, 25, 3e-8)
+        b = slow.solve_cgd(ps, x0c, 25, 3e-8)
+        o = orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0c, 25, 3e-8)
+        rel = _relerr(a["f_end"], b["f_end"], 1e-12)
+        exact = all(np.array_equal(a[k], b[k]) for k in ("f_init", "f_end", "iters", "status", "x"))
+        print("%s: %d problems, resident smem %d B, worst rel f_end vs generic %.2e, exact=%s, evals %d" % (
+            name, ps.n, info["resident_smem_bytes"], rel.max(), exact, int(a["n_feval"].sum() + a["n_geval"].sum())))
+        assert exact
+        assert np.array_equal(a["n_feval"], b["n_feval"]) and np.array_equal(a["n_geval"], b["n_geval"])
+        assert np.array_equal(fast.get_x(), slow.get_x())
+        _check_solves(a, o)
+        _check_committed_state(fast, sp, ps, x0, a)
+        # device-state start (x0 = None) on a subset: nothing outside the subset moves
+        sub = ps.subset(range(0, ps.n, 2))
+        fast.set_x(x0); slow.set_x(x0)
+        a = fast.solve_cgd(sub, None, 25, 3e-8); b = slow.solve_cgd(sub, None, 25, 3e-8)
+        assert np.array_equal(a["f_end"], b["f_end"]) and np.array_equal(a["x"], b["x"])
+        assert np.array_equal(fast.get_x(), slow.get_x())

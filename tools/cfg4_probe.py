@@ -17,17 +17,31 @@ print("generated V=%d F=%d in %.1f s" % (spec["V"], spec["F"], time.perf_counter
 t0 = time.perf_counter()
 ps = P.sinusoid_subtree_problems(spec, levels)
 print("%d sibling components, %d vars / %d factors each, built in %.1f s" % (ps.n, ps.var_off[1], ps.fac_off[1], time.perf_counter() - t0))
+t0 = time.perf_counter()
 ctx = Context.from_spec(spec)
+print("context (finalize incl. term table) in %.1f s" % (time.perf_counter() - t0))
 ctx.set_x(x0)
 f0 = ctx.eval()
-b = ctx.batch(ps)
-print("mapping", b.info())
-for rep in range(2):
-    ctx.set_x(x0)
-    ctx.synchronize()
+results = {}
+modes = os.environ.get("CFG4_MODES", "resident,generic").split(",")
+reps = int(os.environ.get("CFG4_REPS", "2"))
+for mode in modes:
+    if mode == "generic":
+        ctx.set_option("generic_only", 1)
     t0 = time.perf_counter()
-    b.solve(None, 25, 3e-8)
-    ctx.synchronize()
-    dt = time.perf_counter() - t0
-    r = b.fetch(want_x=False)
-    print("rep %d: %.2f ms for %d solves => %.0f solves/s; objective %.6e -> %.6e" % (rep, dt * 1e3, ps.n, ps.n / dt, f0, ctx.eval()))
+    b = ctx.batch(ps)
+    print(mode, "batch build %.1f ms, mapping" % ((time.perf_counter() - t0) * 1e3), b.info())
+    for rep in range(reps):
+        ctx.set_x(x0)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        b.solve(None, 25, 3e-8)
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        r = b.fetch(want_x=True)
+        print("%s rep %d: %.2f ms for %d solves => %.0f solves/s; objective %.6e -> %.6e; evals %d value + %d gradient" % (
+            mode, rep, dt * 1e3, ps.n, ps.n / dt, f0, ctx.eval(), int(r["n_feval"].sum()), int(r["n_geval"].sum())))
+    results[mode] = r
+    b.close()
+same = len(results) < 2 or all(np.array_equal(results["resident"][k], results["generic"][k]) for k in ("f_end", "iters", "status"))
+print("resident == generic (f_end, iters, status):", same)
