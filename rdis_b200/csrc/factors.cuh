@@ -51,6 +51,7 @@ struct GraphView {
   const double* t_konst;  // f64[U]
   const uint8_t* t_sine;  // u8[U]
   int32_t* vloc;          // i32[V] scratch: variable -> slot inside the component that owns it
+  int32_t* floc;          // i32[F] scratch: factor -> slot inside the component that owns it
   // BA
   const int32_t* cam;
   const int32_t* pt;

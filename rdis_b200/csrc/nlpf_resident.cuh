@@ -20,8 +20,10 @@
 // are the generic kernel's too, so the two kernels publish bit-identical objective / slope sequences
 // (tests/test_gpu_parity.py demands equality of the whole result, not a tolerance).
 // Edges on frozen variables (assigned ancestors) become constant terms evaluated once.
-// Full gradients (one per CG iteration) stay on the generic path (per-edge partials to `gedge`, variable-major
-// gather in ascending factor id): p and xi are kept current in HBM and in shared memory.
+// Full gradients (one per CG iteration) take the same two passes with the per-edge partials parked in an
+// L2-resident scratch slice of the problem, then a third pass, one thread per variable, folds the variable's
+// incident partials in ascending factor id (productGradient's order, src/State.h:157-194) through a
+// shared-memory incidence list built once at the start of the solve — no index chasing per gradient.
 //
 // Reference semantics: CGDSubspaceOptimizer::optimize src/optimizers/CGDSubspaceOptimizer.cpp:19-98,
 // SubfunctionFD::operator()/df :124-157, quickAssignVals :160-184, NonlinearProductFactor::evalFactor /
@@ -32,13 +34,18 @@
 
 namespace rdisgpu {
 
-constexpr int kResThreads = 256;  // = the generic block kernel's widest CTA: same factor -> thread mapping
+// CTA width.  512 threads (128 registers, 16 warps on the SM) is the default: the passes are latency-bound and twice
+// the warps hide more of it (cfg4 wave 36 -> 27 ms).  256 threads is the generic block kernel's widest CTA — the same
+// factor -> thread mapping and reduction tree, hence bit-identical results — and stays selectable
+// (rdisgpu_set_option "resident_threads") for the equality test.
+constexpr int kResThreads = 512;
+constexpr int kResThreadsExact = 256;
 
 // Shared-memory carve-up, computed identically on the host (fits? how many bytes to ask for) and in the kernel.
 struct ResLayout {
   int xs, ds, lb, ub, tval, tdt, texpo, tkonst, fcoef;  // double arrays (byte offsets)
   int toff, frow;                                        // int32
-  int tlv, elt;                                          // uint16
+  int tlv, elt, vinc;                                    // uint16
   int tsine;                                             // uint8
   int total;
 };
@@ -55,7 +62,7 @@ __host__ __device__ inline ResLayout res_layout(int nv, int nf, int nE, int nT, 
   L.texpo = take(8 * nT); L.tkonst = take(8 * nT);
   L.fcoef = take(8 * nf);
   L.toff = take(4 * (nv + 1)); L.frow = take(4 * (nf + 1));
-  L.tlv = take(2 * (nT + nFz)); L.elt = take(2 * nE);
+  L.tlv = take(2 * (nT + nFz)); L.elt = take(2 * nE); L.vinc = take(2 * nE);
   L.tsine = take(nT);
   L.total = o;
   return L;
@@ -95,34 +102,48 @@ __device__ __forceinline__ void block_exclusive_scan(int32_t* a, int n, int32_t*
 struct ResView {
   double *xs, *ds, *lb, *ub, *tval, *tdt, *texpo, *tkonst, *fcoef;
   int32_t *toff, *frow;
-  uint16_t *tlv, *elt;
+  uint16_t *tlv, *elt, *vinc;
   uint8_t* tsine;
   int nT;
+  double* gscr;  // this problem's slice of the per-edge partial scratch (HBM/L2), indexed by local edge
 };
 
 // One line evaluation: f(p + alpha*xi) and, if want_slope, d/dalpha — the shared-memory form of objective_along_line.
 __device__ __forceinline__ void resident_line_eval(const GraphView& G, const ResView& R, Block& grp, const int32_t* fids, int nf,
                                                    double alpha, bool want_slope, double& f, double& slope) {
   const int T = blockDim.x, tid = threadIdx.x;
-  // ---- pass 1: terms ----
-  for (int t = tid; t < R.nT; t += T) {
-    const int lv = R.tlv[t];
-    const double raw = R.xs[lv] + alpha * R.ds[lv];
-    const double xv = clamp_to_domain(raw, make_double2(R.lb[lv], R.ub[lv]));
-    const double ex = R.texpo[t], kk = R.tkonst[t];
-    const bool sn = R.tsine[t] != 0;
+  // ---- pass 1: terms, two per trip: every input of both is loaded before either result is stored, so the two
+  // dependency chains (clamp, power, sincos) interleave ----
+  for (int t = tid; t < R.nT; t += 2 * T) {
+    const int u = t + T;
+    const bool two = u < R.nT;
+    const int ub_ = two ? u : t;
+    const int lv0 = R.tlv[t], lv1 = R.tlv[ub_];
+    const double raw0 = R.xs[lv0] + alpha * R.ds[lv0], raw1 = R.xs[lv1] + alpha * R.ds[lv1];
+    const double xv0 = clamp_to_domain(raw0, make_double2(R.lb[lv0], R.ub[lv0]));
+    const double xv1 = clamp_to_domain(raw1, make_double2(R.lb[lv1], R.ub[lv1]));
+    const double ex0 = R.texpo[t], kk0 = R.tkonst[t], ex1 = R.texpo[ub_], kk1 = R.tkonst[ub_];
+    const bool sn0 = R.tsine[t] != 0, sn1 = R.tsine[ub_] != 0;
     if (want_slope) {
-      double tv, dt;
-      nlpf_term_grad(xv, kk, ex, sn, tv, dt);
-      R.tval[t] = tv;
-      R.tdt[t] = dt;
+      double tv0, dt0, tv1, dt1;
+      nlpf_term_grad(xv0, kk0, ex0, sn0, tv0, dt0);
+      nlpf_term_grad(xv1, kk1, ex1, sn1, tv1, dt1);
+      R.tval[t] = tv0;
+      R.tdt[t] = dt0;
+      if (two) {
+        R.tval[u] = tv1;
+        R.tdt[u] = dt1;
+      }
     } else {
-      R.tval[t] = nlpf_term_value(xv, kk, ex, sn);
+      const double tv0 = nlpf_term_value(xv0, kk0, ex0, sn0), tv1 = nlpf_term_value(xv1, kk1, ex1, sn1);
+      R.tval[t] = tv0;
+      if (two) R.tval[u] = tv1;
     }
   }
   __syncthreads();
   // ---- pass 2: factors, thread k owns factors k, k+T, ... (objective_along_line's mapping) ----
   double fs = 0.0, ss = 0.0;
+#pragma unroll 2
   for (int k = tid; k < nf; k += T) {
     const int r0 = R.frow[k] & 0x7fffffff;
     const int n = (R.frow[k + 1] & 0x7fffffff) - r0;
@@ -183,8 +204,98 @@ __device__ __forceinline__ void resident_line_eval(const GraphView& G, const Res
   slope = ss;
 }
 
+// Value and full gradient at p (Factor::computeGradient of every factor + computeGradientOfSum restricted to the
+// problem's variables): returns this thread's partial of the objective (caller reduces it when it needs f);
+// thread j-strided gradient entries are handed to `sink(j, dF/dx_j)`.  R.toff holds the incidence offsets here.
+template <class Sink>
+__device__ __forceinline__ double resident_gradient(const GraphView& G, const ResView& R, const int32_t* fids, int nv, int nf,
+                                                    Sink sink) {
+  const int T = blockDim.x, tid = threadIdx.x;
+  for (int t = tid; t < R.nT; t += 2 * T) {  // two terms per trip (see resident_line_eval)
+    const int u = t + T;
+    const bool two = u < R.nT;
+    const int ub_ = two ? u : t;
+    const int lv0 = R.tlv[t], lv1 = R.tlv[ub_];
+    const double xv0 = clamp_to_domain(R.xs[lv0], make_double2(R.lb[lv0], R.ub[lv0]));  // load_var<false>
+    const double xv1 = clamp_to_domain(R.xs[lv1], make_double2(R.lb[lv1], R.ub[lv1]));
+    const double ex0 = R.texpo[t], kk0 = R.tkonst[t], ex1 = R.texpo[ub_], kk1 = R.tkonst[ub_];
+    const bool sn0 = R.tsine[t] != 0, sn1 = R.tsine[ub_] != 0;
+    double tv0, dt0, tv1, dt1;
+    nlpf_term_grad(xv0, kk0, ex0, sn0, tv0, dt0);
+    nlpf_term_grad(xv1, kk1, ex1, sn1, tv1, dt1);
+    R.tval[t] = tv0;
+    R.tdt[t] = dt0;
+    if (two) {
+      R.tval[u] = tv1;
+      R.tdt[u] = dt1;
+    }
+  }
+  __syncthreads();
+  double fs = 0.0;
+  for (int k = tid; k < nf; k += T) {  // NlpfOps::gradient, expression for expression
+    const int r0 = R.frow[k] & 0x7fffffff;
+    const int n = (R.frow[k + 1] & 0x7fffffff) - r0;
+    const bool is_const = R.frow[k] < 0;
+    const double c = R.fcoef[k];
+    double prod = 1.0;
+    if (n <= NlpfOps::kMaxArityFast) {
+      double t[NlpfOps::kMaxArityFast], dt[NlpfOps::kMaxArityFast];
+#pragma unroll
+      for (int i = 0; i < NlpfOps::kMaxArityFast; ++i) {
+        if (i < n) {
+          const int lt = R.elt[r0 + i];
+          t[i] = R.tval[lt];
+          dt[i] = R.tdt[lt];
+          prod *= t[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NlpfOps::kMaxArityFast; ++i) {
+        if (i < n) {
+          double pe = 1.0;
+#pragma unroll
+          for (int j = 0; j < NlpfOps::kMaxArityFast; ++j) {
+            if (j < n) pe *= (j == i) ? dt[j] : t[j];
+          }
+          R.gscr[r0 + i] = pe * c;
+        }
+      }
+    } else {
+      for (int i = 0; i < n; ++i) {
+        prod *= R.tval[R.elt[r0 + i]];
+        double pe = 1.0;
+        for (int j = 0; j < n; ++j) {
+          const int lj = R.elt[r0 + j];
+          pe *= (j == i) ? R.tdt[lj] : R.tval[lj];
+        }
+        R.gscr[r0 + i] = pe * c;
+      }
+    }
+    double fv = prod * c;
+    if (is_const) fv = G.fconst_val[fids[k]];
+    fs += fv;
+  }
+  __syncthreads();  // the partials of every factor are visible to the CTA
+  for (int j = tid; j < nv; j += T) {
+    const int a0 = R.toff[j], a1 = R.toff[j + 1];
+    double acc = 0.0;
+    for (int a = a0; a < a1; a += 4) {  // four partials in flight, folded in list order (gather_var's filter path)
+      double ge[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ge[i] = (a + i < a1) ? R.gscr[R.vinc[a + i]] : 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (a + i < a1) acc = (a + i == a0) ? ge[i] : acc + ge[i];
+      }
+    }
+    sink(j, acc);
+  }
+  return fs;
+}
+
 // grid = number of resident-class problems, one CTA each; dynamic shared memory = the largest layout of the class.
-__global__ void __launch_bounds__(kResThreads, 1)
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, 1)
     solve_nlpf_resident_kernel(GraphView G, BatchView B, const int32_t* order, int count, int maxiters, double ftol) {
   extern __shared__ __align__(16) unsigned char res_smem[];
   __shared__ double scratch[260];
@@ -209,6 +320,8 @@ __global__ void __launch_bounds__(kResThreads, 1)
   R.fcoef = reinterpret_cast<double*>(res_smem + L.fcoef);
   R.toff = reinterpret_cast<int32_t*>(res_smem + L.toff); R.frow = reinterpret_cast<int32_t*>(res_smem + L.frow);
   R.tlv = reinterpret_cast<uint16_t*>(res_smem + L.tlv); R.elt = reinterpret_cast<uint16_t*>(res_smem + L.elt);
+  R.vinc = reinterpret_cast<uint16_t*>(res_smem + L.vinc);
+  R.gscr = B.gscr + P.goff;
   R.tsine = res_smem + L.tsine;
   R.nT = P.nT;
 
@@ -227,6 +340,7 @@ __global__ void __launch_bounds__(kResThreads, 1)
   for (int k = tid; k < nf; k += T) {
     const int32_t fid = fids[k];
     G.fstamp[fid] = stamp;
+    G.floc[fid] = k;
     R.frow[k] = __ldg(&G.rowptr[fid + 1]) - __ldg(&G.rowptr[fid]);
     R.fcoef[k] = __ldg(&G.coeff[fid]);
   }
@@ -267,6 +381,28 @@ __global__ void __launch_bounds__(kResThreads, 1)
     }
   }
   __syncthreads();
+  // variable-major incidence of the component (local edge ids, ascending factor id = the order of the global
+  // incidence list): toff is free now and becomes its offsets
+  for (int j = tid; j < nv; j += T) {
+    const int32_t vid = vids[j];
+    int cnt = 0;
+    for (int32_t r = __ldg(&G.vrow[vid]); r < __ldg(&G.vrow[vid + 1]); ++r)
+      cnt += (G.fstamp[__ldg(&G.efac[__ldg(&G.vedge[r])])] == stamp);
+    R.toff[j] = cnt;
+  }
+  __syncthreads();
+  block_exclusive_scan(R.toff, nv, wtot);
+  for (int j = tid; j < nv; j += T) {
+    const int32_t vid = vids[j];
+    int pos = R.toff[j];
+    for (int32_t r = __ldg(&G.vrow[vid]); r < __ldg(&G.vrow[vid + 1]); ++r) {
+      const int32_t e = __ldg(&G.vedge[r]);
+      const int32_t f = __ldg(&G.efac[e]);
+      if (G.fstamp[f] != stamp) continue;
+      R.vinc[pos++] = (uint16_t)(R.frow[G.floc[f]] + (e - __ldg(&G.rowptr[f])));
+    }
+  }
+  __syncthreads();
   // assigned-constant factors: flag in the sign bit of the row start (values fetched from HBM when it is set)
   if (G.fconst_on != nullptr) {
     for (int k = tid; k < nf; k += T) {
@@ -281,18 +417,15 @@ __global__ void __launch_bounds__(kResThreads, 1)
 
   while (!m.done()) {
     if (m.req == REQ_INIT_GRAD) {
-      double fs = write_factor_partials<NlpfOps>(G, grp, fids, nf);
-      double zero = 0.0;
-      grp.sum2(fs, zero);
-      grp.sync();
-      for (int j = tid; j < nv; j += T) {
+      double fs = resident_gradient(G, R, fids, nv, nf, [&](int j, double gr) {
         const int32_t vid = vids[j];
-        const double gneg = -NlpfOps::gather_var(G, vid, stamp, true);
+        const double gneg = -gr;
         G.gvec[vid] = gneg;
         G.hvec[vid] = gneg;
-        G.xbd[vid].y = gneg;
         R.ds[j] = gneg;
-      }
+      });
+      double zero = 0.0;
+      grp.sum2(fs, zero);
       grp.sync();
       f_init = fs;
       m.on_init(fs);
@@ -305,37 +438,28 @@ __global__ void __launch_bounds__(kResThreads, 1)
     while (m.req == REQ_MOVE) {
       const double step = m.alpha;
       for (int j = tid; j < nv; j += T) {  // minimize_nrc.h:508-511
-        const int32_t vid = vids[j];
         double2 xb = make_double2(R.xs[j], R.ds[j]);
         xb.y *= step;
         xb.x += xb.y;
-        G.xbd[vid] = xb;
         R.xs[j] = xb.x; R.ds[j] = xb.y;
       }
       grp.sync();
       m.on_moved();
       if (m.req != REQ_GRADIENT) break;
 
-      (void)write_factor_partials<NlpfOps>(G, grp, fids, nf);
-      grp.sync();
       double gg = 0.0, dgg = 0.0, dummy = 0.0, tnum = 0.0;
-      for (int j = tid; j < nv; j += T) {
-        const int32_t vid = vids[j];
-        const double gr = NlpfOps::gather_var(G, vid, stamp, true);
+      (void)resident_gradient(G, R, fids, nv, nf, [&](int j, double gr) {
         R.ds[j] = gr;  // func.df(p, xi), :654
         const double pj = fabs(R.xs[j]);
-        const double t = fabs(gr) * ((pj < 1.0) ? 1.0 : pj);
+        const double t = fabs(gr) * ((pj < 1.0) ? 1.0 : pj);  // :659 numerator
         tnum = (t > tnum) ? t : tnum;
-        const double gj = G.gvec[vid];
+        const double gj = G.gvec[vids[j]];
         gg += gj * gj;
         dgg += (gr + gj) * gr;
-      }
+      });
       grp.sum3max(gg, dgg, dummy, tnum);
       m.on_gradient(tnum, gg, dgg);
-      if (m.req != REQ_DIRECTION) {
-        for (int j = tid; j < nv; j += T) G.xbd[vids[j]].y = R.ds[j];
-        break;
-      }
+      if (m.req != REQ_DIRECTION) break;
       const double gam = m.gam;
       for (int j = tid; j < nv; j += T) {  // :681-685
         const int32_t vid = vids[j];
@@ -343,7 +467,6 @@ __global__ void __launch_bounds__(kResThreads, 1)
         const double hj = gj + gam * G.hvec[vid];
         G.gvec[vid] = gj;
         G.hvec[vid] = hj;
-        G.xbd[vid].y = hj;
         R.ds[j] = hj;
       }
       grp.sync();

@@ -121,10 +121,11 @@ struct rdisgpu_ctx {
   bool lm_vloc_ready = false;
   bool ba_smem_optin = false;
   // resident NonlinearProductFactor components (nlpf_resident.cuh): term table + host copies for classification
-  DevBuf<int32_t> tvrow, eterm, vloc;
+  DevBuf<int32_t> tvrow, eterm, vloc, floc;
   DevBuf<double> t_expo, t_konst;
   DevBuf<uint8_t> t_sine;
   std::vector<int32_t> h_rp32, h_evid32, h_tvrow, vowner;
+  int res_threads = kResThreads;  // rdisgpu_set_option("resident_threads", 256 | 512)
   int res_smem_cap = -1;  // dynamic shared memory a resident CTA may ask for (queried at the first NLPF batch)
   DevBuf<uint8_t> cc_assigned;
   DevBuf<int32_t> cc_vlabel, cc_flabel, cc_flag;
@@ -170,6 +171,7 @@ struct rdisgpu_batch {
   // bundle-adjustment block fast paths (ba_block_kernels.cuh)
   int n_pt_warps = 0, n_cam = 0, cam_nf_max = 0;
   int cam_C = 0, cam_T = 0;  // chosen at the first solve (needs the occupancy query)
+  DevBuf<double> res_gscr;  // resident NLPF class: per-edge partials, one slice per problem
   int res_smem = 0;  // dynamic shared memory of the resident NLPF class (largest layout in the batch)
   int last_launches = 0;
   bool solved = false;
@@ -206,7 +208,7 @@ void fill_view(rdisgpu_ctx* c) {
   g.rowptr = c->rowptr.p; g.evid = c->evid.p; g.expo = c->expo.p; g.konst = c->konst.p;
   g.sine = c->sine.p; g.coeff = c->coeff.p; g.vrow = c->vrow.p; g.vedge = c->vedge.p; g.efac = c->efac.p;
   g.tvrow = c->tvrow.p; g.eterm = c->eterm.p; g.t_expo = c->t_expo.p; g.t_konst = c->t_konst.p; g.t_sine = c->t_sine.p;
-  g.vloc = c->vloc.p;
+  g.vloc = c->vloc.p; g.floc = c->floc.p;
   g.cam = c->cam.p; g.pt = c->pt.p; g.obs = c->obs.p; g.ncams = c->ncams; g.npts = c->npts;
   g.crow = c->crow.p; g.cfac = c->cfac.p; g.prow = c->prow.p; g.pfac = c->pfac.p;
   g.fconst_on = c->has_fconst ? c->fconst_on.p : nullptr;
@@ -307,6 +309,11 @@ int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return RDISGPU_ERR_ARG;
   if (std::strcmp(name, "generic_only") == 0) {
     ctx->generic_only = (value != 0);
+    return RDISGPU_OK;
+  }
+  if (std::strcmp(name, "resident_threads") == 0) {
+    if (value != kResThreads && value != kResThreadsExact) return ctx->fail(RDISGPU_ERR_ARG, "set_option: resident_threads must be 256 or 512");
+    ctx->res_threads = (int)value;
     return RDISGPU_OK;
   }
   return ctx->fail(RDISGPU_ERR_ARG, "set_option: unknown option");
@@ -459,6 +466,7 @@ int rdisgpu_finalize(rdisgpu_ctx* ctx) {
       CK(upload(ctx->t_konst, t_konst.data(), t_konst.size(), s));
       CK(upload(ctx->t_sine, t_sine.data(), t_sine.size(), s));
       CK(ctx->vloc.ensure((size_t)V));
+      CK(ctx->floc.ensure((size_t)std::max<int64_t>(F, 1)));
       CK(cudaStreamSynchronize(s));  // the staging vectors die with this scope
       ctx->h_tvrow.swap(tvrow);
       ctx->h_rp32 = rp;
@@ -970,15 +978,17 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
   }
   // NonlinearProductFactor components that fit one CTA's shared memory: the resident kernel (nlpf_resident.cuh)
   std::vector<int32_t> res_list;
+  int64_t res_edges = 0;
   b->res_smem = 0;
   if (ctx->kind == KIND_NLPF && !ctx->generic_only) {
     if (ctx->res_smem_cap < 0) {
       int optin = 0;
       cudaFuncAttributes fa;
       CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-      CK(cudaFuncGetAttributes(&fa, solve_nlpf_resident_kernel));
+      CK(cudaFuncGetAttributes(&fa, solve_nlpf_resident_kernel<kResThreads>));
       ctx->res_smem_cap = std::max(0, optin - (int)fa.sharedSizeBytes);
-      CK(cudaFuncSetAttribute(solve_nlpf_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_smem_cap));
+      CK(cudaFuncSetAttribute(solve_nlpf_resident_kernel<kResThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_smem_cap));
+      CK(cudaFuncSetAttribute(solve_nlpf_resident_kernel<kResThreadsExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_smem_cap));
     }
     for (int64_t p = 0; p < nprobs; ++p) {
       ProblemDesc& D = b->h_probs[p];
@@ -996,10 +1006,11 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
           ++nE;
         }
       }
-      if (!ok || nT + nFz > 0xffff || nE > 0x3fffffff) continue;
+      if (!ok || nT + nFz > 0xffff || nE > 0xffff || res_edges + nE > 0x7fffffffLL) continue;
       const ResLayout L = res_layout(D.nv, D.nf, (int)nE, (int)nT, (int)nFz);
       if (L.total > ctx->res_smem_cap) continue;
-      D.nE = (int32_t)nE; D.nT = (int32_t)nT; D.nFz = (int32_t)nFz;
+      D.nE = (int32_t)nE; D.nT = (int32_t)nT; D.nFz = (int32_t)nFz; D.goff = (int32_t)res_edges;
+      res_edges += nE;
       h_probs[p] = D;
       b->res_smem = std::max(b->res_smem, L.total);
       res_list.push_back((int32_t)p);
@@ -1031,7 +1042,8 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
     b->h_order.insert(b->h_order.end(), block_lists[t].begin(), block_lists[t].end());
   }
   if (!res_list.empty()) {
-    b->classes.push_back({3, kResThreads, (int64_t)b->h_order.size(), (int64_t)res_list.size()});
+    CK(b->res_gscr.ensure((size_t)res_edges));
+    b->classes.push_back({3, ctx->res_threads, (int64_t)b->h_order.size(), (int64_t)res_list.size()});
     b->h_order.insert(b->h_order.end(), res_list.begin(), res_list.end());
   }
   if (!grid_list.empty()) {
@@ -1113,6 +1125,7 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
   bv.x0 = x0_host ? (x0_on_device ? x0_host : b->x0.p) : nullptr;
   bv.xout = b->xout.p;
   bv.res = b->res.p;
+  bv.gscr = b->res_gscr.p;
   GraphView gv = ctx->gv;
   int launches = 0;
   if (b->n_pt_warps > 0) {
@@ -1197,7 +1210,10 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
         solve_block_kernel<BaOps><<<cnt, c.param, 0, s>>>(gv, bv, ord, cnt, maxiters, ftol);
       ++launches;
     } else if (c.kind == 3) {
-      solve_nlpf_resident_kernel<<<cnt, c.param, (size_t)b->res_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
+      if (c.param == kResThreadsExact)
+        solve_nlpf_resident_kernel<kResThreadsExact><<<cnt, kResThreadsExact, (size_t)b->res_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
+      else
+        solve_nlpf_resident_kernel<kResThreads><<<cnt, kResThreads, (size_t)b->res_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
       ++launches;
     } else {
       const int threads = 256;
@@ -1402,6 +1418,7 @@ int rdisgpu_solve_lm_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_of
   bv.x0 = x0 ? (x0_on_device ? x0 : b->x0.p) : nullptr;
   bv.xout = b->xout.p;
   bv.res = b->res.p;
+  bv.gscr = nullptr;
   LmView lv;
   lv.vloc = ctx->lm_vloc.p;
   lv.scratch = ctx->lm_scratch.p;

@@ -32,7 +32,7 @@ struct ProblemDesc {
   int32_t nf;
   // resident NonlinearProductFactor class only (nlpf_resident.cuh), 0 otherwise: edges, distinct terms of the
   // problem's own variables, edges on frozen variables
-  int32_t nE, nT, nFz, pad_;
+  int32_t nE, nT, nFz, goff;  // goff: first slot of the problem's slice of BatchView::gscr
 };
 
 struct ResultRec {
@@ -51,6 +51,7 @@ struct BatchView {
   const double* x0;  // nullable
   double* xout;
   ResultRec* res;
+  double* gscr;  // resident NLPF class: per-edge partial scratch, one slice per problem (nullable)
 };
 
 // ------------------------------------------------------------------------------------------
