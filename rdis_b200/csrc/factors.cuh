@@ -90,7 +90,7 @@ __device__ __forceinline__ double load_var(const GraphView& G, int32_t vid, doub
     return xb.x;
   }
   dirv = xb.y;
-  const double raw = kAlongLine ? (xb.x + alpha * xb.y) : xb.x;
+  const double raw = kAlongLine ? __fma_rn(alpha, xb.y, xb.x) : xb.x;  // explicit: every kernel forms p + alpha*xi the same way
   return clamp_to_domain(raw, __ldg(&G.dom[vid]));
 }
 
@@ -242,7 +242,7 @@ struct NlpfOps {
               }
             }
           }
-          s += (pe * c) * dir[i];
+          s = __fma_rn(pe * c, dir[i], s);  // explicit contraction: the resident kernel (nlpf_resident.cuh) folds the same way
         }
       }
       slope = s;
@@ -255,7 +255,7 @@ struct NlpfOps {
       bool pl;
       term<kAlongLine>(G, ei, alpha, ti, dti, pl, diri);
       prod *= ti;
-      if (diri != 0.0) s += partial<kAlongLine>(G, e0, e1, ei, alpha) * c * diri;
+      if (diri != 0.0) s = __fma_rn(partial<kAlongLine>(G, e0, e1, ei, alpha) * c, diri, s);
     }
     slope = s;
     return prod * c;

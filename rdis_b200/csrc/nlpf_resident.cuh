@@ -8,7 +8,7 @@
 // component, ~445 evaluations per solve.  Here the component is flattened once, at the start of the solve, into
 //   variables   p, xi, lb, ub                                                (4 x 8 B per variable)
 //   TERMS       the distinct (variable, k, e, sine) tuples of the component  (value, derivative, e, k, flag, owner)
-//   edges       u16 index of their term                                      (2 B per edge)
+//   edges       u16 index of their term + u16 slot of their variable         (4 B per edge)
 //   factors     coefficient + first edge                                     (12 B per factor)
 // and a line evaluation is two shared-memory passes: (1) one thread per TERM clamps p + alpha*xi and evaluates the
 // term (and its derivative when the slope is wanted), (2) one thread per FACTOR folds the product in slot order.
@@ -20,6 +20,10 @@
 // are the generic kernel's too, so the two kernels publish bit-identical objective / slope sequences
 // (tests/test_gpu_parity.py demands equality of the whole result, not a tolerance).
 // Edges on frozen variables (assigned ancestors) become constant terms evaluated once.
+// Terms are laid out by class — all sine terms first, then the rest — so a warp of pass 1 runs ONE of the two
+// bodies (the sincos chain or the few-instruction polynomial one) instead of both under divergence, and pass 2
+// dispatches on the factor's arity to straight-line code (the generators emit factors arity-major, so warps are
+// uniform there too).
 // Full gradients (one per CG iteration) take the same two passes with the per-edge partials parked in an
 // L2-resident scratch slice of the problem, then a third pass, one thread per variable, folds the variable's
 // incident partials in ascending factor id (productGradient's order, src/State.h:157-194) through a
@@ -40,13 +44,18 @@ namespace rdisgpu {
 // (rdisgpu_set_option "resident_threads") for the equality test.
 constexpr int kResThreads = 512;
 constexpr int kResThreadsExact = 256;
+// Small components (a few hundred variables) leave a 512-thread CTA mostly idle and a CTA owns the whole register
+// file: they run 128 threads wide, four CTAs to the SM.
+constexpr int kResThreadsSmall = 128;
+constexpr int kResSmallCtas = 4;
+constexpr int kResSmallFactors = 1536;      // at most this many factors ...
+constexpr int kResSmallSmem = 52 * 1024;    // ... and this much shared memory
 
 // Shared-memory carve-up, computed identically on the host (fits? how many bytes to ask for) and in the kernel.
 struct ResLayout {
   int xs, ds, lb, ub, tval, tdt, texpo, tkonst, fcoef;  // double arrays (byte offsets)
   int toff, frow;                                        // int32
-  int tlv, elt, vinc;                                    // uint16
-  int tsine;                                             // uint8
+  int tlv, elt, elv;                                     // uint16
   int total;
 };
 __host__ __device__ inline ResLayout res_layout(int nv, int nf, int nE, int nT, int nFz) {
@@ -57,13 +66,12 @@ __host__ __device__ inline ResLayout res_layout(int nv, int nf, int nE, int nT, 
     o += (bytes + 15) & ~15;
     return at;
   };
-  L.xs = take(8 * nv); L.ds = take(8 * nv); L.lb = take(8 * nv); L.ub = take(8 * nv);
+  L.xs = take(8 * nv); L.ds = take(8 * (nv + 1)); L.lb = take(8 * nv); L.ub = take(8 * nv);
   L.tval = take(8 * (nT + nFz)); L.tdt = take(8 * (nT + nFz));
   L.texpo = take(8 * nT); L.tkonst = take(8 * nT);
   L.fcoef = take(8 * nf);
   L.toff = take(4 * (nv + 1)); L.frow = take(4 * (nf + 1));
-  L.tlv = take(2 * (nT + nFz)); L.elt = take(2 * nE); L.vinc = take(2 * nE);
-  L.tsine = take(nT);
+  L.tlv = take(2 * nT); L.elt = take(2 * nE); L.elv = take(2 * nE);
   L.total = o;
   return L;
 }
@@ -102,94 +110,133 @@ __device__ __forceinline__ void block_exclusive_scan(int32_t* a, int n, int32_t*
 struct ResView {
   double *xs, *ds, *lb, *ub, *tval, *tdt, *texpo, *tkonst, *fcoef;
   int32_t *toff, *frow;
-  uint16_t *tlv, *elt, *vinc;
-  uint8_t* tsine;
-  int nT;
-  double* gscr;  // this problem's slice of the per-edge partial scratch (HBM/L2), indexed by local edge
+  uint16_t *tlv, *elt, *elv;
+  int nT, nS;            // own terms; the first nS of them are the sine class
+  double* gscr;          // this problem's slice of the per-edge partial scratch (HBM/L2), indexed by local edge
+  const uint16_t* vinc;  // ... and of the variable-major incidence list (local edge ids, ascending factor id)
 };
 
-// One line evaluation: f(p + alpha*xi) and, if want_slope, d/dalpha — the shared-memory form of objective_along_line.
-__device__ __forceinline__ void resident_line_eval(const GraphView& G, const ResView& R, Block& grp, const int32_t* fids, int nf,
-                                                   double alpha, bool want_slope, double& f, double& slope) {
-  const int T = blockDim.x, tid = threadIdx.x;
-  // ---- pass 1: terms, two per trip: every input of both is loaded before either result is stored, so the two
-  // dependency chains (clamp, power, sincos) interleave ----
-  for (int t = tid; t < R.nT; t += 2 * T) {
-    const int u = t + T;
-    const bool two = u < R.nT;
-    const int ub_ = two ? u : t;
-    const int lv0 = R.tlv[t], lv1 = R.tlv[ub_];
-    const double raw0 = R.xs[lv0] + alpha * R.ds[lv0], raw1 = R.xs[lv1] + alpha * R.ds[lv1];
-    const double xv0 = clamp_to_domain(raw0, make_double2(R.lb[lv0], R.ub[lv0]));
-    const double xv1 = clamp_to_domain(raw1, make_double2(R.lb[lv1], R.ub[lv1]));
-    const double ex0 = R.texpo[t], kk0 = R.tkonst[t], ex1 = R.texpo[ub_], kk1 = R.tkonst[ub_];
-    const bool sn0 = R.tsine[t] != 0, sn1 = R.tsine[ub_] != 0;
-    if (want_slope) {
-      double tv0, dt0, tv1, dt1;
-      nlpf_term_grad(xv0, kk0, ex0, sn0, tv0, dt0);
-      nlpf_term_grad(xv1, kk1, ex1, sn1, tv1, dt1);
-      R.tval[t] = tv0;
-      R.tdt[t] = dt0;
-      if (two) {
-        R.tval[u] = tv1;
-        R.tdt[u] = dt1;
+// Sum of two doubles per thread over the CTA: Block::reduce's order (warp butterfly, warp partials folded 0..nw-1 by
+// every thread), so a 256-thread CTA reproduces the generic kernel's totals to the bit.  buf = 2 x 64 doubles.
+__device__ __forceinline__ void resident_sum2(double* buf2, int& flip, double& a, double& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  double* buf = buf2 + flip * 64;
+  flip ^= 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) {
+    buf[2 * warp] = a;
+    buf[2 * warp + 1] = b;
+  }
+  __syncthreads();
+  a = buf[0];
+  b = buf[1];
+  for (int w = 1; w < nw; ++w) {
+    a += buf[2 * w];
+    b += buf[2 * w + 1];
+  }
+}
+
+// One factor of arity N (compile-time): value term product in slot order and, with kSlope, the directional
+// derivative sum_i (d f/d x_i) xi_i — NlpfOps::value's expressions (1.0 * t == t, so the leading 1.0 is dropped).
+template <int N, bool kSlope>
+__device__ __forceinline__ void resident_fold(const ResView& R, int r0, double c, double& prod, double& s) {
+  double t[N], dt[N], dir[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int lt = R.elt[r0 + i];
+    t[i] = R.tval[lt];
+    if (kSlope) {
+      dt[i] = R.tdt[lt];
+      dir[i] = R.ds[R.elv[r0 + i]];  // slot nv holds 0.0: frozen variable
+    }
+  }
+  prod = t[0];
+#pragma unroll
+  for (int i = 1; i < N; ++i) prod *= t[i];
+  s = 0.0;
+  if (kSlope) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (dir[i] != 0.0) {
+        double pe = (i == 0) ? dt[0] : t[0];  // getDerivative: own slot replaced by its derivative (1.0 when plain)
+#pragma unroll
+        for (int j = 1; j < N; ++j) pe *= (j == i) ? dt[j] : t[j];
+        s = __fma_rn(pe * c, dir[i], s);
       }
+    }
+  }
+}
+
+// Pass 1 of an evaluation: every own term at x = clamp(p + alpha*xi).  kGrad: also the own-slot derivative.
+template <bool kGrad>
+__device__ __forceinline__ void resident_terms(const ResView& R, double alpha, bool along) {
+  const int T = blockDim.x, tid = threadIdx.x;
+  for (int t = tid; t < R.nS; t += T) {  // sine class
+    const int lv = R.tlv[t];
+    const double raw = along ? __fma_rn(alpha, R.ds[lv], R.xs[lv]) : R.xs[lv];
+    const double xv = clamp_to_domain(raw, make_double2(R.lb[lv], R.ub[lv]));
+    if (kGrad) {
+      double tv, dt;
+      nlpf_term_grad(xv, R.tkonst[t], R.texpo[t], true, tv, dt);
+      R.tval[t] = tv;
+      R.tdt[t] = dt;
     } else {
-      const double tv0 = nlpf_term_value(xv0, kk0, ex0, sn0), tv1 = nlpf_term_value(xv1, kk1, ex1, sn1);
-      R.tval[t] = tv0;
-      if (two) R.tval[u] = tv1;
+      R.tval[t] = nlpf_term_value(xv, R.tkonst[t], R.texpo[t], true);
+    }
+  }
+  for (int t = R.nS + tid; t < R.nT; t += T) {  // polynomial class
+    const int lv = R.tlv[t];
+    const double raw = along ? __fma_rn(alpha, R.ds[lv], R.xs[lv]) : R.xs[lv];
+    const double xv = clamp_to_domain(raw, make_double2(R.lb[lv], R.ub[lv]));
+    if (kGrad) {
+      double tv, dt;
+      nlpf_term_grad(xv, R.tkonst[t], R.texpo[t], false, tv, dt);
+      R.tval[t] = tv;
+      R.tdt[t] = dt;
+    } else {
+      R.tval[t] = nlpf_term_value(xv, R.tkonst[t], R.texpo[t], false);
     }
   }
   __syncthreads();
+}
+
+// One line evaluation: f(p + alpha*xi) and, with kSlope, d/dalpha — the shared-memory form of objective_along_line.
+template <bool kSlope>
+__device__ __forceinline__ void resident_line_eval(const GraphView& G, const ResView& R, double* buf2, int& flip,
+                                                   const int32_t* fids, int nf, double alpha, double& f, double& slope) {
+  const int T = blockDim.x, tid = threadIdx.x;
+  resident_terms<kSlope>(R, alpha, true);
   // ---- pass 2: factors, thread k owns factors k, k+T, ... (objective_along_line's mapping) ----
   double fs = 0.0, ss = 0.0;
-#pragma unroll 2
   for (int k = tid; k < nf; k += T) {
     const int r0 = R.frow[k] & 0x7fffffff;
     const int n = (R.frow[k + 1] & 0x7fffffff) - r0;
     const bool is_const = R.frow[k] < 0;  // Factor::eval of an assigned constant (src/Factor.cpp:110-119)
     const double c = R.fcoef[k];
     double prod = 1.0, s = 0.0;
-    if (n <= NlpfOps::kMaxArityFast) {
-      double t[NlpfOps::kMaxArityFast], dt[NlpfOps::kMaxArityFast], dir[NlpfOps::kMaxArityFast];
-#pragma unroll
-      for (int i = 0; i < NlpfOps::kMaxArityFast; ++i) {
-        if (i < n) {
-          const int lt = R.elt[r0 + i];
-          t[i] = R.tval[lt];
-          if (want_slope) {
-            dt[i] = R.tdt[lt];
-            dir[i] = (lt < R.nT) ? R.ds[R.tlv[lt]] : 0.0;
-          }
-          prod *= t[i];
-        }
-      }
-      if (want_slope) {
-#pragma unroll
-        for (int i = 0; i < NlpfOps::kMaxArityFast; ++i) {
-          if (i < n && dir[i] != 0.0) {
-            double pe = 1.0;  // getDerivative: product in slot order, own slot replaced by its derivative (1.0 when plain)
-#pragma unroll
-            for (int j = 0; j < NlpfOps::kMaxArityFast; ++j) {
-              if (j < n) pe *= (j == i) ? dt[j] : t[j];
+    switch (n) {
+      case 0: break;
+      case 1: resident_fold<1, kSlope>(R, r0, c, prod, s); break;
+      case 2: resident_fold<2, kSlope>(R, r0, c, prod, s); break;
+      case 3: resident_fold<3, kSlope>(R, r0, c, prod, s); break;
+      case 4: resident_fold<4, kSlope>(R, r0, c, prod, s); break;
+      default: {
+        for (int i = 0; i < n; ++i) prod *= R.tval[R.elt[r0 + i]];
+        if (kSlope) {
+          for (int i = 0; i < n; ++i) {
+            const double diri = R.ds[R.elv[r0 + i]];
+            if (diri != 0.0) {
+              double pe = 1.0;
+              for (int j = 0; j < n; ++j) {
+                const int lj = R.elt[r0 + j];
+                pe *= (j == i) ? R.tdt[lj] : R.tval[lj];
+              }
+              s = __fma_rn(pe * c, diri, s);
             }
-            s += (pe * c) * dir[i];
-          }
-        }
-      }
-    } else {
-      for (int i = 0; i < n; ++i) prod *= R.tval[R.elt[r0 + i]];
-      if (want_slope) {
-        for (int i = 0; i < n; ++i) {
-          const int lt = R.elt[r0 + i];
-          const double diri = (lt < R.nT) ? R.ds[R.tlv[lt]] : 0.0;
-          if (diri != 0.0) {
-            double pe = 1.0;
-            for (int j = 0; j < n; ++j) {
-              const int lj = R.elt[r0 + j];
-              pe *= (j == i) ? R.tdt[lj] : R.tval[lj];
-            }
-            s += pe * c * diri;
           }
         }
       }
@@ -199,9 +246,32 @@ __device__ __forceinline__ void resident_line_eval(const GraphView& G, const Res
     fs += fv;
     ss += s;
   }
-  grp.sum2(fs, ss);  // one __syncthreads inside: also orders this evaluation's reads of tval before the next pass 1
+  resident_sum2(buf2, flip, fs, ss);  // its barrier also orders this evaluation's reads of tval before the next pass 1
   f = fs;
   slope = ss;
+}
+
+// Per-edge partials of one factor of arity N into the scratch slice (NlpfOps::gradient's expressions).
+template <int N>
+__device__ __forceinline__ double resident_partials(const ResView& R, int r0, double c) {
+  double t[N], dt[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int lt = R.elt[r0 + i];
+    t[i] = R.tval[lt];
+    dt[i] = R.tdt[lt];
+  }
+  double prod = t[0];
+#pragma unroll
+  for (int i = 1; i < N; ++i) prod *= t[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double pe = (i == 0) ? dt[0] : t[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) pe *= (j == i) ? dt[j] : t[j];
+    R.gscr[r0 + i] = pe * c;
+  }
+  return prod;
 }
 
 // Value and full gradient at p (Factor::computeGradient of every factor + computeGradientOfSum restricted to the
@@ -211,65 +281,30 @@ template <class Sink>
 __device__ __forceinline__ double resident_gradient(const GraphView& G, const ResView& R, const int32_t* fids, int nv, int nf,
                                                     Sink sink) {
   const int T = blockDim.x, tid = threadIdx.x;
-  for (int t = tid; t < R.nT; t += 2 * T) {  // two terms per trip (see resident_line_eval)
-    const int u = t + T;
-    const bool two = u < R.nT;
-    const int ub_ = two ? u : t;
-    const int lv0 = R.tlv[t], lv1 = R.tlv[ub_];
-    const double xv0 = clamp_to_domain(R.xs[lv0], make_double2(R.lb[lv0], R.ub[lv0]));  // load_var<false>
-    const double xv1 = clamp_to_domain(R.xs[lv1], make_double2(R.lb[lv1], R.ub[lv1]));
-    const double ex0 = R.texpo[t], kk0 = R.tkonst[t], ex1 = R.texpo[ub_], kk1 = R.tkonst[ub_];
-    const bool sn0 = R.tsine[t] != 0, sn1 = R.tsine[ub_] != 0;
-    double tv0, dt0, tv1, dt1;
-    nlpf_term_grad(xv0, kk0, ex0, sn0, tv0, dt0);
-    nlpf_term_grad(xv1, kk1, ex1, sn1, tv1, dt1);
-    R.tval[t] = tv0;
-    R.tdt[t] = dt0;
-    if (two) {
-      R.tval[u] = tv1;
-      R.tdt[u] = dt1;
-    }
-  }
-  __syncthreads();
+  resident_terms<true>(R, 0.0, false);  // load_var<false>: x = clamp(p)
   double fs = 0.0;
-  for (int k = tid; k < nf; k += T) {  // NlpfOps::gradient, expression for expression
+  for (int k = tid; k < nf; k += T) {
     const int r0 = R.frow[k] & 0x7fffffff;
     const int n = (R.frow[k + 1] & 0x7fffffff) - r0;
     const bool is_const = R.frow[k] < 0;
     const double c = R.fcoef[k];
     double prod = 1.0;
-    if (n <= NlpfOps::kMaxArityFast) {
-      double t[NlpfOps::kMaxArityFast], dt[NlpfOps::kMaxArityFast];
-#pragma unroll
-      for (int i = 0; i < NlpfOps::kMaxArityFast; ++i) {
-        if (i < n) {
-          const int lt = R.elt[r0 + i];
-          t[i] = R.tval[lt];
-          dt[i] = R.tdt[lt];
-          prod *= t[i];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < NlpfOps::kMaxArityFast; ++i) {
-        if (i < n) {
+    switch (n) {
+      case 0: break;
+      case 1: prod = resident_partials<1>(R, r0, c); break;
+      case 2: prod = resident_partials<2>(R, r0, c); break;
+      case 3: prod = resident_partials<3>(R, r0, c); break;
+      case 4: prod = resident_partials<4>(R, r0, c); break;
+      default:
+        for (int i = 0; i < n; ++i) {
+          prod *= R.tval[R.elt[r0 + i]];
           double pe = 1.0;
-#pragma unroll
-          for (int j = 0; j < NlpfOps::kMaxArityFast; ++j) {
-            if (j < n) pe *= (j == i) ? dt[j] : t[j];
+          for (int j = 0; j < n; ++j) {
+            const int lj = R.elt[r0 + j];
+            pe *= (j == i) ? R.tdt[lj] : R.tval[lj];
           }
           R.gscr[r0 + i] = pe * c;
         }
-      }
-    } else {
-      for (int i = 0; i < n; ++i) {
-        prod *= R.tval[R.elt[r0 + i]];
-        double pe = 1.0;
-        for (int j = 0; j < n; ++j) {
-          const int lj = R.elt[r0 + j];
-          pe *= (j == i) ? R.tdt[lj] : R.tval[lj];
-        }
-        R.gscr[r0 + i] = pe * c;
-      }
     }
     double fv = prod * c;
     if (is_const) fv = G.fconst_val[fids[k]];
@@ -294,11 +329,12 @@ __device__ __forceinline__ double resident_gradient(const GraphView& G, const Re
 }
 
 // grid = number of resident-class problems, one CTA each; dynamic shared memory = the largest layout of the class.
-template <int kThreads>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kThreads, int kMinCtas>
+__global__ void __launch_bounds__(kThreads, kMinCtas)
     solve_nlpf_resident_kernel(GraphView G, BatchView B, const int32_t* order, int count, int maxiters, double ftol) {
   extern __shared__ __align__(16) unsigned char res_smem[];
   __shared__ double scratch[260];
+  __shared__ double buf2[128];
   __shared__ int32_t wtot[32];
   __shared__ int32_t nfz_counter;
   if ((int)blockIdx.x >= count) return;
@@ -310,6 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int32_t stamp = pidx;
   const int T = blockDim.x, tid = threadIdx.x;
   Block grp(scratch);
+  int flip2 = 0;
 
   const ResLayout L = res_layout(nv, nf, P.nE, P.nT, P.nFz);
   ResView R;
@@ -320,13 +357,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   R.fcoef = reinterpret_cast<double*>(res_smem + L.fcoef);
   R.toff = reinterpret_cast<int32_t*>(res_smem + L.toff); R.frow = reinterpret_cast<int32_t*>(res_smem + L.frow);
   R.tlv = reinterpret_cast<uint16_t*>(res_smem + L.tlv); R.elt = reinterpret_cast<uint16_t*>(res_smem + L.elt);
-  R.vinc = reinterpret_cast<uint16_t*>(res_smem + L.vinc);
+  R.elv = reinterpret_cast<uint16_t*>(res_smem + L.elv);
   R.gscr = B.gscr + P.goff;
-  R.tsine = res_smem + L.tsine;
+  uint16_t* vinc = B.gvinc + P.goff;
+  R.vinc = vinc;
   R.nT = P.nT;
 
   // ---- claim (CGD.cpp:33: quickAssignVals of the start point) + flatten ----
-  if (tid == 0) nfz_counter = 0;
+  if (tid == 0) {
+    nfz_counter = 0;
+    R.ds[nv] = 0.0;  // the "frozen variable" direction slot
+  }
   for (int j = tid; j < nv; j += T) {
     const int32_t vid = vids[j];
     const double xv = (B.x0 != nullptr) ? B.x0[P.var_off + j] : G.xbd[vid].x;
@@ -335,7 +376,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     G.vloc[vid] = j;
     const double2 dm = __ldg(&G.dom[vid]);
     R.xs[j] = xv; R.ds[j] = 0.0; R.lb[j] = dm.x; R.ub[j] = dm.y;
-    R.toff[j] = __ldg(&G.tvrow[vid + 1]) - __ldg(&G.tvrow[vid]);
+    int ns = 0, np = 0;  // sine-class / polynomial-class terms of this variable, packed (each total < 65536)
+    for (int32_t g = __ldg(&G.tvrow[vid]); g < __ldg(&G.tvrow[vid + 1]); ++g) {
+      if (__ldg(&G.t_sine[g])) ++ns; else ++np;
+    }
+    R.toff[j] = ns | (np << 16);
   }
   for (int k = tid; k < nf; k += T) {
     const int32_t fid = fids[k];
@@ -347,16 +392,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   block_exclusive_scan(R.toff, nv, wtot);
   block_exclusive_scan(R.frow, nf, wtot);
-  // term descriptors of the component's own variables
+  const int nS = R.toff[nv] & 0xffff;
+  R.nS = nS;
+  // term descriptors of the component's own variables: sine class in [0, nS), the rest in [nS, nT)
   for (int j = tid; j < nv; j += T) {
     const int32_t vid = vids[j];
-    const int32_t g0 = __ldg(&G.tvrow[vid]);
-    const int t0 = R.toff[j], n = R.toff[j + 1] - t0;
-    for (int u = 0; u < n; ++u) {
-      R.tlv[t0 + u] = (uint16_t)j;
-      R.texpo[t0 + u] = __ldg(&G.t_expo[g0 + u]);
-      R.tkonst[t0 + u] = __ldg(&G.t_konst[g0 + u]);
-      R.tsine[t0 + u] = __ldg(&G.t_sine[g0 + u]);
+    int a = R.toff[j] & 0xffff, b = nS + (int)((uint32_t)R.toff[j] >> 16);
+    for (int32_t g = __ldg(&G.tvrow[vid]); g < __ldg(&G.tvrow[vid + 1]); ++g) {
+      const int slot = __ldg(&G.t_sine[g]) ? a++ : b++;
+      R.tlv[slot] = (uint16_t)j;
+      R.texpo[slot] = __ldg(&G.t_expo[g]);
+      R.tkonst[slot] = __ldg(&G.t_konst[g]);
     }
   }
   // edges: own variables -> their term; frozen variables -> a constant term evaluated here, once
@@ -372,17 +418,23 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int slot = P.nT + atomicAdd(&nfz_counter, 1);
         R.tval[slot] = nlpf_term_value(xb.x, __ldg(&G.konst[e]), __ldg(&G.expo[e]), __ldg(&G.sine[e]) != 0);
         R.tdt[slot] = 0.0;
-        R.tlv[slot] = 0;
         R.elt[r0 + i] = (uint16_t)slot;
+        R.elv[r0 + i] = (uint16_t)nv;
       } else {
         const int lv = G.vloc[vid];
-        R.elt[r0 + i] = (uint16_t)(R.toff[lv] + (__ldg(&G.eterm[e]) - __ldg(&G.tvrow[vid])));
+        const int32_t g0 = __ldg(&G.tvrow[vid]), gt = __ldg(&G.eterm[e]);
+        const bool sn = __ldg(&G.t_sine[gt]) != 0;
+        int rank = 0;  // terms of the same class that precede this one in the variable's list
+        for (int32_t g = g0; g < gt; ++g) rank += ((__ldg(&G.t_sine[g]) != 0) == sn);
+        const int base = sn ? (R.toff[lv] & 0xffff) : nS + (int)((uint32_t)R.toff[lv] >> 16);
+        R.elt[r0 + i] = (uint16_t)(base + rank);
+        R.elv[r0 + i] = (uint16_t)lv;
       }
     }
   }
   __syncthreads();
   // variable-major incidence of the component (local edge ids, ascending factor id = the order of the global
-  // incidence list): toff is free now and becomes its offsets
+  // incidence list) into the problem's scratch slice: toff is free now and becomes its offsets
   for (int j = tid; j < nv; j += T) {
     const int32_t vid = vids[j];
     int cnt = 0;
@@ -399,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int32_t e = __ldg(&G.vedge[r]);
       const int32_t f = __ldg(&G.efac[e]);
       if (G.fstamp[f] != stamp) continue;
-      R.vinc[pos++] = (uint16_t)(R.frow[G.floc[f]] + (e - __ldg(&G.rowptr[f])));
+      vinc[pos++] = (uint16_t)(R.frow[G.floc[f]] + (e - __ldg(&G.rowptr[f])));
     }
   }
   __syncthreads();
@@ -431,7 +483,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       m.on_init(fs);
     } else {
       double f, sl;
-      resident_line_eval(G, R, grp, fids, nf, m.alpha, m.req == REQ_VALUE_SLOPE, f, sl);
+      if (m.req == REQ_VALUE_SLOPE)
+        resident_line_eval<true>(G, R, buf2, flip2, fids, nf, m.alpha, f, sl);
+      else
+        resident_line_eval<false>(G, R, buf2, flip2, fids, nf, m.alpha, f, sl);
       m.on_eval(f, sl);
     }
 

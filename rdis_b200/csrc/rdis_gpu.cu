@@ -171,7 +171,9 @@ struct rdisgpu_batch {
   // bundle-adjustment block fast paths (ba_block_kernels.cuh)
   int n_pt_warps = 0, n_cam = 0, cam_nf_max = 0;
   int cam_C = 0, cam_T = 0;  // chosen at the first solve (needs the occupancy query)
+  DevBuf<uint16_t> res_gvinc;  // ... and their variable-major incidence lists
   DevBuf<double> res_gscr;  // resident NLPF class: per-edge partials, one slice per problem
+  int res_small_smem = 0;
   int res_smem = 0;  // dynamic shared memory of the resident NLPF class (largest layout in the batch)
   int last_launches = 0;
   bool solved = false;
@@ -977,18 +979,19 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
     }
   }
   // NonlinearProductFactor components that fit one CTA's shared memory: the resident kernel (nlpf_resident.cuh)
-  std::vector<int32_t> res_list;
+  std::vector<int32_t> res_list, res_small_list;
   int64_t res_edges = 0;
-  b->res_smem = 0;
+  b->res_smem = b->res_small_smem = 0;
   if (ctx->kind == KIND_NLPF && !ctx->generic_only) {
     if (ctx->res_smem_cap < 0) {
       int optin = 0;
       cudaFuncAttributes fa;
       CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-      CK(cudaFuncGetAttributes(&fa, solve_nlpf_resident_kernel<kResThreads>));
+      CK(cudaFuncGetAttributes(&fa, solve_nlpf_resident_kernel<kResThreads, 1>));
       ctx->res_smem_cap = std::max(0, optin - (int)fa.sharedSizeBytes);
-      CK(cudaFuncSetAttribute(solve_nlpf_resident_kernel<kResThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_smem_cap));
-      CK(cudaFuncSetAttribute(solve_nlpf_resident_kernel<kResThreadsExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_smem_cap));
+      CK(cudaFuncSetAttribute(solve_nlpf_resident_kernel<kResThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_smem_cap));
+      CK(cudaFuncSetAttribute(solve_nlpf_resident_kernel<kResThreadsExact, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_smem_cap));
+      CK(cudaFuncSetAttribute(solve_nlpf_resident_kernel<kResThreadsSmall, kResSmallCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmallSmem));
     }
     for (int64_t p = 0; p < nprobs; ++p) {
       ProblemDesc& D = b->h_probs[p];
@@ -1012,8 +1015,13 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
       D.nE = (int32_t)nE; D.nT = (int32_t)nT; D.nFz = (int32_t)nFz; D.goff = (int32_t)res_edges;
       res_edges += nE;
       h_probs[p] = D;
-      b->res_smem = std::max(b->res_smem, L.total);
-      res_list.push_back((int32_t)p);
+      if (ctx->res_threads != kResThreadsExact && D.nf <= kResSmallFactors && L.total <= kResSmallSmem) {
+        b->res_small_smem = std::max(b->res_small_smem, L.total);
+        res_small_list.push_back((int32_t)p);
+      } else {
+        b->res_smem = std::max(b->res_smem, L.total);
+        res_list.push_back((int32_t)p);
+      }
       fast[p] = 3;
     }
   }
@@ -1041,10 +1049,17 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
     b->classes.push_back({1, 64 << t, (int64_t)b->h_order.size(), (int64_t)block_lists[t].size()});
     b->h_order.insert(b->h_order.end(), block_lists[t].begin(), block_lists[t].end());
   }
-  if (!res_list.empty()) {
+  if (res_edges > 0) {
     CK(b->res_gscr.ensure((size_t)res_edges));
+    CK(b->res_gvinc.ensure((size_t)res_edges));
+  }
+  if (!res_list.empty()) {
     b->classes.push_back({3, ctx->res_threads, (int64_t)b->h_order.size(), (int64_t)res_list.size()});
     b->h_order.insert(b->h_order.end(), res_list.begin(), res_list.end());
+  }
+  if (!res_small_list.empty()) {
+    b->classes.push_back({3, kResThreadsSmall, (int64_t)b->h_order.size(), (int64_t)res_small_list.size()});
+    b->h_order.insert(b->h_order.end(), res_small_list.begin(), res_small_list.end());
   }
   if (!grid_list.empty()) {
     b->classes.push_back({2, 256, (int64_t)b->h_order.size(), (int64_t)grid_list.size()});
@@ -1126,6 +1141,7 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
   bv.xout = b->xout.p;
   bv.res = b->res.p;
   bv.gscr = b->res_gscr.p;
+  bv.gvinc = b->res_gvinc.p;
   GraphView gv = ctx->gv;
   int launches = 0;
   if (b->n_pt_warps > 0) {
@@ -1210,10 +1226,12 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
         solve_block_kernel<BaOps><<<cnt, c.param, 0, s>>>(gv, bv, ord, cnt, maxiters, ftol);
       ++launches;
     } else if (c.kind == 3) {
-      if (c.param == kResThreadsExact)
-        solve_nlpf_resident_kernel<kResThreadsExact><<<cnt, kResThreadsExact, (size_t)b->res_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
+      if (c.param == kResThreadsSmall)
+        solve_nlpf_resident_kernel<kResThreadsSmall, kResSmallCtas><<<cnt, kResThreadsSmall, (size_t)b->res_small_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
+      else if (c.param == kResThreadsExact)
+        solve_nlpf_resident_kernel<kResThreadsExact, 1><<<cnt, kResThreadsExact, (size_t)b->res_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
       else
-        solve_nlpf_resident_kernel<kResThreads><<<cnt, kResThreads, (size_t)b->res_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
+        solve_nlpf_resident_kernel<kResThreads, 1><<<cnt, kResThreads, (size_t)b->res_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
       ++launches;
     } else {
       const int threads = 256;
@@ -1419,6 +1437,7 @@ int rdisgpu_solve_lm_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_of
   bv.xout = b->xout.p;
   bv.res = b->res.p;
   bv.gscr = nullptr;
+  bv.gvinc = nullptr;
   LmView lv;
   lv.vloc = ctx->lm_vloc.p;
   lv.scratch = ctx->lm_scratch.p;
@@ -1535,7 +1554,7 @@ int rdisgpu_batch_resident_info(const rdisgpu_batch* b, int32_t out[2]) {
   out[0] = 0;
   for (const auto& c : b->classes)
     if (c.kind == 3) out[0] += (int32_t)c.count;
-  out[1] = b->res_smem;
+  out[1] = std::max(b->res_smem, b->res_small_smem);
   return RDISGPU_OK;
 }
 

@@ -51,7 +51,8 @@ struct BatchView {
   const double* x0;  // nullable
   double* xout;
   ResultRec* res;
-  double* gscr;  // resident NLPF class: per-edge partial scratch, one slice per problem (nullable)
+  double* gscr;     // resident NLPF class: per-edge partial scratch, one slice per problem (nullable)
+  uint16_t* gvinc;  // ... and the variable-major incidence lists, same slices
 };
 
 // ------------------------------------------------------------------------------------------
