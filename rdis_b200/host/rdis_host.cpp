@@ -431,6 +431,42 @@ void ComponentBatcher::createChildren(const OptimizableFunction& func, const Var
   });
 }
 
+void ComponentBatcher::createChildrenOnDevice(OptimizableFunction& func, const VariableIDVec& componentVars,
+                                              std::vector<ChildComponent>& children) {
+  children.clear();
+  if (!func.device()) throw std::logic_error("createChildrenOnDevice before init");
+  func.flushAssignments();  // assigned-constant factors carry no edges: the device overlay must be current
+  const VariablePtrVec& vars = func.getVariables();
+  const int64_t V = (int64_t)vars.size(), F = (int64_t)func.getFactors().size();
+  std::vector<uint8_t> assigned((size_t)V, 1);  // everything outside the component counts as removed
+  for (VariableID vid : componentVars)
+    if (!vars[(size_t)vid]->isAssigned()) assigned[(size_t)vid] = 0;
+  std::vector<int32_t> vlabel((size_t)V), flabel((size_t)std::max<int64_t>(F, 1));
+  int32_t ncomp = 0;
+  if (rdisgpu_components(func.device(), assigned.data(), vlabel.data(), flabel.data(), &ncomp, nullptr) != RDISGPU_OK)
+    throw std::runtime_error(std::string("rdisgpu_components: ") + rdisgpu_last_error(func.device()));
+  // label = smallest variable id of the component: children in ascending label order, then the reference's size order
+  std::vector<int32_t> slot((size_t)V, -1);
+  children.reserve((size_t)ncomp);
+  for (int64_t v = 0; v < V; ++v) {
+    const int32_t l = vlabel[(size_t)v];
+    if (l < 0) continue;
+    if (slot[(size_t)l] < 0) {
+      slot[(size_t)l] = (int32_t)children.size();
+      children.emplace_back();
+    }
+    children[(size_t)slot[(size_t)l]].vars.push_back(v);  // ascending v: already sorted
+  }
+  for (int64_t f = 0; f < F; ++f) {
+    const int32_t l = flabel[(size_t)f];
+    if (l >= 0) children[(size_t)slot[(size_t)l]].factors.push_back(f);
+  }
+  std::stable_sort(children.begin(), children.end(), [](const ChildComponent& a, const ChildComponent& b) {
+    if (a.vars.size() != b.vars.size()) return a.vars.size() < b.vars.size();
+    return a.vars.front() < b.vars.front();
+  });
+}
+
 void ComponentBatcher::leafProblem(OptimizableFunction& func, const ChildComponent& child, const NumericVec& fallback,
                                    ComponentProblem& out) {
   VariablePtrVec& vars = func.getVariables();

@@ -323,6 +323,10 @@ class ComponentBatcher {
  public:
   static void createChildren(const OptimizableFunction& func, const VariableIDVec& componentVars,
                              std::vector<ChildComponent>& children);
+  // Same children, labelled on the GPU (rdisgpu_components: min-label propagation over the device CSR) — for
+  // million-variable graphs, where the host union-find over heap objects is the slow part.  Needs init().
+  static void createChildrenOnDevice(OptimizableFunction& func, const VariableIDVec& componentVars,
+                                     std::vector<ChildComponent>& children);
   // The subspace problem of optimising ALL variables of a child (a leaf visit):
   // gdfs = the child's factors whose other variables are all assigned (src/RDISOptimizer.cpp:1049-1059),
   // start values = current values of the variables that are assigned, else `fallback[vid]`.

@@ -2,6 +2,7 @@
 // Reads a problem written by tests/test_host_adapter.py (flat little-endian arrays), builds the
 // reference-shaped object graph (Variable / Factor / OptimizableFunction), and runs one of:
 //   children <file>            ComponentBatcher::createChildren over the unassigned variables (no GPU needed)
+//   children_gpu <file>        ComponentBatcher::createChildrenOnDevice: the same listing through rdisgpu_components
 //   wave <file> <maxiters>     one sibling wave through CudaSubspaceOptimizer::optimizeBatch
 //   single <file> <maxiters>   the same wave, one CudaSubspaceOptimizer::optimize call per child
 //                              (the reference's sibling loop, src/RDISOptimizer.cpp:291-314)
@@ -161,8 +162,13 @@ int main(int argc, char** argv) {
     const std::string mode = argv[1];
     assign_flagged(L);
     std::vector<ChildComponent> kids;
-    ComponentBatcher::createChildren(*L.fn, unassigned(L), kids);
-    if (mode == "children") {
+    if (mode == "children_gpu") {  // children_gpu <file>: the same listing, labelled by rdisgpu_components
+      L.fn->init(0);
+      ComponentBatcher::createChildrenOnDevice(*L.fn, unassigned(L), kids);
+    } else {
+      ComponentBatcher::createChildren(*L.fn, unassigned(L), kids);
+    }
+    if (mode == "children" || mode == "children_gpu") {
       std::printf("children %zu\n", kids.size());
       for (const ChildComponent& c : kids) {
         std::printf("%zu %zu |", c.vars.size(), c.factors.size());

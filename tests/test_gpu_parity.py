@@ -708,6 +708,8 @@ def test_nlpf_resident_kernel_matches_generic_path(gpu, oracle_mod):
     cases = []
     tree = P.sinusoid(9, 2, 4)
     cases.append(("sinusoid h=9 subtrees", tree, P.sinusoid_subtree_problems(tree, 3), P.random_start(tree, 11), ()))
+    big = P.sinusoid(12, 2, 4)   # components of BASELINE config 4's shape: 1023 variables / 4092 factors, 3 frozen ancestors
+    cases.append(("config-4-shaped components", big, P.sinusoid_subtree_problems(big, 3).subset([0, 5]), P.random_start(big, 4), ()))
     spec, probs, x0 = _two_group_nlpf(17)
     cases.append(("two-group general terms", spec, ProblemSet.from_lists(probs), x0, ()))
     cases.append(("two-group + assigned constants", spec, ProblemSet.from_lists(probs), x0, (3, 40, 41, 200)))

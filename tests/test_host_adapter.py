@@ -117,6 +117,27 @@ def test_children_membership_is_exact_cpu(driver, tmp_path):
     assert len(kids) == 40 and all(len(v) == 3 for v, _ in kids)
 
 
+@pytest.mark.gpu
+def test_children_membership_on_device_is_exact(driver, tmp_path):
+    """ComponentBatcher::createChildrenOnDevice (rdisgpu_components under the C++ host layer) lists exactly the
+    children the host union-find lists — same sets, same order — on the cuts of the CPU test."""
+    from rdis_b200 import problems as P
+    spec = P.ba_synthetic(ncams=5, npts=40, nobs=150, seed=3)
+    sp2 = P.sinusoid(6, 2, 4)
+    cases = []
+    a = np.zeros(spec["V"], np.uint8); a[:9 * 5] = 1; cases.append((spec, a))
+    a = np.zeros(spec["V"], np.uint8); a[9 * 5:] = 1; cases.append((spec, a))
+    a = np.zeros(spec["V"], np.uint8); a[:9 * 2] = 1; a[9 * 5:9 * 5 + 30] = 1; cases.append((spec, a))
+    a = np.zeros(sp2["V"], np.uint8); a[:7] = 1; cases.append((sp2, a))
+    a = np.zeros(sp2["V"], np.uint8); a[::3] = 1; cases.append((sp2, a))
+    for i, (sp, a) in enumerate(cases):
+        path = str(tmp_path / ("p%d.bin" % i))
+        write_problem(path, sp, np.zeros(sp["V"]), a)
+        cpu = parse_children(subprocess.run([driver, "children", path], capture_output=True, text=True, check=True).stdout)
+        gpu = parse_children(subprocess.run([driver, "children_gpu", path], capture_output=True, text=True, check=True).stdout)
+        assert gpu == cpu == reference_children(sp, a), "case %d: device membership differs" % i
+
+
 def _parse_wave(text):
     lines = text.strip().splitlines()
     n = int(lines[0].split()[1]); total = float(lines[0].split()[3])
