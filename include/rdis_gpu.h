@@ -203,6 +203,19 @@ RDISGPU_API int rdisgpu_batch_last_launches(const rdisgpu_batch* b);
 RDISGPU_API int rdisgpu_components(rdisgpu_ctx* ctx, const uint8_t* assigned, int32_t* var_label, int32_t* fac_label,
                                    int32_t* n_components, int32_t* n_rounds);
 
+/* ---- interval bounds for branch & bound ------------------------------------ */
+/* Factor::computeBounds (src/Factor.cpp:122-139) for every listed factor and their interval sum as
+ * OptimizableFunction::computeBounds folds it (src/OptimizableFunction.cpp:186-216; the caller applies that function's
+ * assigned-key filter by choosing the list).  A variable with assigned[v] != 0 enters as the point [x, x] (device
+ * state, rdisgpu_set_x), any other as its domain hull [lb, ub]; a factor whose variables are all assigned, or that is
+ * an assigned constant, contributes its point value.  NonlinearProductFactor::computeFactorBounds
+ * (src/NonlinearProductFactor.cpp:120-145) and BundleAdjustmentFactor::evalFactor(IntervalVec)
+ * (src/bundleadjust/BundleAdjustmentFactor.cpp:104-157,186-232) over the reference's no-rounding / no-checking
+ * Boost.Interval policy (src/common.h:43-60).  fid NULL = all factors; lower / upper (nf doubles, nullable) receive
+ * the per-factor bounds, sum (nullable) = {lower, upper} of the list, accumulated in list order. */
+RDISGPU_API int rdisgpu_bounds(rdisgpu_ctx* ctx, const uint8_t* assigned, int64_t nf, const int64_t* fid, double* lower,
+                               double* upper, double sum[2]);
+
 /* ---- introspection (tests / bench) ------------------------------------------------------ */
 RDISGPU_API int64_t rdisgpu_num_vars(const rdisgpu_ctx* ctx);
 RDISGPU_API int64_t rdisgpu_num_factors(const rdisgpu_ctx* ctx);

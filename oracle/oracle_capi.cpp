@@ -13,6 +13,7 @@
 
 #include "rdis_oracle.hpp"
 #include "lm_oracle.hpp"
+#include "interval_oracle.hpp"
 
 using namespace oracle;
 
@@ -484,6 +485,36 @@ double orc_eval(void* h, int64_t nf, const int64_t* fid, double* per_factor, int
     }
   }
   return fn.evalFactors(fs, use_cache != 0);
+}
+
+// Factor::computeBounds per listed factor (nullptr = all) and OptimizableFunction::computeBounds' interval sum over the
+// list.  point[v] != 0: the variable enters as its current value (it must be assigned), otherwise as its domain hull —
+// the caller expresses "assigned and not in vidsToIgnore" through this mask.
+void orc_bounds(void* h, const uint8_t* point, int64_t nf, const int64_t* fid, double* lower, double* upper, double* sum2) {
+  OptimizableFunction& fn = *H(h)->fn;
+  auto is_point = [&](const Variable& v) { return point[v.getID()] != 0; };
+  Interval total(0.0);  // semiring Product identity, src/OptimizableFunction.cpp:192
+  const int64_t n = fid ? nf : (int64_t)fn.factors.size();
+  for (int64_t i = 0; i < n; ++i) {
+    Factor* f = fn.factors[fid ? fid[i] : i];
+    bool all_points = true;
+    for (const Variable* v : f->getVariables()) all_points = all_points && is_point(*v);
+    Interval b;
+    if (f->isAssigned() || all_points) {
+      b = Interval(f->isAssigned() ? f->eval(fn.counters) : f->evalNoCache());  // src/Factor.cpp:128
+    } else if (fn.kind == OptimizableFunction::KIND_NLPF) {
+      b = nlpf_factor_bounds(*static_cast<NonlinearProductFactor*>(f), is_point);
+    } else {
+      b = ba_factor_bounds(*static_cast<BundleAdjustmentFactor*>(f), is_point);
+    }
+    if (lower) lower[i] = b.lower();
+    if (upper) upper[i] = b.upper();
+    total = total + b;
+  }
+  if (sum2) {
+    sum2[0] = total.lower();
+    sum2[1] = total.upper();
+  }
 }
 
 // computeGradientOfSum restricted to `vid` (SubfunctionFD::df without the assign).

@@ -68,6 +68,7 @@ def _load(path):
     lib.orc_get_x.argtypes = [vp, C.c_int64, vp, _f64p]
     lib.orc_unassign.argtypes = [vp, C.c_int64, vp]
     lib.orc_set_factor_const.argtypes = [vp, C.c_int64, _i64p, _f64p, _u8p]
+    lib.orc_bounds.argtypes = [vp, _u8p, C.c_int64, vp, vp, vp, _f64p]
     lib.orc_eval.restype = C.c_double
     lib.orc_eval.argtypes = [vp, C.c_int64, vp, vp, C.c_int]
     lib.orc_grad.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, _f64p]
@@ -223,6 +224,15 @@ class OracleFunction:
     def set_factor_const(self, fid, val, on):
         self._lib.orc_set_factor_const(self._h, len(fid), np.ascontiguousarray(fid, np.int64),
                                        np.ascontiguousarray(val, np.float64), np.ascontiguousarray(on, np.uint8))
+
+    def bounds(self, point, fid=None):
+        """Factor::computeBounds per factor + the interval sum: (lower, upper, (sum_lower, sum_upper))."""
+        pt = np.ascontiguousarray(point, np.uint8)
+        f = _opt(fid, np.int64)
+        n = self.F if fid is None else len(f)
+        lo = np.empty(n); hi = np.empty(n); tot = np.zeros(2)
+        self._lib.orc_bounds(self._h, pt, n, _ptr(f), _ptr(lo), _ptr(hi), tot)
+        return lo, hi, (float(tot[0]), float(tot[1]))
 
     # ---- hot path -----------------------------------------------------------------
     def eval(self, fid=None, per_factor=False, use_cache=True):

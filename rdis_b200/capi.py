@@ -21,7 +21,7 @@ EXPORTS = (
     "rdisgpu_set_x", "rdisgpu_get_x", "rdisgpu_set_factor_const",
     "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_eval_device", "rdisgpu_grad_device", "rdisgpu_factor_grad",
     "rdisgpu_solve_cgd", "rdisgpu_solve_cgd_csr", "rdisgpu_solve_lm_csr", "rdisgpu_batch_create", "rdisgpu_batch_create_csr", "rdisgpu_batch_info", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
-    "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches", "rdisgpu_batch_resident_info", "rdisgpu_components",
+    "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches", "rdisgpu_batch_resident_info", "rdisgpu_components", "rdisgpu_bounds",
     "rdisgpu_num_vars", "rdisgpu_num_factors", "rdisgpu_device_state", "rdisgpu_launch_count", "rdisgpu_version",
 )
 
@@ -71,6 +71,7 @@ def load_library(path=LIB_PATH):
         "rdisgpu_solve_cgd_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, C.c_int, dbl, vp, vp, vp, vp, vp, vp, vp]),
         "rdisgpu_solve_lm_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
         "rdisgpu_components": (C.c_int, [vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]),
+        "rdisgpu_bounds": (C.c_int, [vp, vp, i64, vp, vp, vp, vp]),
         "rdisgpu_batch_info": (C.c_int, [vp, vp]),
         "rdisgpu_batch_resident_info": (C.c_int, [vp, vp]),
         "rdisgpu_batch_solve_cgd": (C.c_int, [vp, vp, C.c_int, dbl]),
@@ -275,6 +276,17 @@ class Context:
         rows = np.zeros((len(f), arity_max))
         self._ck(self._lib.rdisgpu_factor_grad(self._h, len(f), _p(f), arity_max, _p(rows)))
         return rows
+
+    # ---- interval bounds -------------------------------------------------------------
+    def bounds(self, assigned, fids=None):
+        """rdisgpu_bounds: (lower[nf], upper[nf], (sum_lower, sum_upper)) of the listed factors (None = all)."""
+        a = _arr(assigned, np.uint8)
+        assert len(a) == self.V
+        f = None if fids is None else _arr(fids, np.int64)
+        n = self.F if f is None else len(f)
+        lo = np.empty(n); hi = np.empty(n); tot = np.zeros(2)
+        self._ck(self._lib.rdisgpu_bounds(self._h, _p(a), n, None if f is None else _p(f), _p(lo), _p(hi), _p(tot)))
+        return lo, hi, (float(tot[0]), float(tot[1]))
 
     # ---- component membership ----------------------------------------------------------
     def components(self, assigned):

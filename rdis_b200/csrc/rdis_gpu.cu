@@ -20,6 +20,7 @@
 #include "ba_sweep.cuh"
 #include "components.cuh"
 #include "nlpf_resident.cuh"
+#include "bounds_kernels.cuh"
 
 using namespace rdisgpu;
 
@@ -1530,6 +1531,53 @@ int rdisgpu_components(rdisgpu_ctx* ctx, const uint8_t* assigned, int32_t* var_l
     *n_components = n;
   }
   if (n_rounds) *n_rounds = rounds + 1;
+  return RDISGPU_OK;
+}
+
+int rdisgpu_bounds(rdisgpu_ctx* ctx, const uint8_t* assigned, int64_t nf, const int64_t* fid, double* lower, double* upper,
+                   double sum[2]) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "bounds before finalize");
+  if (!assigned) return ctx->fail(RDISGPU_ERR_ARG, "bounds: null argument");
+  if (!fid) nf = ctx->F;
+  if (nf < 0) return ctx->fail(RDISGPU_ERR_ARG, "bounds: bad argument");
+  if (sum) sum[0] = sum[1] = 0.0;  // semiring Product identity (MinSum: +, 0), src/OptimizableFunction.cpp:192
+  if (nf == 0) return RDISGPU_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (fid) {
+    int rc = upload_fids(ctx, nf, fid, ctx->s_i32a);
+    if (rc) return rc;
+  }
+  CK(ctx->cc_assigned.ensure((size_t)ctx->V));
+  CK(cudaMemcpyAsync(ctx->cc_assigned.p, assigned, (size_t)ctx->V, cudaMemcpyHostToDevice, s));
+  CK(ctx->s_f64a.ensure((size_t)nf));
+  CK(ctx->s_f64b.ensure((size_t)nf));
+  const int threads = 128;
+  const int blocks = (int)std::min<int64_t>((nf + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
+  if (ctx->kind == KIND_NLPF)
+    factor_bounds_kernel<NlpfOps><<<blocks, threads, 0, s>>>(ctx->gv, ctx->cc_assigned.p, fid ? ctx->s_i32a.p : nullptr, nf, ctx->s_f64a.p, ctx->s_f64b.p);
+  else
+    factor_bounds_kernel<BaOps><<<blocks, threads, 0, s>>>(ctx->gv, ctx->cc_assigned.p, fid ? ctx->s_i32a.p : nullptr, nf, ctx->s_f64a.p, ctx->s_f64b.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  std::vector<double> lo_tmp, hi_tmp;
+  double* lo = lower;
+  double* hi = upper;
+  if (!lo) { lo_tmp.resize((size_t)nf); lo = lo_tmp.data(); }
+  if (!hi) { hi_tmp.resize((size_t)nf); hi = hi_tmp.data(); }
+  CK(cudaMemcpyAsync(lo, ctx->s_f64a.p, (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hi, ctx->s_f64b.p, (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (sum) {  // bounds = Product(bounds, fb), factor by factor in list order (OptimizableFunction.cpp:194-211)
+    double a = 0.0, b = 0.0;
+    for (int64_t k = 0; k < nf; ++k) {
+      a += lo[k];
+      b += hi[k];
+    }
+    sum[0] = a;
+    sum[1] = b;
+  }
   return RDISGPU_OK;
 }
 

@@ -243,6 +243,22 @@ void OptimizableFunction::computeGradient(const FactorPtrVec& facs, const Variab
         "rdisgpu_grad");
 }
 
+NumericInterval OptimizableFunction::computeBounds(const FactorPtrVec& fctrs, VariableID assignedVID) {
+  NumericInterval out{0.0, 0.0};  // semiring Product identity (MinSum), src/OptimizableFunction.cpp:192
+  std::vector<int64_t> fid;
+  for (const Factor* f : fctrs)  // :196-213
+    if (assignedVID < 0 || (f->isAssigned() && f->getAssignedKey() == assignedVID) || !f->isAssigned()) fid.push_back(f->getID());
+  if (fid.empty()) return out;
+  flushAssignments();
+  std::vector<uint8_t> assigned(variables.size());
+  for (size_t v = 0; v < variables.size(); ++v) assigned[v] = variables[v]->isAssigned() ? 1 : 0;
+  double sum[2] = {0.0, 0.0};
+  check(rdisgpu_bounds(ctx, assigned.data(), (int64_t)fid.size(), fid.data(), nullptr, nullptr, sum), "rdisgpu_bounds");
+  out.lo = sum[0];
+  out.hi = sum[1];
+  return out;
+}
+
 // ------------------------------------------------------------------------------------------
 // SubspaceOptimizer
 // ------------------------------------------------------------------------------------------

@@ -45,6 +45,11 @@ typedef long long int VariableCount;
 typedef long long int VariableID;
 typedef long long int FactorID;
 typedef std::vector<Numeric> NumericVec;
+struct NumericInterval {  // boost::numeric::interval<Numeric> as the callers use it: lower() / upper()
+  Numeric lo, hi;
+  Numeric lower() const { return lo; }
+  Numeric upper() const { return hi; }
+};
 typedef std::vector<VariableID> VariableIDVec;
 typedef std::vector<FactorID> FactorIDVec;
 
@@ -224,6 +229,11 @@ class OptimizableFunction {
   // gradient of sum_{f in facs} f restricted to `vars` (computeGradient + the scatter of
   // SubfunctionFD::df, src/OptimizableFunction.cpp:234-262, CGDSubspaceOptimizer.cpp:135-157)
   virtual void computeGradient(const FactorPtrVec& facs, const VariablePtrVec& vars, NumericVec& gradient);
+  // Interval bounds of the sum of `fctrs` for branch & bound (src/OptimizableFunction.cpp:181-216): factors that are
+  // unassigned, or assigned under the key `assignedVID` (any factor when assignedVID < 0), each bounded by
+  // Factor::computeBounds (assigned variables as points, the rest as their domain hull) — through rdisgpu_bounds.
+  virtual NumericInterval computeBounds(const FactorPtrVec& fctrs, VariableID assignedVID = -1);
+  NumericInterval computeBounds() { return computeBounds(factors, -1); }
 
   // hook the reference calls after every Variable::assign made by a subspace optimizer (no-op there,
   // src/OptimizableFunction.h:65-69); here the host->device mirroring is driven by Variable::assign itself

@@ -219,6 +219,10 @@ int main(int argc, char** argv) {
           return 1;
         }
     std::printf("eval_all %.17g\n", L.fn->eval());
+    {  // interval bounds through the plugin surface: everything assigned -> the point value
+      const NumericInterval b = L.fn->computeBounds();
+      std::printf("bounds_all %.17g %.17g\n", b.lower(), b.upper());
+    }
     // gradient of everything w.r.t. the first problem's variables, through the plugin surface
     if (!probs.empty()) {
       NumericVec g;

@@ -177,6 +177,8 @@ def test_host_adapter_wave_matches_ctypes_path_and_oracle(driver, oracle_mod, tm
         assert fval == r["f_end"][k] and dfv == r["f_end"][k] - r["f_init"][k]
         assert [x[int(v)] for v in vids] == r["x"][ps.var_off[k]:ps.var_off[k + 1]].tolist()
     assert abs(rest_w["eval_all"][0] - ctx.eval()) <= 1e-12 * abs(ctx.eval())
+    # OptimizableFunction::computeBounds through the plugin surface: every variable assigned -> the point value
+    assert abs(rest_w["bounds_all"][0] - ctx.eval()) <= 1e-12 * abs(ctx.eval()) and rest_w["bounds_all"][0] == rest_w["bounds_all"][1]
     g = ctx.grad(vid=ps.vids[:3])
     assert np.allclose(rest_w["grad0"], g, rtol=1e-13, atol=0)
     # vs the oracle
