@@ -427,10 +427,29 @@ def cfg4_sibling_wave(device, stream, rank, world, dist, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     r = b.fetch(want_x=False)
-    return {"workload": "sinusoid h=19 k=2 arity=4 (V=%d, F=%d): %d sibling components of %d variables / %d factors after assigning "
-                        "the top 10 tree levels, %d per rank" % (spec["V"], spec["F"], ps.n, ps.var_off[1], ps.fac_off[1], mine.n),
-            "scaling": "strong", "n_gpus": world, "ms": ms, "solves_per_sec": ps.n / (ms * 1e-3),
-            "objective_sum_f_end": float(obj.item()), "mapping": b.info()}
+    out = {"workload": "sinusoid h=19 k=2 arity=4 (V=%d, F=%d): %d sibling components of %d variables / %d factors after assigning "
+                       "the top 10 tree levels, %d per rank" % (spec["V"], spec["F"], ps.n, ps.var_off[1], ps.fac_off[1], mine.n),
+           "scaling": "strong", "n_gpus": world, "ms": ms, "solves_per_sec": ps.n / (ms * 1e-3),
+           "objective_sum_f_end": float(obj.item()), "mapping": b.info()}
+    if rank == 0:
+        # the callers either side of the solve on the same graph (host buffers in and out, wall clock around the C call):
+        # sibling membership (rdisgpu_components) and interval bounds of every factor (rdisgpu_bounds)
+        import time
+        assigned = np.zeros(spec["V"], np.uint8); assigned[:1023] = 1     # the top 10 tree levels
+        ctx.set_x(x0)
+        ctx.components(assigned)
+        t0 = time.perf_counter(); vl, fl, ncomp, rounds = ctx.components(assigned); t1 = time.perf_counter()
+        out["membership"] = {"what": "rdisgpu_components: labels of %d variables / %d factors, host buffers" % (spec["V"], spec["F"]),
+                             "ms": (t1 - t0) * 1e3, "components": int(ncomp), "rounds": int(rounds),
+                             "matches_generator": bool(ncomp == ps.n and np.array_equal(np.sort(np.nonzero(vl == vl[ps.vids[0]])[0]),
+                                                                                         np.sort(ps.vids[:ps.var_off[1]])))}
+        ctx.bounds(assigned)
+        t0 = time.perf_counter(); lo, hi, tot = ctx.bounds(assigned); t1 = time.perf_counter()
+        out["bounds"] = {"what": "rdisgpu_bounds: interval bounds of all %d factors (top 10 levels assigned, the rest at their domains), "
+                                 "host buffers, per-factor bounds returned" % spec["F"],
+                         "ms": (t1 - t0) * 1e3, "factor_bounds_per_sec": spec["F"] / (t1 - t0), "sum": [tot[0], tot[1]],
+                         "parity": "unpinned upstream (Boost.Interval not vendored); tested against oracle/interval_oracle.hpp"}
+    return out
 
 
 def sweep_roofline(device, stream):

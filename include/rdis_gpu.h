@@ -81,8 +81,8 @@ RDISGPU_API const char* rdisgpu_last_error(const rdisgpu_ctx* ctx); /* ctx may b
 RDISGPU_API int rdisgpu_set_stream(rdisgpu_ctx* ctx, void* cuda_stream);
 RDISGPU_API int rdisgpu_synchronize(rdisgpu_ctx* ctx);
 /* Tuning / test switches.  "generic_only" != 0: batches created afterwards bypass the bundle-adjustment
- * block kernels and run every problem through the generic tile / CTA / grid kernels.  "resident_threads" = 256 | 512:
- * CTA width of the shared-memory resident NonlinearProductFactor component kernel (512 = default; 256 reproduces the
+ * block kernels and run every problem through the generic tile / CTA / grid kernels.  "resident_threads" = 256 | 1024:
+ * CTA width of the shared-memory resident NonlinearProductFactor component kernel (1024 = default; 256 reproduces the
  * generic CTA kernel's reduction order and therefore its results to the bit — used by the equality test). */
 RDISGPU_API int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value);
 

@@ -38,11 +38,15 @@
 
 namespace rdisgpu {
 
-// CTA width.  512 threads (128 registers, 16 warps on the SM) is the default: the passes are latency-bound and twice
-// the warps hide more of it (cfg4 wave 36 -> 27 ms).  256 threads is the generic block kernel's widest CTA — the same
+// CTA width.  The passes are issue- and barrier-bound, so the CTA is as wide as the register file allows: with the
+// state machine in shared memory the kernel needs 64 registers and runs 1024 threads (cfg4 wave: 256 threads 36 ms,
+// 512 threads 16.2 ms, 768 15.3 ms, 1024 15.1 ms).  256 threads is the generic block kernel's widest CTA — the same
 // factor -> thread mapping and reduction tree, hence bit-identical results — and stays selectable
 // (rdisgpu_set_option "resident_threads") for the equality test.
-constexpr int kResThreads = 512;
+#ifndef RDIS_RES_THREADS
+#define RDIS_RES_THREADS 1024
+#endif
+constexpr int kResThreads = RDIS_RES_THREADS;
 constexpr int kResThreadsExact = 256;
 // Small components (a few hundred variables) leave a 512-thread CTA mostly idle and a CTA owns the whole register
 // file: they run 128 threads wide, four CTAs to the SM.
@@ -116,8 +120,11 @@ struct ResView {
   const uint16_t* vinc;  // ... and of the variable-major incidence list (local edge ids, ascending factor id)
 };
 
-// Sum of two doubles per thread over the CTA: Block::reduce's order (warp butterfly, warp partials folded 0..nw-1 by
-// every thread), so a 256-thread CTA reproduces the generic kernel's totals to the bit.  buf = 2 x 64 doubles.
+// Sum of two doubles per thread over the CTA, delivered to WARP 0 only (the state machine's thread is its consumer).
+// kExact: Block::reduce's order — warp butterfly, warp partials folded 0..nw-1 — so a 256-thread CTA reproduces the
+// generic kernel's totals to the bit.  Otherwise the warp partials are folded by a second butterfly (5 shuffle steps
+// instead of a serial walk over up to 32 partials on the critical path of every evaluation).  buf = 2 x 64 doubles.
+template <bool kExact>
 __device__ __forceinline__ void resident_sum2(double* buf2, int& flip, double& a, double& b) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -132,11 +139,22 @@ __device__ __forceinline__ void resident_sum2(double* buf2, int& flip, double& a
     buf[2 * warp + 1] = b;
   }
   __syncthreads();
-  a = buf[0];
-  b = buf[1];
-  for (int w = 1; w < nw; ++w) {
-    a += buf[2 * w];
-    b += buf[2 * w + 1];
+  if (warp != 0) return;
+  if (kExact) {
+    a = buf[0];
+    b = buf[1];
+    for (int w = 1; w < nw; ++w) {
+      a += buf[2 * w];
+      b += buf[2 * w + 1];
+    }
+  } else {
+    a = (lane < nw) ? buf[2 * lane] : 0.0;
+    b = (lane < nw) ? buf[2 * lane + 1] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
   }
 }
 
@@ -205,7 +223,7 @@ __device__ __forceinline__ void resident_terms(const ResView& R, double alpha, b
 }
 
 // One line evaluation: f(p + alpha*xi) and, with kSlope, d/dalpha — the shared-memory form of objective_along_line.
-template <bool kSlope>
+template <bool kSlope, bool kExact>
 __device__ __forceinline__ void resident_line_eval(const GraphView& G, const ResView& R, double* buf2, int& flip,
                                                    const int32_t* fids, int nf, double alpha, double& f, double& slope) {
   const int T = blockDim.x, tid = threadIdx.x;
@@ -246,7 +264,7 @@ __device__ __forceinline__ void resident_line_eval(const GraphView& G, const Res
     fs += fv;
     ss += s;
   }
-  resident_sum2(buf2, flip, fs, ss);  // its barrier also orders this evaluation's reads of tval before the next pass 1
+  resident_sum2<kExact>(buf2, flip, fs, ss);  // totals in warp 0; its barrier also orders this evaluation's reads of tval before the next pass 1
   f = fs;
   slope = ss;
 }
@@ -463,12 +481,20 @@ __global__ void __launch_bounds__(kThreads, kMinCtas)
     __syncthreads();
   }
 
-  CgdMachine m;
-  m.start(maxiters, ftol);
-  double f_init = 0.0;
-
-  while (!m.done()) {
-    if (m.req == REQ_INIT_GRAD) {
+  // The CG / line-search state machine lives in shared memory and is advanced by ONE thread; everybody else reads the
+  // published request.  (Replicating it in every thread, as the generic kernels do, costs 13 % of this kernel's
+  // instructions and ~70 registers per thread — the difference between 16 and 32 resident warps.)  Every branch below
+  // has a CTA barrier between the reads at the top of the loop and thread 0's update, and the loop's own barrier
+  // publishes the update.
+  __shared__ CgdMachine m;
+  __shared__ double s_f_init;
+  if (tid == 0) m.start(maxiters, ftol);
+  for (;;) {
+    __syncthreads();
+    const int req = m.req;
+    if (req == REQ_DONE) break;
+    const double alpha = m.alpha, gam = m.gam;
+    if (req == REQ_INIT_GRAD) {
       double fs = resident_gradient(G, R, fids, nv, nf, [&](int j, double gr) {
         const int32_t vid = vids[j];
         const double gneg = -gr;
@@ -478,30 +504,28 @@ __global__ void __launch_bounds__(kThreads, kMinCtas)
       });
       double zero = 0.0;
       grp.sum2(fs, zero);
-      grp.sync();
-      f_init = fs;
-      m.on_init(fs);
-    } else {
+      if (tid == 0) {
+        s_f_init = fs;
+        m.on_init(fs);
+      }
+    } else if (req == REQ_VALUE || req == REQ_VALUE_SLOPE) {
       double f, sl;
-      if (m.req == REQ_VALUE_SLOPE)
-        resident_line_eval<true>(G, R, buf2, flip2, fids, nf, m.alpha, f, sl);
+      constexpr bool kExact = (kThreads == kResThreadsExact);
+      if (req == REQ_VALUE_SLOPE)
+        resident_line_eval<true, kExact>(G, R, buf2, flip2, fids, nf, alpha, f, sl);
       else
-        resident_line_eval<false>(G, R, buf2, flip2, fids, nf, m.alpha, f, sl);
-      m.on_eval(f, sl);
-    }
-
-    while (m.req == REQ_MOVE) {
-      const double step = m.alpha;
+        resident_line_eval<false, kExact>(G, R, buf2, flip2, fids, nf, alpha, f, sl);
+      if (tid == 0) m.on_eval(f, sl);
+    } else if (req == REQ_MOVE) {
       for (int j = tid; j < nv; j += T) {  // minimize_nrc.h:508-511
         double2 xb = make_double2(R.xs[j], R.ds[j]);
-        xb.y *= step;
+        xb.y *= alpha;
         xb.x += xb.y;
         R.xs[j] = xb.x; R.ds[j] = xb.y;
       }
-      grp.sync();
-      m.on_moved();
-      if (m.req != REQ_GRADIENT) break;
-
+      __syncthreads();
+      if (tid == 0) m.on_moved();
+    } else if (req == REQ_GRADIENT) {
       double gg = 0.0, dgg = 0.0, dummy = 0.0, tnum = 0.0;
       (void)resident_gradient(G, R, fids, nv, nf, [&](int j, double gr) {
         R.ds[j] = gr;  // func.df(p, xi), :654
@@ -513,10 +537,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas)
         dgg += (gr + gj) * gr;
       });
       grp.sum3max(gg, dgg, dummy, tnum);
-      m.on_gradient(tnum, gg, dgg);
-      if (m.req != REQ_DIRECTION) break;
-      const double gam = m.gam;
-      for (int j = tid; j < nv; j += T) {  // :681-685
+      if (tid == 0) m.on_gradient(tnum, gg, dgg);
+    } else {  // REQ_DIRECTION, :681-685
+      for (int j = tid; j < nv; j += T) {
         const int32_t vid = vids[j];
         const double gj = -R.ds[j];
         const double hj = gj + gam * G.hvec[vid];
@@ -524,10 +547,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas)
         G.hvec[vid] = hj;
         R.ds[j] = hj;
       }
-      grp.sync();
-      m.on_directed();
+      __syncthreads();
+      if (tid == 0) m.on_directed();
     }
   }
+  const double f_init = s_f_init;
 
   // ---- commit (CGD.cpp:61-89) ----
   double fret = m.fret;

@@ -126,7 +126,7 @@ struct rdisgpu_ctx {
   DevBuf<double> t_expo, t_konst;
   DevBuf<uint8_t> t_sine;
   std::vector<int32_t> h_rp32, h_evid32, h_tvrow, vowner;
-  int res_threads = kResThreads;  // rdisgpu_set_option("resident_threads", 256 | 512)
+  int res_threads = kResThreads;  // rdisgpu_set_option("resident_threads", 256 | 1024)
   int res_smem_cap = -1;  // dynamic shared memory a resident CTA may ask for (queried at the first NLPF batch)
   DevBuf<uint8_t> cc_assigned;
   DevBuf<int32_t> cc_vlabel, cc_flabel, cc_flag;
@@ -315,7 +315,7 @@ int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value) {
     return RDISGPU_OK;
   }
   if (std::strcmp(name, "resident_threads") == 0) {
-    if (value != kResThreads && value != kResThreadsExact) return ctx->fail(RDISGPU_ERR_ARG, "set_option: resident_threads must be 256 or 512");
+    if (value != kResThreads && value != kResThreadsExact) return ctx->fail(RDISGPU_ERR_ARG, "set_option: resident_threads must be 256 or 1024");
     ctx->res_threads = (int)value;
     return RDISGPU_OK;
   }
