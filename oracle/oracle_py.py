@@ -25,7 +25,7 @@ def build(force=False):
     """Compile the oracle (and, where /root/reference exists, the _ref variant)."""
     if force or not os.path.exists(LIB_RESTATED) or \
             os.path.getmtime(LIB_RESTATED) < max(os.path.getmtime(os.path.join(_HERE, f))
-                                                  for f in ("oracle_capi.cpp", "rdis_oracle.hpp", "nr_minimize.hpp", "lm_oracle.hpp")):
+                                                  for f in ("oracle_capi.cpp", "rdis_oracle.hpp", "nr_minimize.hpp", "lm_oracle.hpp", "interval_oracle.hpp")):
         subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
     elif not os.path.exists(LIB_REFNRC) and os.path.exists("/root/reference/external/include/minimize_nrc.h"):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)

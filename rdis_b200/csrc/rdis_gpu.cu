@@ -9,6 +9,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rdis_gpu.h"
@@ -994,23 +995,51 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
       CK(cudaFuncSetAttribute(solve_nlpf_resident_kernel<kResThreadsExact, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_smem_cap));
       CK(cudaFuncSetAttribute(solve_nlpf_resident_kernel<kResThreadsSmall, kResSmallCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmallSmem));
     }
+    // pass 1 (host threads when the batch is large): per problem the flattened sizes — edges, distinct terms of its
+    // own variables, edges on frozen variables — and whether it is a proper sibling set
+    struct ResCount { int64_t nE, nT, nFz; bool ok; };
+    std::vector<ResCount> cnt((size_t)nprobs);
+    auto count_range = [&](int64_t p0, int64_t p1) {
+      for (int64_t p = p0; p < p1; ++p) {
+        const ProblemDesc& D = b->h_probs[p];
+        ResCount c{0, 0, 0, true};
+        if (D.nf <= kTileMax || D.nv > 0xffff) {
+          c.ok = false;
+          cnt[(size_t)p] = c;
+          continue;
+        }
+        const int32_t* pvv = vids + D.var_off;
+        const int32_t* pf = fids + D.fac_off;
+        for (int j = 0; j < D.nv; ++j) c.nT += ctx->h_tvrow[pvv[j] + 1] - ctx->h_tvrow[pvv[j]];
+        for (int k = 0; k < D.nf && c.ok; ++k) {
+          for (int32_t e = ctx->h_rp32[pf[k]]; e < ctx->h_rp32[pf[k] + 1]; ++e) {
+            const int32_t v = ctx->h_evid32[e];
+            if (ctx->vmark[v] != epoch) ++c.nFz;                       // frozen variable: a constant term
+            else if (ctx->vowner[v] != (int32_t)p) c.ok = false;        // not a sibling set: leave it to the generic path
+            ++c.nE;
+          }
+        }
+        cnt[(size_t)p] = c;
+      }
+    };
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (tf >= 200000 && nprobs >= 2 * (int64_t)hw && hw > 1) {
+      std::vector<std::thread> pool;
+      const int64_t per = (nprobs + hw - 1) / hw;
+      for (unsigned t = 0; t < hw; ++t) {
+        const int64_t p0 = std::min<int64_t>(nprobs, (int64_t)t * per), p1 = std::min<int64_t>(nprobs, p0 + per);
+        if (p0 < p1) pool.emplace_back(count_range, p0, p1);
+      }
+      for (std::thread& th : pool) th.join();
+    } else {
+      count_range(0, nprobs);
+    }
+    // pass 2: admission in problem order (scratch slices are handed out in that order)
     for (int64_t p = 0; p < nprobs; ++p) {
       ProblemDesc& D = b->h_probs[p];
-      if (D.nf <= kTileMax || D.nv > 0xffff) continue;
-      const int32_t* pvv = vids + D.var_off;
-      const int32_t* pf = fids + D.fac_off;
-      int64_t nE = 0, nT = 0, nFz = 0;
-      bool ok = true;
-      for (int j = 0; j < D.nv; ++j) nT += ctx->h_tvrow[pvv[j] + 1] - ctx->h_tvrow[pvv[j]];
-      for (int k = 0; k < D.nf && ok; ++k) {
-        for (int32_t e = ctx->h_rp32[pf[k]]; e < ctx->h_rp32[pf[k] + 1]; ++e) {
-          const int32_t v = ctx->h_evid32[e];
-          if (ctx->vmark[v] != epoch) ++nFz;                       // frozen variable: a constant term
-          else if (ctx->vowner[v] != (int32_t)p) ok = false;        // not a sibling set: leave it to the generic path
-          ++nE;
-        }
-      }
-      if (!ok || nT + nFz > 0xffff || nE > 0xffff || res_edges + nE > 0x7fffffffLL) continue;
+      const ResCount& c = cnt[(size_t)p];
+      const int64_t nE = c.nE, nT = c.nT, nFz = c.nFz;
+      if (!c.ok || nT + nFz > 0xffff || nE > 0xffff || res_edges + nE > 0x7fffffffLL) continue;
       const ResLayout L = res_layout(D.nv, D.nf, (int)nE, (int)nT, (int)nFz);
       if (L.total > ctx->res_smem_cap) continue;
       D.nE = (int32_t)nE; D.nT = (int32_t)nT; D.nFz = (int32_t)nFz; D.goff = (int32_t)res_edges;
