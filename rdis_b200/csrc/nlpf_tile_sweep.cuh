@@ -48,6 +48,9 @@ constexpr int kTileThreads = RDIS_TILE_THREADS;   // consumer threads (one more 
 constexpr int kTileEdges = RDIS_TILE_EDGES;
 constexpr int kTileFactors = RDIS_TILE_FACTORS;
 constexpr int kTileStages = RDIS_TILE_STAGES;
+#ifndef RDIS_TILE_CTAS_GRAD
+#define RDIS_TILE_CTAS_GRAD 2
+#endif
 constexpr int kTileCtasPerSm = RDIS_TILE_CTAS;
 constexpr int kEdgeBatch = kTileEdges / kTileThreads;  // gathers per thread per tile, issued one tile ahead
 
@@ -158,7 +161,7 @@ constexpr int kGatherLag = RDIS_TILE_GATHER_LAG;
 static_assert(kGatherLag >= 1 && kGatherLag < kTileStages, "the gather trails the bulk copy by fewer tiles than there are stages");
 
 template <bool kGrad>
-__global__ void __launch_bounds__(kTileThreads + 32, kGrad ? 2 : kTileCtasPerSm)
+__global__ void __launch_bounds__(kTileThreads + 32, kGrad ? RDIS_TILE_CTAS_GRAD : kTileCtasPerSm)
     nlpf_tile_sweep_kernel(GraphView G, const TileDesc* __restrict__ tiles, int ntiles, double* __restrict__ per_factor,
                            double* partials, unsigned int* counter, double* sum_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
