@@ -341,6 +341,9 @@ def run_ours(args):
                                           "per wave (NOT the headline workload: shows the throughput regime of the same kernels)" % (K, pts_k.n, cams_k.n),
                                   "ms_per_wave": ms_k, "solves_per_sec": (pts_k.n + cams_k.n) / (ms_k * 1e-3), "camera_mapping": bck.info()}
         del bpk, bck, ctx_k
+    # ---- BASELINE config 2: optSinusoid d=1000, the whole graph as ONE subspace problem (rank 0) ----
+    if rank == 0 and not args.no_sweep:
+        out["cfg2_full_solve"] = cfg2_full_solve(local_rank, stream, with_cpu=not args.no_cpu)
     # ---- BASELINE config 4: sibling-component shard of the 1e6-variable / 4e6-factor graph (all ranks) ----
     if not args.no_sweep:
         c4 = cfg4_sibling_wave(local_rank, stream, rank, world, dist if world > 1 else None, dev)
@@ -387,6 +390,52 @@ def ba_sweep_rates(spec, device, stream, dev):
                      "sum": float(tot.item())}
         del ctx
     res["kernels"] = "ba_camera_table_kernel + ba_sweep_kernel (back-to-back launches, per-factor values written)"
+    return res
+
+
+def cfg2_full_solve(device, stream, with_cpu=True):
+    """BASELINE config 2 (optSinusoid d=1000): the chain h=999 k=1 arity 3 (V=1000, F=2999) and the
+    default-shaped tree h=6 k=3 arity 3 (V=1093, F=3278), every variable and every factor in ONE subspace problem, SSmaxit 25,
+    ftol 3e-8, seeded start.  One CTA solves it resident in shared memory (nlpf_resident.cuh); the CPU oracle solves
+    the same problem from the same start on one core."""
+    import time
+    import torch
+    from rdis_b200 import Context, problems as P
+    res = {}
+    for name, (h, k, ar) in (("chain_h999_k1_arity3", (999, 1, 3)), ("tree_h6_k3_arity3", (6, 3, 3))):
+        spec = P.sinusoid(h, k, ar)
+        x0 = P.random_start(spec, 834725927 % 1000)
+        ps = P.full_problem(spec)
+        ctx = Context.from_spec(spec, device=device, stream=stream.cuda_stream)
+        b = ctx.batch(ps)
+        x0_dev = torch.from_numpy(x0).to("cuda:%d" % device)
+        ts = []
+        for it in range(4):
+            ctx.set_x_device(x0_dev.data_ptr(), spec["V"])
+            torch.cuda.synchronize()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            b.solve(None, MAXITERS, FTOL)
+            e.record(stream)
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(e))
+        r = b.fetch(want_x=True)
+        info = b.info()
+        rec = {"V": int(spec["V"]), "F": int(spec["F"]), "ms_per_solve": float(np.min(ts[1:])), "f_init": float(r["f_init"][0]),
+               "f_end": float(r["f_end"][0]), "iters": int(r["iters"][0]), "evaluations": int(r["n_feval"][0] + r["n_geval"][0]),
+               "resident": bool(info["resident_problems"] == 1), "resident_smem_bytes": info["resident_smem_bytes"]}
+        if with_cpu:
+            from oracle import oracle_py as O
+            orc = O.OracleFunction.from_spec(spec)
+            orc.set_x(x0)
+            t0 = time.perf_counter()
+            o = orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[ps.vids], MAXITERS, FTOL)
+            rec["cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
+            rec["cpu_f_end"] = float(o["f_end"][0])
+            rec["rel_diff_f_end"] = abs(rec["f_end"] - rec["cpu_f_end"]) / max(abs(rec["cpu_f_end"]), 1e-300)
+        res[name] = rec
+        b.close()
+        del ctx
     return res
 
 

@@ -750,3 +750,36 @@ def test_nlpf_resident_kernel_matches_generic_path(gpu, oracle_mod):
         a = fast.solve_cgd(sub, None, 25, 3e-8); b = slow.solve_cgd(sub, None, 25, 3e-8)
         assert np.array_equal(a["f_end"], b["f_end"]) and np.array_equal(a["x"], b["x"])
         assert np.array_equal(fast.get_x(), slow.get_x())
+
+
+@pytest.mark.gpu
+def test_config2_whole_graph_as_one_problem(gpu, oracle_mod):
+    """BASELINE config 2 (optSinusoid d=1000): every variable and factor of the chain (h=999, k=1) and of the default-
+    shaped tree (h=6, k=3) in ONE subspace problem — no frozen variables, the resident kernel's widest case.  Equal to
+    the generic CTA kernel at 256 threads; within the band of the reference's own rounding twin against the oracle
+    (a 1000-variable, 25-iteration CG on a sum of sines is not a contraction: see test_solve_ba_camera_blocks)."""
+    from rdis_b200 import Context, problems as P
+    for h, k, ar in ((999, 1, 3), (6, 3, 3)):
+        sp = P.sinusoid(h, k, ar)
+        x0 = P.random_start(sp, 727)
+        ps = P.full_problem(sp)
+        fast = Context.from_spec(sp); slow = Context.from_spec(sp); wide = Context.from_spec(sp)
+        slow.set_option("generic_only", 1); fast.set_option("resident_threads", 256)
+        for c in (fast, slow, wide):
+            c.set_x(x0)
+        bi = wide.batch(ps); info = bi.info(); bi.close()
+        assert info["resident_problems"] == 1, info
+        a = fast.solve_cgd(ps, x0, 25, 3e-8); b = slow.solve_cgd(ps, x0, 25, 3e-8); w = wide.solve_cgd(ps, x0, 25, 3e-8)
+        assert all(np.array_equal(a[key], b[key]) for key in ("f_init", "f_end", "iters", "status", "x", "n_feval", "n_geval"))
+        o = _oracle_batch(oracle_mod, sp, ps, x0, 25)
+        assert _relerr(a["f_init"], o["f_init"], 1e-12).max() <= 1e-12 and _relerr(w["f_init"], o["f_init"], 1e-12).max() <= 1e-12
+        try:
+            of = _oracle_batch(oracle_mod, sp, ps, x0, 25, "fma")
+            spread = float(_relerr(of["f_end"], o["f_end"], 1e-12).max())
+        except Exception:
+            spread = 0.0
+        rel = max(float(_relerr(a["f_end"], o["f_end"], 1e-12).max()), float(_relerr(w["f_end"], o["f_end"], 1e-12).max()))
+        print("config 2 h=%d k=%d: V=%d F=%d, gpu-vs-oracle rel f_end %.2e, oracle-vs-FMA-twin %.2e, evals %d" % (
+            h, k, sp["V"], sp["F"], rel, spread, int(a["n_feval"][0] + a["n_geval"][0])))
+        assert rel <= max(1e-6, 10.0 * spread)
+        assert (w["f_end"] <= w["f_init"]).all() and (a["f_end"] <= a["f_init"]).all()
