@@ -48,12 +48,17 @@ namespace rdisgpu {
 #endif
 constexpr int kResThreads = RDIS_RES_THREADS;
 constexpr int kResThreadsExact = 256;
-// Small components (a few hundred variables) leave a 512-thread CTA mostly idle and a CTA owns the whole register
-// file: they run 128 threads wide, four CTAs to the SM.
-constexpr int kResThreadsSmall = 128;
+// Components whose layout leaves room for at least two CTAs on the SM run 256 threads wide, up to four CTAs to the SM
+// (64 registers): half of an evaluation is a serial path (barriers, the scalar line-search step), and a second
+// resident CTA fills it.  (Level-13 subtrees of config 4, 127 variables: 18.0 ms per 8192 solves at 128 threads,
+// 16.4 ms at 256.)
+#ifndef RDIS_RES_SMALL_THREADS
+#define RDIS_RES_SMALL_THREADS 256
+#endif
+constexpr int kResThreadsSmall = RDIS_RES_SMALL_THREADS;
 constexpr int kResSmallCtas = 4;
-constexpr int kResSmallFactors = 1536;      // at most this many factors ...
-constexpr int kResSmallSmem = 52 * 1024;    // ... and this much shared memory
+constexpr int kResSmallFactors = 4096;       // at most this many factors ...
+constexpr int kResSmallSmem = 110 * 1024;    // ... and this much shared memory (two CTAs per SM)
 
 // Shared-memory carve-up, computed identically on the host (fits? how many bytes to ask for) and in the kernel.
 struct ResLayout {

@@ -166,7 +166,7 @@ struct rdisgpu_batch {
   DevBuf<ResultRec> res;
   // size classes of the generic kernels
   std::vector<int32_t> h_order;      // problem indices grouped by class
-  struct Class { int kind; int param; int64_t off; int64_t count; };  // kind 0 = tile(G), 1 = block(threads), 2 = grid
+  struct Class { int kind; int param; int64_t off; int64_t count; };  // kind 0 = tile(G), 1 = block(threads), 2 = grid, 3 / 4 = resident NLPF (wide / small CTAs)
   std::vector<Class> classes;
   PinnedBuf<ResultRec> h_res;
   PinnedBuf<double> h_x;  // staging for x0 upload and xout download
@@ -1088,7 +1088,7 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
     b->h_order.insert(b->h_order.end(), res_list.begin(), res_list.end());
   }
   if (!res_small_list.empty()) {
-    b->classes.push_back({3, kResThreadsSmall, (int64_t)b->h_order.size(), (int64_t)res_small_list.size()});
+    b->classes.push_back({4, kResThreadsSmall, (int64_t)b->h_order.size(), (int64_t)res_small_list.size()});
     b->h_order.insert(b->h_order.end(), res_small_list.begin(), res_small_list.end());
   }
   if (!grid_list.empty()) {
@@ -1255,10 +1255,11 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
       else
         solve_block_kernel<BaOps><<<cnt, c.param, 0, s>>>(gv, bv, ord, cnt, maxiters, ftol);
       ++launches;
+    } else if (c.kind == 4) {
+      solve_nlpf_resident_kernel<kResThreadsSmall, kResSmallCtas><<<cnt, kResThreadsSmall, (size_t)b->res_small_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
+      ++launches;
     } else if (c.kind == 3) {
-      if (c.param == kResThreadsSmall)
-        solve_nlpf_resident_kernel<kResThreadsSmall, kResSmallCtas><<<cnt, kResThreadsSmall, (size_t)b->res_small_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
-      else if (c.param == kResThreadsExact)
+      if (c.param == kResThreadsExact)
         solve_nlpf_resident_kernel<kResThreadsExact, 1><<<cnt, kResThreadsExact, (size_t)b->res_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
       else
         solve_nlpf_resident_kernel<kResThreads, 1><<<cnt, kResThreads, (size_t)b->res_smem, s>>>(gv, bv, ord, cnt, maxiters, ftol);
@@ -1614,7 +1615,7 @@ int rdisgpu_batch_info(const rdisgpu_batch* b, int32_t out[8]) {
   if (!b || !out) return RDISGPU_ERR_ARG;
   int n_generic = 0;
   for (const auto& c : b->classes)
-    if (c.kind != 3) n_generic += (int)c.count;
+    if (c.kind != 3 && c.kind != 4) n_generic += (int)c.count;
   out[0] = (int32_t)b->nprobs;
   out[1] = b->n_pt_warps;
   out[2] = b->n_cam;
@@ -1630,7 +1631,7 @@ int rdisgpu_batch_resident_info(const rdisgpu_batch* b, int32_t out[2]) {
   if (!b || !out) return RDISGPU_ERR_ARG;
   out[0] = 0;
   for (const auto& c : b->classes)
-    if (c.kind == 3) out[0] += (int32_t)c.count;
+    if (c.kind == 3 || c.kind == 4) out[0] += (int32_t)c.count;
   out[1] = std::max(b->res_smem, b->res_small_smem);
   return RDISGPU_OK;
 }
