@@ -360,13 +360,20 @@ struct NlpfOps {
     const bool sn = __ldg(&G.sine[e]) != 0;
     double val = xv;
     if (k != 0) val -= k;
-    if (ex != 1) val = rdis_power(val, ex);
     plain = (ex == 1) && !sn;
     if (plain) {
       t = val;
       dt = 1.0;
       return;
     }
+    if (ex == 1) {  // sine of x - k: the general path below reduces to dt = 1.0 * 1.0 * cos(val) bit for bit (nlpf_term_grad)
+      double sv, cv;
+      rdis_sincos(val, sv, cv);
+      t = sv;
+      dt = cv;
+      return;
+    }
+    val = rdis_power(val, ex);
     const double inner = xv - k;
     const double innerexp = rdis_power(inner, ex);
     double dv = rdis_power(inner, ex - 1.0);
