@@ -11,7 +11,8 @@
 // /root/reference and is not installed here.  The class below restates the library's published algorithms
 // (numeric/interval/arith.hpp, arith2.hpp, transc.hpp, detail/division.hpp, constants.hpp) in terms of plain double
 // operations, which is what that policy reduces them to.  The reference holds no golden bound values; the tests pin
-// this file by the ENCLOSURE property (every sampled point value lies inside the bound) and hand-derived cases.
+// this file by the ENCLOSURE property (every sampled point value lies inside the bound), hand-derived cases, and an
+// independent interval library (mpmath.iv) evaluating the same expressions (tests/test_bounds.py).
 #pragma once
 #include <algorithm>
 #include <cmath>
