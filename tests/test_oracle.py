@@ -309,3 +309,33 @@ def test_nlpf_values_match_a_direct_numpy_evaluation(oracle_mod):
     s2, pf2 = orc2.eval(per_factor=True)
     want2 = numpy_eval(spec2, x2)
     assert np.allclose(pf2, want2, rtol=1e-12, atol=1e-300)
+
+
+def test_lm_restatement_reaches_minpack_minima(oracle_mod):
+    """Independent cross-check of the LM oracle (levmar restated from its published algorithm: PARITY UNPINNED upstream):
+    on bundle-adjustment point blocks, run to convergence, it stops at the minimum MINPACK's Levenberg-Marquardt
+    (scipy.optimize.least_squares(method='lm')) finds for the same residuals r_j = sqrt(2 f_j)
+    (LMSSOpt::evalFunc, src/optimizers/LMSubspaceOptimizer.cpp:176-204)."""
+    from scipy.optimize import least_squares
+    from rdis_b200 import problems as P
+    spec = P.ba_synthetic(ncams=5, npts=60, nobs=240, seed=2)
+    ps = P.ba_point_problems(spec)
+    x0 = spec["x0"]
+    orc = oracle_mod.OracleFunction.from_spec(spec); orc.set_x(x0)
+    r = orc.solve_lm_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[ps.vids], 2000, 1e-17)
+    aux = oracle_mod.OracleFunction.from_spec(spec)
+    checked = 0
+    for k in range(ps.n):
+        vids = ps.vids[ps.var_off[k]:ps.var_off[k + 1]]; fids = ps.fids[ps.fac_off[k]:ps.fac_off[k + 1]]
+        if len(fids) < 3 or r["stop"][k] != 2 or checked >= 12:   # MINPACK needs residuals >= variables; 2 = converged (small step)
+            continue
+
+        def res(z):
+            x = x0.copy(); x[vids] = z; aux.set_x(x)
+            _, pf = aux.eval(fids, per_factor=True, use_cache=False)
+            return np.sqrt(2.0 * pf)
+        sol = least_squares(res, x0[vids], method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15)
+        f_mp = 0.5 * float(np.sum(sol.fun ** 2))
+        assert abs(f_mp - r["f_end"][k]) <= 1e-9 * max(f_mp, 1e-300), (k, f_mp, r["f_end"][k])
+        checked += 1
+    assert checked >= 8
