@@ -479,7 +479,10 @@ def cfg4_sibling_wave(device, stream, rank, world, dist, dev):
     out = {"workload": "sinusoid h=19 k=2 arity=4 (V=%d, F=%d): %d sibling components of %d variables / %d factors after assigning "
                        "the top 10 tree levels, %d per rank" % (spec["V"], spec["F"], ps.n, ps.var_off[1], ps.fac_off[1], mine.n),
            "scaling": "strong", "n_gpus": world, "ms": ms, "solves_per_sec": ps.n / (ms * 1e-3),
-           "objective_sum_f_end": float(obj.item()), "mapping": b.info()}
+           "objective_sum_f_end": float(obj.item()), "mapping": b.info(),
+           "kernel": "solve_nlpf_resident_kernel (one CTA per component, resident in shared memory)",
+           "dram_bytes_per_launch_ncu": measured_traffic("solve_nlpf_resident_kernel"),
+           "fp64_pipe_active_pct_ncu": measured_traffic("solve_nlpf_resident_kernel", "fp64_pipe_active_pct")}
     if rank == 0:
         # the callers either side of the solve on the same graph (host buffers in and out, wall clock around the C call):
         # sibling membership (rdisgpu_components) and interval bounds of every factor (rdisgpu_bounds)
