@@ -3,7 +3,9 @@
 The reference holds NO golden bound values and Boost.Interval is not vendored (parity unpinned), so
 the oracle's restatement is pinned by what the domain offers:
   - hand-derived intervals of small expressions (monotone pieces, sign cases of the product, the power quirk),
-  - the ENCLOSURE property: for any point of the box, every factor's value lies inside its bound,
+  - the ENCLOSURE property: for any point of the box, every factor's value lies inside its bound — which is the
+    reference's own DEBUG invariant for an optimised child component (src/Component.cpp:259-305, tol 1e-6),
+  - an independent interval library (mpmath.iv) evaluating the same expressions,
   - the all-assigned / assigned-constant rule of src/Factor.cpp:128 (the bound collapses to the point value).
 The GPU test then compares rdisgpu_bounds with the oracle on the same inputs (1e-12: device sin/cos vs libm)."""
 import numpy as np
@@ -231,3 +233,33 @@ def test_oracle_bounds_match_an_independent_interval_library(oracle_mod):
         assert _iv_close(lo[f], hi[f], err, 1e-9), (f, lo[f], hi[f], err)
         checked += 1
     assert checked >= 20
+
+
+def test_component_optimum_lies_inside_its_unassigned_bounds(oracle_mod):
+    """The reference's own DEBUG invariant (Component::onChildEvaluated, src/Component.cpp:259-305, tol 1e-6): the value a
+    child component is optimised to lies inside the bounds computed for it while its variables were unassigned.
+    Sibling subtrees of the sinusoid family (ancestors assigned = points, the subtree's variables at their domains),
+    optimised by the CGD oracle; and bundle-adjustment point blocks on boxes a few per cent wide."""
+    from rdis_b200 import problems as P
+    tol = 1e-6
+    tree = P.sinusoid(7, 2, 4)
+    x0 = P.random_start(tree, 13)
+    ps = P.sinusoid_subtree_problems(tree, 3)
+    orc = oracle_mod.OracleFunction.from_spec(tree); orc.set_x(x0)
+    point = np.ones(tree["V"], np.uint8); point[ps.vids] = 0
+    bounds = []
+    for k in range(ps.n):
+        fids = ps.fids[ps.fac_off[k]:ps.fac_off[k + 1]]
+        bounds.append(orc.bounds(point, fids)[2])
+    o = orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[ps.vids], 25, 3e-8)
+    for k, (lo, hi) in enumerate(bounds):
+        assert lo - tol <= o["f_end"][k] <= hi + tol and lo - tol <= o["f_init"][k] <= hi + tol, (k, lo, o["f_end"][k], hi)
+    ba = P.ba_synthetic(ncams=4, npts=40, nobs=140, seed=6)
+    ba = dict(ba); w = 0.03 * np.maximum(np.abs(ba["x0"]), 0.05); ba["lb"] = ba["x0"] - w; ba["ub"] = ba["x0"] + w
+    pts = P.ba_point_problems(ba)
+    orc = oracle_mod.OracleFunction.from_spec(ba); orc.set_x(ba["x0"])
+    point = np.ones(ba["V"], np.uint8); point[pts.vids] = 0
+    bounds = [orc.bounds(point, pts.fids[pts.fac_off[k]:pts.fac_off[k + 1]])[2] for k in range(pts.n)]
+    o = orc.solve_cgd_batch(pts.var_off, pts.vids, pts.fac_off, pts.fids, ba["x0"][pts.vids], 25, 3e-8)
+    for k, (lo, hi) in enumerate(bounds):
+        assert lo - tol * max(1.0, abs(lo)) <= o["f_end"][k] <= hi + tol * max(1.0, abs(hi)), (k, lo, o["f_end"][k], hi)
