@@ -579,7 +579,7 @@ double orc_solve_cgd_batch(void* h, int64_t nprobs, const int64_t* var_off, cons
       const double fe = orc_solve_cgd(hh, var_off[p + 1] - var_off[p], vids + var_off[p], fac_off[p + 1] - fac_off[p],
                                       fids + fac_off[p], x_inout + var_off[p], maxiters, ftol, &d, &it);
       if (f_end) f_end[p] = fe;
-      if (f_init) f_init[p] = fe - d;
+      if (f_init) f_init[p] = H(hh)->cgd->lastInitialFval;  // the value itself (fe - d would round)
       if (iters) iters[p] = it;
     }
   };

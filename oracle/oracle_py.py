@@ -14,6 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_RESTATED = os.path.join(_HERE, "liboracle.so")
 LIB_REFNRC = os.path.join(_HERE, "_ref", "liboracle_refnrc.so")
 LIB_FMA = os.path.join(_HERE, "liboracle_fma.so")
+LIB_DEVTRIG = os.path.join(_HERE, "liboracle_devtrig.so")
+_TWINS = {"recip": "liboracle_recip.so", "treefold": "liboracle_treefold.so", "devtrig_treefold": "liboracle_devtrig_treefold.so"}
 
 _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -98,14 +100,20 @@ _LIBS = {}
 
 def lib(variant="restated"):
     """variant: 'restated' (own-words NR driver), 'refnrc' (reference's minimize_nrc.h, oracle/_ref),
-    'fma' (restated, compiled with FMA contraction: the perturbation twin)."""
-    path = {"restated": LIB_RESTATED, "refnrc": LIB_REFNRC, "fma": LIB_FMA}[variant]
+    'fma' (restated, compiled with FMA contraction: a perturbation twin), 'devtrig' (restated, sin/cos = the device's
+    routines compiled for the host: what the strict device mode must match bit for bit), 'recip' / 'treefold' /
+    'devtrig_treefold' (further perturbation twins, see oracle/Makefile)."""
+    paths = {"restated": LIB_RESTATED, "refnrc": LIB_REFNRC, "fma": LIB_FMA, "devtrig": LIB_DEVTRIG}
+    paths.update({k: os.path.join(_HERE, v) for k, v in _TWINS.items()})
+    path = paths[variant]
     if path not in _LIBS:
         if not os.path.exists(path):
             if variant == "fma":
                 subprocess.check_call(["make", "-C", _HERE, "fma"], stdout=subprocess.DEVNULL)
+            elif variant in _TWINS:
+                subprocess.check_call(["make", "-C", _HERE, "twins"], stdout=subprocess.DEVNULL)
             else:
-                build()
+                build(force=True)
         _LIBS[path] = _load(path)
     return _LIBS[path]
 

@@ -48,9 +48,24 @@ namespace rdis { typedef double Numeric; }
 #include "nr_minimize.hpp"
 #endif
 
+#ifdef ORACLE_DEVICE_TRIG
+// "devtrig" twin: sin / cos are the DEVICE's routines compiled for the host (rdis_b200/csrc/trig.cuh: explicit
+// fma, bit-identical to the CUDA math library) instead of glibc's.  Every other operation of the path (+ - * /
+// sqrt, compares) is correctly rounded IEEE on both sides, so the strict device mode must reproduce this twin
+// BIT FOR BIT; the twin against the glibc build measures what a different libm alone does to a solve.
+#include "trig.cuh"  // found via -I rdis_b200/csrc
+#endif
+
 namespace oracle {
 
 typedef double Numeric;
+#ifdef ORACLE_DEVICE_TRIG
+inline Numeric orc_sin(Numeric x) { return rdisgpu::rdis_sin(x); }
+inline Numeric orc_cos(Numeric x) { return rdisgpu::rdis_cos(x); }
+#else
+inline Numeric orc_sin(Numeric x) { return std::sin(x); }
+inline Numeric orc_cos(Numeric x) { return std::cos(x); }
+#endif
 typedef long long VariableID;
 typedef long long FactorID;
 
@@ -302,7 +317,7 @@ class NonlinearProductFactor : public Factor {
       const Term& t = terms_[i];
       if (t.hasConstant()) val -= t.constant;
       if (t.hasExp()) val = power(val, t.exponent);
-      if (t.useSine) val = std::sin(val);
+      if (t.useSine) val = orc_sin(val);
       prod *= val;
     }
     Numeric fe = prod;
@@ -323,12 +338,12 @@ class NonlinearProductFactor : public Factor {
         const Numeric innerexp = power(inner, t.exponent);
         val = power(val, t.exponent - 1.0);
         val *= t.exponent;
-        if (t.useSine) val *= std::cos(innerexp);
+        if (t.useSine) val *= orc_cos(innerexp);
         prod *= val;
       } else {
         if (t.hasConstant()) val -= t.constant;
         if (t.hasExp()) val = power(val, t.exponent);
-        if (t.useSine) val = std::sin(val);
+        if (t.useSine) val = orc_sin(val);
         prod *= val;
       }
     }
@@ -452,8 +467,8 @@ inline Numeric ba_forward(const Numeric* x, Numeric obsx, Numeric obsy, BAForwar
   m.axp[1] = a[2] * P[0] - a[0] * P[2];
   m.axp[2] = a[0] * P[1] - a[1] * P[0];
   if (m.theta > 0.0) {
-    const Numeric c = std::cos(m.theta);
-    const Numeric s = std::sin(m.theta);
+    const Numeric c = orc_cos(m.theta);
+    const Numeric s = orc_sin(m.theta);
     const Numeric omc = 1 - c;
     m.adp = a[0] * P[0] + a[1] * P[1] + a[2] * P[2];
     for (int i = 0; i < 3; ++i) P[i] = P[i] * c + m.axp[i] * s + a[i] * omc * m.adp;  // :305-307
@@ -484,7 +499,7 @@ inline Numeric ba_gradient(const Numeric* x, Numeric obsx, Numeric obsy, Numeric
   const Numeric f = x[FOCAL], k1 = x[RDL_K1], k2 = x[RDL_K2];
   const Numeric t1 = 2.0 * (k1 + 2.0 * k2 * m.r2);
   const Numeric q[3] = {x[PT_X], x[PT_Y], x[PT_Z]};
-  const Numeric s = std::sin(m.theta), c = std::cos(m.theta);
+  const Numeric s = orc_sin(m.theta), c = orc_cos(m.theta);
   const Numeric* a = m.axis;
   const Numeric* P = m.P;
   const Numeric vnorm = m.theta;
@@ -495,9 +510,21 @@ inline Numeric ba_gradient(const Numeric* x, Numeric obsx, Numeric obsy, Numeric
 
   // Chain a 3-vector dP (derivative of the camera-frame point) through
   // divide -> distort -> residual, :418-422 and its repeats.
+#ifdef ORACLE_TWIN_RECIP
+  // perturbation twin (not reference behaviour): every quotient by P_z^2, P_z and |r| becomes a product with
+  // the denominator's reciprocal (<= 1 ulp away per quotient) — what round 1's device gradient did
+  const Numeric iP22 = 1.0 / P22, iP2 = 1.0 / P[2], ivn = 1.0 / vnorm;
+#define ORC_DIV_P22(x) ((x) * iP22)
+#define ORC_DIV_P2(x) ((x) * iP2)
+#define ORC_DIV_VN(x) ((x) * ivn)
+#else
+#define ORC_DIV_P22(x) ((x) / P22)
+#define ORC_DIV_P2(x) ((x) / P[2])
+#define ORC_DIV_VN(x) ((x) / vnorm)
+#endif
   auto through_projection = [&](const Numeric dP[3]) -> Numeric {
-    const Numeric dppx = (P[0] * dP[2] - P[2] * dP[0]) / P22;
-    const Numeric dppy = (P[1] * dP[2] - P[2] * dP[1]) / P22;
+    const Numeric dppx = ORC_DIV_P22(P[0] * dP[2] - P[2] * dP[0]);
+    const Numeric dppy = ORC_DIV_P22(P[1] * dP[2] - P[2] * dP[1]);
     const Numeric drx = m.res[0] * (J[0][0] * dppx + J[0][1] * dppy);
     const Numeric dry = m.res[1] * (J[1][0] * dppx + J[1][1] * dppy);
     return f * (drx + dry);
@@ -525,10 +552,10 @@ inline Numeric ba_gradient(const Numeric* x, Numeric obsx, Numeric obsy, Numeric
       if (j == mth) {
         const int o1 = (mth == 0) ? 1 : 0;
         const int o2 = (mth == 2) ? 1 : 2;
-        dadv[j] = (a[o1] * a[o1] + a[o2] * a[o2]) / vnorm;
+        dadv[j] = ORC_DIV_VN(a[o1] * a[o1] + a[o2] * a[o2]);
       } else {
         const int lo = std::min(j, mth), hi = std::max(j, mth);
-        dadv[j] = -a[lo] * a[hi] / vnorm;
+        dadv[j] = ORC_DIV_VN(-a[lo] * a[hi]);
       }
     }
     Numeric dP[3];
@@ -551,12 +578,12 @@ inline Numeric ba_gradient(const Numeric* x, Numeric obsx, Numeric obsy, Numeric
     grad[PT_X + j] = through_projection(dP);
   }
   // translation (:514-526)
-  grad[TRANS_X] = (m.res[0] * J[0][0] + m.res[1] * J[1][0]) * -f / P[2];
-  grad[TRANS_Y] = (m.res[0] * J[0][1] + m.res[1] * J[1][1]) * -f / P[2];
+  grad[TRANS_X] = ORC_DIV_P2((m.res[0] * J[0][0] + m.res[1] * J[1][0]) * -f);
+  grad[TRANS_Y] = ORC_DIV_P2((m.res[0] * J[0][1] + m.res[1] * J[1][1]) * -f);
   {
     const Numeric dpx = J[0][0] * P[0] + J[0][1] * P[1];
     const Numeric dpy = J[1][0] * P[0] + J[1][1] * P[1];
-    grad[TRANS_Z] = (m.res[0] * dpx + m.res[1] * dpy) * f / P22;
+    grad[TRANS_Z] = ORC_DIV_P22((m.res[0] * dpx + m.res[1] * dpy) * f);
   }
   // intrinsics (:528-538)
   grad[FOCAL] = m.res[0] * (m.dist * m.pp[0]) + m.res[1] * (m.dist * m.pp[1]);
@@ -610,6 +637,21 @@ class OptimizableFunction {
 
   // src/OptimizableFunction.cpp:95-135, MinSum semiring: Product = +, identity 0.
   Numeric evalFactors(const std::vector<Factor*>& fs, bool useCached = true) {
+#ifdef ORACLE_TWIN_TREEFOLD
+    // perturbation twin (not reference behaviour): the factor values are summed pairwise (a balanced tree, the
+    // shape of a GPU butterfly / block reduction) instead of left to right
+    std::vector<Numeric> vals;
+    vals.reserve(fs.size());
+    for (Factor* fp : fs) {
+      const Factor& f = *fp;
+      if (!f.isAssigned() && !f.areAllVarsAssigned()) continue;
+      vals.push_back(useCached ? f.eval(counters) : f.evalNoCache());
+    }
+    if (vals.empty()) return 0.0;
+    for (size_t stride = 1; stride < vals.size(); stride *= 2)
+      for (size_t i = 0; i + stride < vals.size(); i += 2 * stride) vals[i] = vals[i] + vals[i + stride];
+    return vals[0];
+#else
     Numeric feval = 0.0;
     for (Factor* fp : fs) {
       const Factor& f = *fp;
@@ -618,6 +660,7 @@ class OptimizableFunction {
       feval = feval + nf;
     }
     return feval;
+#endif
   }
   // src/OptimizableFunction.cpp:248-262
   void computeGradientOfSum(const std::vector<Factor*>& fs, PartialGradient& gradient) {
@@ -662,6 +705,7 @@ class SubspaceOptimizer {
   virtual Numeric optimize(const std::vector<Variable*>& vars, const std::vector<Factor*>& factors,
                            std::vector<Numeric>& xval, Numeric& deltaFval, bool printdbg) = 0;
   size_t lastIters = 0;
+  Numeric lastInitialFval = 0;  // initialFval of the last optimize() (test instrumentation)
 
  protected:
   void quickAssignVals(const std::vector<Variable*>& vars, const std::vector<Numeric>& xval, bool sanitize) {  // :38-53
@@ -737,11 +781,13 @@ class CGDSubspaceOptimizer : public SubspaceOptimizer {
     assert(xval.size() == vars.size());
     if (gdfs.empty()) {
       deltaFval = 0;
+      lastInitialFval = 0;
       return 0;
     }
     quickAssignVals(vars, xval, true);
     SubfunctionFD sfd{f, vars, gdfs, pgtmp};
     const Numeric initialFval = sfd(xval);
+    lastInitialFval = initialFval;
     const std::vector<Numeric> initxval(xval.begin(), xval.end());
 #ifdef ORACLE_USE_REFERENCE_NRC
     rdis::nrc::Frprmn<SubfunctionFD> gdmin(sfd, (int)maxiters, ftol);

@@ -9,6 +9,8 @@ import os
 
 import numpy as np
 
+from .problems import ProblemSet  # noqa: F401  (numpy only; re-exported)
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RDIS_B200_LIB") or os.path.join(_HERE, "librdis_b200.so")  # override: kernel experiments only
 
@@ -110,42 +112,18 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-class ProblemSet:
-    """Host-side description of a batch of subspace problems (CSR style)."""
-
-    def __init__(self, var_off, vids, fac_off, fids):
-        self.var_off = _arr(var_off, np.int64)
-        self.vids = _arr(vids, np.int32)
-        self.fac_off = _arr(fac_off, np.int64)
-        self.fids = _arr(fids, np.int64)
-        self.n = len(self.var_off) - 1
-        assert len(self.fac_off) == self.n + 1
-
-    @classmethod
-    def from_lists(cls, problems):
-        """problems: iterable of (vids, fids)."""
-        vo, fo, vs, fs = [0], [0], [], []
-        for v, f in problems:
-            vs.append(np.asarray(v, np.int32)); fs.append(np.asarray(f, np.int64))
-            vo.append(vo[-1] + len(v)); fo.append(fo[-1] + len(f))
-        return cls(vo, np.concatenate(vs) if vs else np.zeros(0, np.int32), fo,
-                   np.concatenate(fs) if fs else np.zeros(0, np.int64))
-
-    def subset(self, idx):
-        return ProblemSet.from_lists([(self.vids[self.var_off[i]:self.var_off[i + 1]],
-                                       self.fids[self.fac_off[i]:self.fac_off[i + 1]]) for i in idx])
-
-    def c_array(self, x0=None):
-        arr = (Problem * self.n)()
-        vbase, fbase = self.vids.ctypes.data, self.fids.ctypes.data
-        xbase = None if x0 is None else x0.ctypes.data
-        for i in range(self.n):
-            arr[i].nv = int(self.var_off[i + 1] - self.var_off[i])
-            arr[i].nf = int(self.fac_off[i + 1] - self.fac_off[i])
-            arr[i].vid = vbase + 4 * int(self.var_off[i])
-            arr[i].fid = fbase + 8 * int(self.fac_off[i])
-            arr[i].x0 = None if xbase is None else xbase + 8 * int(self.var_off[i])
-        return arr
+def problem_array(ps, x0=None):
+    """The rdisgpu_problem array of a ProblemSet (pointers into its arrays: keep `ps` and `x0` alive)."""
+    arr = (Problem * ps.n)()
+    vbase, fbase = ps.vids.ctypes.data, ps.fids.ctypes.data
+    xbase = None if x0 is None else x0.ctypes.data
+    for i in range(ps.n):
+        arr[i].nv = int(ps.var_off[i + 1] - ps.var_off[i])
+        arr[i].nf = int(ps.fac_off[i + 1] - ps.fac_off[i])
+        arr[i].vid = vbase + 4 * int(ps.var_off[i])
+        arr[i].fid = fbase + 8 * int(ps.fac_off[i])
+        arr[i].x0 = None if xbase is None else xbase + 8 * int(ps.var_off[i])
+    return arr
 
 
 class Context:
@@ -348,7 +326,7 @@ class Context:
         """rdisgpu_solve_cgd (array of rdisgpu_problem / rdisgpu_result structs): same results."""
         ps = problems
         x0a = None if x0 is None else _arr(x0, np.float64)
-        parr = ps.c_array(x0a)
+        parr = problem_array(ps, x0a)
         xout = np.empty(len(ps.vids))
         rarr = (Result * ps.n)()
         for i in range(ps.n):

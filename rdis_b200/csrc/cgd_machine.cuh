@@ -11,9 +11,15 @@
 // runs an identical copy of the machine on identical inputs, so no broadcast is needed.
 //
 // Evaluations the reference repeats at an already-evaluated point (fp=func(p) at :634 after the
-// caller's own evaluation, fa=func(0) at :88, fx=funcd(bx) at :315) are not re-requested: the device
-// objective is a deterministic function of the point, so the known value is reused.  All scalar
-// arithmetic keeps the operand order of the cited lines.
+// caller's own evaluation, fa=func(0) at :88, fx=funcd(bx) at :315) are not re-requested where the
+// objective is a deterministic function of the point.  It is NOT one under the reference's value cache:
+// Variable::assign suppresses the dirty notification of a move below 1e-12 (src/Variable.cpp:69-73), so
+// Factor::eval may return the value of an earlier, nearby point (src/Factor.cpp:110-119), and the
+// re-evaluation at :88 may then see a different number than the line search left in fret.  A machine started
+// `faithful` therefore requests fa = func(0) as well (PH_BR_FA), and every kernel takes fx at :315 from the
+// evaluation that comes back, so a group that emulates the cache (every solve kernel does) follows the
+// reference's evaluation sequence event for event.  All scalar arithmetic keeps the operand order of the
+// cited lines.
 //
 // The header is __host__ __device__ clean: tests/native/machine_harness.cpp compiles it with g++ and
 // demands bit-identical request sequences against the reference's own header (oracle/_ref).
@@ -70,10 +76,11 @@ struct CgdMachine {
   int db_iter;
   int br_iter;
   bool small_step;
+  bool faithful;  // request fa = func(ax = 0) at the top of every line search (minimize_nrc.h:88)
 
   enum Phase : int {
     PH_INIT = 0,
-    PH_BR_FB, PH_BR_FC, PH_BR_PARAB_INSIDE, PH_BR_PARAB_BEYOND, PH_BR_PARAB_BEYOND2, PH_BR_SHIFT,
+    PH_BR_FA, PH_BR_FB, PH_BR_FC, PH_BR_PARAB_INSIDE, PH_BR_PARAB_BEYOND, PH_BR_PARAB_BEYOND2, PH_BR_SHIFT,
     PH_DB_FIRST, PH_DB_EVAL,
     PH_MOVED, PH_GRAD, PH_DIRECTED
   };
@@ -82,7 +89,8 @@ struct CgdMachine {
 
   RDIS_HD static double pick_max(double p, double q) { return (p < q) ? q : p; }  // std::max, :60-63
 
-  RDIS_HD void start(int maxiters_, double ftol_) {
+  RDIS_HD void start(int maxiters_, double ftol_, bool faithful_ = false) {
+    faithful = faithful_;
     maxiters = maxiters_;
     ftol = ftol_;
     fret = 1.7976931348623157e308;  // std::numeric_limits<double>::max(), :609
@@ -172,14 +180,18 @@ struct CgdMachine {
     ++n_slope;
   }
 
-  // linmin(): bracket(0, 1) then dbrent (:496-507).  fa = f(p + 0*xi) = fp is known.
+  // linmin(): bracket(0, 1) then dbrent (:496-507).  fa = f(p + 0*xi): fp unless the group emulates the
+  // reference's value cache (see the header comment), in which case it is asked for.
   RDIS_HD void begin_line_search() {
     iter = its;  // :645
     ax = 0.0;
     bx = 1.0;
     fa = fp;
     br_iter = 0;
-    ask_value(bx, PH_BR_FB);
+    if (faithful)
+      ask_value(ax, PH_BR_FA);
+    else
+      ask_value(bx, PH_BR_FB);
   }
 
   RDIS_HD void line_search_done(double xmin, double fmin) {
@@ -256,6 +268,10 @@ struct CgdMachine {
   RDIS_HD void advance(double f, double slope) {
     int stage = SG_NONE;
     switch (phase) {
+      case PH_BR_FA:  // :88
+        fa = f;
+        ask_value(bx, PH_BR_FB);
+        break;
       case PH_BR_FB: {  // :89-98
         fb = f;
         if (fb > fa) {

@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "trig.cuh"
+
 namespace rdisgpu {
 
 enum FactorKind : int { KIND_NONE = -1, KIND_NLPF = 0, KIND_BA = 1 };
@@ -64,6 +66,11 @@ struct GraphView {
   // constant overlay (nullable)
   const uint8_t* fconst_on;
   const double* fconst_val;
+  // the reference's per-factor value cache (src/Factor.h:228-234) and Variable::assign's change flags, strict mode
+  // only (nullable): fcache f64[F] last value Factor::eval computed, fdirty u8[F], vchg u8[V]
+  double* fcache;
+  uint8_t* fdirty;
+  uint8_t* vchg;
   // scratch
   double* gedge;
   double* gvec;
@@ -78,108 +85,31 @@ __device__ __forceinline__ double clamp_to_domain(double v, double2 d) {
   return d.y;
 }
 
-// Value of variable `vid` at line-search abscissa alpha.  Frozen variables (direction slot NaN)
-// are read as stored; variables of the running solve are p + alpha*xi clamped into their
-// domain (SubfunctionFD::quickAssignVals, src/optimizers/CGDSubspaceOptimizer.cpp:160-184).
+// Value of variable `vid` as a factor sees it.  kMode 0 / 1: frozen variables (direction slot NaN) are read as
+// stored; variables of the running solve are p (mode 0) or p + alpha*xi (mode 1) clamped into their domain
+// (SubfunctionFD::quickAssignVals, src/optimizers/CGDSubspaceOptimizer.cpp:160-184).  p + alpha*xi is a product
+// rounded, then a sum rounded — Df1dim's xt[j] = p[j] + x*xi[j] (minimize_nrc.h:434) on a target without FMA.
+// kMode 2: the ASSIGNED value (the dense mirror xval = Variable::eval() of the reference): the strict kernels
+// assign first and evaluate afterwards, like the reference.
 // `dirv` receives xi (0 for frozen variables) so callers can form directional derivatives.
-template <bool kAlongLine>
+constexpr int kAtP = 0, kOnLine = 1, kAssigned = 2;
+template <int kMode>
 __device__ __forceinline__ double load_var(const GraphView& G, int32_t vid, double alpha, double& dirv) {
+  if (kMode == kAssigned) {
+    dirv = 0.0;
+    return G.xval[vid];
+  }
   const double2 xb = G.xbd[vid];
   if (xb.y != xb.y) {  // frozen
     dirv = 0.0;
     return xb.x;
   }
   dirv = xb.y;
-  const double raw = kAlongLine ? __fma_rn(alpha, xb.y, xb.x) : xb.x;  // explicit: every kernel forms p + alpha*xi the same way
+  const double raw = (kMode == kOnLine) ? __dadd_rn(xb.x, __dmul_rn(alpha, xb.y)) : xb.x;  // never contracted
   return clamp_to_domain(raw, __ldg(&G.dom[vid]));
 }
 
-// ------------------------------------------------------------------------------------------
-// sin / cos for the NonlinearProductFactor terms.
-// Same algorithm, constants and operation order as the CUDA math library's fast path (3-constant
-// Cody-Waite reduction by pi/2, degree-13 / degree-14 minimax kernels), so results are bit-identical
-// to sin() / cos() — tests/native/trig_check.cu demands it — but (a) the kernel coefficients are
-// immediates instead of three 16-byte loads from a global table per call, (b) the body is
-// straight-line, so the two edges a thread owns interleave, and (c) sin and cos of one argument
-// (value term + its derivative) share the reduction.  |x| >= 2^31, inf and NaN take the library call.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double f64_bits(unsigned long long b) { return __longlong_as_double((long long)b); }
-
-__device__ __forceinline__ void rdis_trig_reduce(double x, double& r, int& q) {
-  q = __double2int_rn(x * f64_bits(0x3FE45F306DC9C883ULL));  // x * 2/pi, round to nearest
-  const double j = (double)q;
-  r = __fma_rn(j, f64_bits(0xBFF921FB54442D18ULL), x);
-  r = __fma_rn(j, f64_bits(0xBC91A62633145C00ULL), r);
-  r = __fma_rn(j, f64_bits(0xB97B839A252049C0ULL), r);
-}
-// sin kernel on the reduced argument: r + r * P(r^2)
-__device__ __forceinline__ double rdis_sin_kernel(double r, double z) {
-  double p = f64_bits(0x3DE5DB65F9785EBAULL);
-  p = __fma_rn(p, z, f64_bits(0xBE5AE5F12CB0D246ULL));
-  p = __fma_rn(p, z, f64_bits(0x3EC71DE369ACE392ULL));
-  p = __fma_rn(p, z, f64_bits(0xBF2A01A019DB62A1ULL));
-  p = __fma_rn(p, z, f64_bits(0x3F81111111110818ULL));
-  p = __fma_rn(p, z, f64_bits(0xBFC5555555555554ULL));
-  p = __fma_rn(p, z, 0.0);
-  return __fma_rn(p, r, r);
-}
-// cos kernel: 1 + r^2 * Q(r^2)
-__device__ __forceinline__ double rdis_cos_kernel(double z) {
-  double p = f64_bits(0xBDA8FF8320FD8164ULL);
-  p = __fma_rn(p, z, f64_bits(0x3E21EEA7C1EF8528ULL));
-  p = __fma_rn(p, z, f64_bits(0xBE927E4F8E06E6D9ULL));
-  p = __fma_rn(p, z, f64_bits(0x3EFA01A019DDBCE9ULL));
-  p = __fma_rn(p, z, f64_bits(0xBF56C16C16C15D47ULL));
-  p = __fma_rn(p, z, f64_bits(0x3FA5555555555551ULL));
-  p = __fma_rn(p, z, -0.5);
-  return __fma_rn(p, z, 1.0);
-}
-// one kernel evaluation with the coefficient set chosen by the quadrant parity (what the library does)
-__device__ __forceinline__ double rdis_trig_select(double r, int q) {
-  const bool odd = (q & 1) != 0;
-  const double z = __dmul_rn(r, r);
-  double p = odd ? f64_bits(0xBDA8FF8320FD8164ULL) : f64_bits(0x3DE5DB65F9785EBAULL);
-  p = __fma_rn(p, z, odd ? f64_bits(0x3E21EEA7C1EF8528ULL) : f64_bits(0xBE5AE5F12CB0D246ULL));
-  p = __fma_rn(p, z, odd ? f64_bits(0xBE927E4F8E06E6D9ULL) : f64_bits(0x3EC71DE369ACE392ULL));
-  p = __fma_rn(p, z, odd ? f64_bits(0x3EFA01A019DDBCE9ULL) : f64_bits(0xBF2A01A019DB62A1ULL));
-  p = __fma_rn(p, z, odd ? f64_bits(0xBF56C16C16C15D47ULL) : f64_bits(0x3F81111111110818ULL));
-  p = __fma_rn(p, z, odd ? f64_bits(0x3FA5555555555551ULL) : f64_bits(0xBFC5555555555554ULL));
-  p = __fma_rn(p, z, odd ? -0.5 : 0.0);
-  const double v = odd ? __fma_rn(p, z, 1.0) : __fma_rn(p, r, r);
-  return (q & 2) ? (0.0 - v) : v;
-}
-__device__ __forceinline__ double rdis_sin(double x) {
-  if (!(fabs(x) < 2147483648.0)) return sin(x);
-  double r;
-  int q;
-  rdis_trig_reduce(x, r, q);
-  return rdis_trig_select(r, q);
-}
-__device__ __forceinline__ double rdis_cos(double x) {
-  if (!(fabs(x) < 2147483648.0)) return cos(x);
-  double r;
-  int q;
-  rdis_trig_reduce(x, r, q);
-  return rdis_trig_select(r, q + 1);
-}
-// s = sin(x), c = cos(x), each bit-identical to the separate calls
-__device__ __forceinline__ void rdis_sincos(double x, double& s, double& c) {
-  if (!(fabs(x) < 2147483648.0)) {
-    s = sin(x);
-    c = cos(x);
-    return;
-  }
-  double r;
-  int q;
-  rdis_trig_reduce(x, r, q);
-  const double z = __dmul_rn(r, r);
-  const double sk = rdis_sin_kernel(r, z), ck = rdis_cos_kernel(z);
-  const double sv = (q & 1) ? ck : sk;
-  const double cv = (q & 1) ? sk : ck;
-  s = (q & 2) ? (0.0 - sv) : sv;
-  c = ((q + 1) & 2) ? (0.0 - cv) : cv;
-}
-
+// sin / cos: trig.cuh (bit-identical to the CUDA math library, and host-compilable for the oracle's devtrig twin)
 __device__ __forceinline__ double rdis_power(double val, double e) {
   if (e == 0.) return 1.;
   if (e == 1.) return val;
@@ -194,7 +124,7 @@ struct NlpfOps {
   static constexpr int kMaxArityFast = 4;  // arities above this take the O(arity^2) recompute path (the generators stop at 4; 8 cost 242 registers)
 
   // f_j at abscissa alpha; if kSlope also d f_j / d alpha = sum_i (d f_j/d x_i) * xi_i.
-  template <bool kAlongLine>
+  template <int kAlongLine>
   __device__ static __forceinline__ double value(const GraphView& G, int64_t fid, double alpha, bool kSlope,
                                                  double& slope) {
     const int32_t e0 = __ldg(&G.rowptr[fid]);
@@ -263,6 +193,7 @@ struct NlpfOps {
 
   // All partials of factor fid at the current point (alpha ignored, direction ignored):
   // writes gedge[e] for e in the factor's row; returns the factor value.
+  template <int kMode = kAtP>
   __device__ static __forceinline__ double gradient(const GraphView& G, int64_t fid, double* gout /*row base*/) {
     const int32_t e0 = __ldg(&G.rowptr[fid]);
     const int32_t e1 = __ldg(&G.rowptr[fid + 1]);
@@ -275,7 +206,7 @@ struct NlpfOps {
 #pragma unroll
       for (int i = 0; i < kMaxArityFast; ++i) {
         if (i < ar) {
-          term<false>(G, e0 + i, 0.0, t[i], dt[i], plain[i], dir[i]);
+          term<kMode>(G, e0 + i, 0.0, t[i], dt[i], plain[i], dir[i]);
           prod *= t[i];
         }
       }
@@ -301,9 +232,9 @@ struct NlpfOps {
     for (int32_t ei = e0; ei < e1; ++ei) {
       double ti, dti, diri;
       bool pl;
-      term<false>(G, ei, 0.0, ti, dti, pl, diri);
+      term<kMode>(G, ei, 0.0, ti, dti, pl, diri);
       prod *= ti;
-      gout[ei - e0] = partial<false>(G, e0, e1, ei, 0.0) * c;
+      gout[ei - e0] = partial<kMode>(G, e0, e1, ei, 0.0) * c;
     }
     return prod * c;
   }
@@ -348,10 +279,30 @@ struct NlpfOps {
     return acc;
   }
 
+  // ---- strict kernels (strict_kernels.cuh): evaluate from the ASSIGNED state, as the reference does ----
+  __device__ static __forceinline__ double strict_value(const GraphView& G, int64_t fid) {
+    double sl;
+    return value<kAssigned>(G, fid, 0.0, false, sl);
+  }
+  __device__ static __forceinline__ double strict_gradient(const GraphView& G, int64_t fid, double* gout) {
+    return gradient<kAssigned>(G, fid, gout);
+  }
+  // did Variable::assign notify this factor (a variable of the running solve moved by >= 1e-12)?
+  __device__ static __forceinline__ bool any_own_changed(const GraphView& G, int64_t fid) {
+    const int32_t e0 = __ldg(&G.rowptr[fid]), e1 = __ldg(&G.rowptr[fid + 1]);
+    bool chg = false;
+    for (int32_t e = e0; e < e1; ++e) {
+      const int32_t v = __ldg(&G.evid[e]);
+      const double d = G.xbd[v].y;
+      if (d == d && G.vchg[v]) chg = true;
+    }
+    return chg;
+  }
+
  private:
   // value term t = [sin]((x-k)^e) and the own-slot derivative factor e*(x-k)^(e-1)*[cos((x-k)^e)];
   // `plain` marks the e==1, no-sine case the reference skips (derivative 1, constant not subtracted).
-  template <bool kAlongLine>
+  template <int kAlongLine>
   __device__ static __forceinline__ void term(const GraphView& G, int32_t e, double alpha, double& t, double& dt,
                                               bool& plain, double& dirv) {
     const double xv = load_var<kAlongLine>(G, __ldg(&G.evid[e]), alpha, dirv);
@@ -391,7 +342,7 @@ struct NlpfOps {
     dt = dv;
   }
   // getDerivative for the variable of edge `etarget` (recompute path, any arity)
-  template <bool kAlongLine>
+  template <int kAlongLine>
   __device__ static __forceinline__ double partial(const GraphView& G, int32_t e0, int32_t e1, int32_t etarget,
                                                    double alpha) {
     double pe = 1.0;
@@ -406,6 +357,26 @@ struct NlpfOps {
       }
     }
     return pe;
+  }
+};
+
+// Quotients by a denominator that is used many times.  The reference divides (IEEE, correctly rounded).
+//   kExact     a / b, the division instruction sequence every time (strict kernels)
+//   kCorrected the reciprocal y = RN(1/b) once, then q = RN(a*y), r = a - b*q (exact, one fma), RN(q + r*y):
+//              the correction step the division sequence itself ends with.  The result is the correctly rounded
+//              quotient unless a/b lies within 3*2^-54 ulp of a rounding boundary after a first guess more than one
+//              ulp off (probability ~2^-52 per quotient; tests/test_gpu_parity.py counts zero mismatches against
+//              `/` on 2^28 operand pairs), or at singular operands (b = 0, inf; signed zeros).
+enum DivMode : int { kExact = 0, kCorrected = 1 };
+template <int kDiv>
+struct QuotBy {
+  double b, y;
+  __device__ __forceinline__ explicit QuotBy(double b_) : b(b_), y(kDiv == kExact ? 0.0 : 1.0 / b_) {}
+  __device__ __forceinline__ double operator()(double a) const {
+    if (kDiv == kExact) return a / b;
+    const double q = __dmul_rn(a, y);
+    const double r = __fma_rn(-b, q, a);
+    return __fma_rn(r, y, q);
   }
 };
 
@@ -436,7 +407,7 @@ struct BaOps {
     }
     m.theta = nrm;
     if (nrm > 0.0) {
-      sincos(nrm, &m.s, &m.c);
+      rdis_sincos(nrm, m.s, m.c);  // bit-identical to sincos() (tests/native/trig_check.cu), inlined and host-reproducible
     } else {
       m.s = 0.0; m.c = 1.0;  // sin(0), cos(0): what the gradient code recomputes from theta
     }
@@ -477,7 +448,10 @@ struct BaOps {
     return project(x, ob, m);
   }
 
-  // 12 partials in slot order.
+  // 12 partials in slot order.  The reference divides by P_z^2, P_z and |r| 24 times per observation
+  // (through_projection is expanded six times, BundleAdjustmentFactor.cpp:418-422 and repeats); QuotBy keeps those
+  // quotients (correctly rounded) while paying for three reciprocals.
+  template <int kDiv = kCorrected>
   __device__ static __forceinline__ void partials(const double* x, const Fwd& m, double* g) {
     const double f = x[6], k1 = x[7], k2 = x[8];
     const double q[3] = {x[9], x[10], x[11]};
@@ -492,14 +466,10 @@ struct BaOps {
     const double J00 = m.dist + t1 * pp00, J01 = t1 * pp01, J10 = t1 * pp01, J11 = m.dist + t1 * pp11;
     const double omc = (1 - c);
 
-    // The reference divides by P_z^2, P_z and |r| 24 times per observation (chain() is called six times);
-    // here each denominator is inverted once and multiplied: <= 1 ulp away per quotient, 21 fewer fp64
-    // division sequences on the evaluation's dependency chain.  (The VALUE path, project(), keeps the
-    // reference's divisions.)
-    const double iP22 = 1.0 / P22, iP2 = 1.0 / P[2], ivn = 1.0 / vnorm;
+    const QuotBy<kDiv> byP22(P22), byP2(P[2]), byVn(vnorm);
     auto chain = [&](double dP0, double dP1, double dP2) -> double {
-      const double dppx = (P[0] * dP2 - P[2] * dP0) * iP22;
-      const double dppy = (P[1] * dP2 - P[2] * dP1) * iP22;
+      const double dppx = byP22(P[0] * dP2 - P[2] * dP0);
+      const double dppy = byP22(P[1] * dP2 - P[2] * dP1);
       const double drx = m.res0 * (J00 * dppx + J01 * dppy);
       const double dry = m.res1 * (J10 * dppx + J11 * dppy);
       return f * (drx + dry);
@@ -521,33 +491,33 @@ struct BaOps {
 
     // rotation vector, component x
     {
-      const double d0 = (a[1] * a[1] + a[2] * a[2]) * ivn;
-      const double d1 = -a[0] * a[1] * ivn;
-      const double d2 = -a[0] * a[2] * ivn;
+      const double d0 = byVn(a[1] * a[1] + a[2] * a[2]);
+      const double d1 = byVn(-a[0] * a[1]);
+      const double d2 = byVn(-a[0] * a[2]);
       g[0] = chain(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[0], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[0],
                      A20 * d0 + A21 * d1 + A22 * d2 + T2 * a[0]);
     }
     {
-      const double d0 = -a[0] * a[1] * ivn;
-      const double d1 = (a[0] * a[0] + a[2] * a[2]) * ivn;
-      const double d2 = -a[1] * a[2] * ivn;
+      const double d0 = byVn(-a[0] * a[1]);
+      const double d1 = byVn(a[0] * a[0] + a[2] * a[2]);
+      const double d2 = byVn(-a[1] * a[2]);
       g[1] = chain(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[1], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[1],
                      A20 * d0 + A21 * d1 + A22 * d2 + T2 * a[1]);
     }
     {
-      const double d0 = -a[0] * a[2] * ivn;
-      const double d1 = -a[1] * a[2] * ivn;
-      const double d2 = (a[0] * a[0] + a[1] * a[1]) * ivn;
+      const double d0 = byVn(-a[0] * a[2]);
+      const double d1 = byVn(-a[1] * a[2]);
+      const double d2 = byVn(a[0] * a[0] + a[1] * a[1]);
       g[2] = chain(A00 * d0 + A01 * d1 + A02 * d2 + T0 * a[2], A10 * d0 + A11 * d1 + A12 * d2 + T1 * a[2],
                      A20 * d0 + A21 * d1 + A22 * d2 + T2 * a[2]);
     }
     // translation
-    g[3] = (m.res0 * J00 + m.res1 * J10) * -f * iP2;
-    g[4] = (m.res0 * J01 + m.res1 * J11) * -f * iP2;
+    g[3] = byP2((m.res0 * J00 + m.res1 * J10) * -f);
+    g[4] = byP2((m.res0 * J01 + m.res1 * J11) * -f);
     {
       const double dpx = J00 * P[0] + J01 * P[1];
       const double dpy = J10 * P[0] + J11 * P[1];
-      g[5] = (m.res0 * dpx + m.res1 * dpy) * f * iP22;
+      g[5] = byP22((m.res0 * dpx + m.res1 * dpy) * f);
     }
     // intrinsics
     g[6] = m.res0 * (m.dist * m.pp0) + m.res1 * (m.dist * m.pp1);
@@ -566,7 +536,7 @@ struct BaOps {
     return (s < 9) ? (9 * cam + s) : (9 * G.ncams + 3 * pt + (s - 9));
   }
 
-  template <bool kAlongLine>
+  template <int kAlongLine>
   __device__ static __forceinline__ double value(const GraphView& G, int64_t fid, double alpha, bool kSlope,
                                                  double& slope) {
     const int32_t cam = __ldg(&G.cam[fid]);
@@ -591,20 +561,40 @@ struct BaOps {
     return fv;
   }
 
+  template <int kMode = kAtP, int kDiv = kCorrected>
   __device__ static __forceinline__ double gradient(const GraphView& G, int64_t fid, double* gout) {
     const int32_t cam = __ldg(&G.cam[fid]);
     const int32_t pt = __ldg(&G.pt[fid]);
     const double2 ob = __ldg(&G.obs[fid]);
     double x[12], dirv;
 #pragma unroll
-    for (int s = 0; s < 12; ++s) x[s] = load_var<false>(G, slot_vid(G, cam, pt, s), 0.0, dirv);
+    for (int s = 0; s < 12; ++s) x[s] = load_var<kMode>(G, slot_vid(G, cam, pt, s), 0.0, dirv);
     Fwd m;
     const double fv = forward(x, ob, m);
     double g[12];
-    partials(x, m, g);
+    partials<kDiv>(x, m, g);
 #pragma unroll
     for (int s = 0; s < 12; ++s) gout[s] = g[s];
     return fv;
+  }
+  __device__ static __forceinline__ double strict_value(const GraphView& G, int64_t fid) {
+    double sl;
+    return value<kAssigned>(G, fid, 0.0, false, sl);
+  }
+  __device__ static __forceinline__ double strict_gradient(const GraphView& G, int64_t fid, double* gout) {
+    return gradient<kAssigned, kExact>(G, fid, gout);
+  }
+  __device__ static __forceinline__ bool any_own_changed(const GraphView& G, int64_t fid) {
+    const int32_t cam = __ldg(&G.cam[fid]);
+    const int32_t pt = __ldg(&G.pt[fid]);
+    bool chg = false;
+#pragma unroll
+    for (int s = 0; s < 12; ++s) {
+      const int32_t v = slot_vid(G, cam, pt, s);
+      const double d = G.xbd[v].y;
+      if (d == d && G.vchg[v]) chg = true;
+    }
+    return chg;
   }
   __device__ static __forceinline__ int64_t edge_base(const GraphView&, int64_t fid) { return fid * 12; }
   __device__ static __forceinline__ int arity(const GraphView&, int64_t) { return 12; }

@@ -22,6 +22,7 @@
 #include "components.cuh"
 #include "nlpf_resident.cuh"
 #include "bounds_kernels.cuh"
+#include "strict_kernels.cuh"
 
 using namespace rdisgpu;
 
@@ -110,6 +111,9 @@ struct rdisgpu_ctx {
   int32_t mark_epoch = 0;
   rdisgpu_batch* scratch_batch = nullptr;  // reused by the one-shot solve entry points
   bool generic_only = false;  // rdisgpu_set_option("generic_only"): bypass the BA block kernels (tests)
+  bool strict = false;        // rdisgpu_set_option("strict"): every solve through strict_kernels.cuh (bit-exact parity instrument)
+  DevBuf<double> fcache;      // strict mode: the reference's per-factor value cache ...
+  DevBuf<uint8_t> fdirty, vchg;  // ... its dirty flags, and Variable::assign's change flags
   GraphView gv;
 
   // scratch for the sweep / state calls
@@ -175,6 +179,7 @@ struct rdisgpu_batch {
   int cam_C = 0, cam_T = 0;  // chosen at the first solve (needs the occupancy query)
   DevBuf<uint16_t> res_gvinc;  // ... and their variable-major incidence lists
   DevBuf<double> res_gscr;  // resident NLPF class: per-edge partials, one slice per problem
+  DevBuf<double> strict_dscr;  // strict mode: Df1dim's derivative vector, one slice per problem
   int res_small_smem = 0;
   int res_smem = 0;  // dynamic shared memory of the resident NLPF class (largest layout in the batch)
   int last_launches = 0;
@@ -217,6 +222,9 @@ void fill_view(rdisgpu_ctx* c) {
   g.crow = c->crow.p; g.cfac = c->cfac.p; g.prow = c->prow.p; g.pfac = c->pfac.p;
   g.fconst_on = c->has_fconst ? c->fconst_on.p : nullptr;
   g.fconst_val = c->has_fconst ? c->fconst_val.p : nullptr;
+  g.fcache = c->strict ? c->fcache.p : nullptr;
+  g.fdirty = c->strict ? c->fdirty.p : nullptr;
+  g.vchg = c->strict ? c->vchg.p : nullptr;
   g.gedge = c->gedge.p; g.gvec = c->gvec.p; g.hvec = c->hvec.p; g.xsave = c->xsave.p; g.fstamp = c->fstamp.p;
 }
 
@@ -313,6 +321,23 @@ int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return RDISGPU_ERR_ARG;
   if (std::strcmp(name, "generic_only") == 0) {
     ctx->generic_only = (value != 0);
+    return RDISGPU_OK;
+  }
+  if (std::strcmp(name, "strict") == 0) {
+    if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "set_option: strict needs a finalized context");
+    if (value != 0 && !ctx->strict) {
+      // the reference's Factor objects start dirty (nothing evaluated yet) and its Variables unassigned: the first
+      // assign of every variable notifies its factors, whatever the value
+      CK(cudaSetDevice(ctx->device));
+      CK(ctx->fcache.ensure((size_t)ctx->F));
+      CK(ctx->fdirty.ensure((size_t)ctx->F));
+      CK(ctx->vchg.ensure((size_t)ctx->V));
+      CK(cudaMemsetAsync(ctx->fcache.p, 0, (size_t)ctx->F * sizeof(double), ctx->stream));
+      CK(cudaMemsetAsync(ctx->fdirty.p, 1, (size_t)ctx->F, ctx->stream));
+      CK(cudaMemsetAsync(ctx->vchg.p, 0, (size_t)ctx->V, ctx->stream));
+    }
+    ctx->strict = (value != 0);
+    fill_view(ctx);
     return RDISGPU_OK;
   }
   if (std::strcmp(name, "resident_threads") == 0) {
@@ -557,7 +582,10 @@ int rdisgpu_set_x(rdisgpu_ctx* ctx, int64_t n, const int32_t* vid, const double*
     if (vid && !is_device_ptr(vid)) return ctx->fail(RDISGPU_ERR_ARG, "set_x: device x needs device (or null) vid");
     const int threads = 256;
     const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 65535);
-    scatter_x_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->gv, n, vid, x);
+    if (ctx->strict)
+      scatter_x_strict_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->gv, n, vid, x);
+    else
+      scatter_x_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->gv, n, vid, x);
     ++ctx->launches;
     CK(cudaGetLastError());
     return RDISGPU_OK;
@@ -574,7 +602,10 @@ int rdisgpu_set_x(rdisgpu_ctx* ctx, int64_t n, const int32_t* vid, const double*
   }
   const int threads = 256;
   const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 65535);
-  scatter_x_kernel<<<blocks, threads, 0, s>>>(ctx->gv, n, vid ? ctx->s_i32a.p : nullptr, ctx->s_f64a.p);
+  if (ctx->strict)
+    scatter_x_strict_kernel<<<blocks, threads, 0, s>>>(ctx->gv, n, vid ? ctx->s_i32a.p : nullptr, ctx->s_f64a.p);
+  else
+    scatter_x_kernel<<<blocks, threads, 0, s>>>(ctx->gv, n, vid ? ctx->s_i32a.p : nullptr, ctx->s_f64a.p);
   ++ctx->launches;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));  // x / vid are caller-owned pageable memory
@@ -636,6 +667,10 @@ int rdisgpu_set_factor_const(rdisgpu_ctx* ctx, int64_t n, const int64_t* fid, co
   set_fconst_kernel<<<blocks, threads, 0, s>>>(ctx->fconst_on.p, ctx->fconst_val.p, n, ctx->s_i32a.p, ctx->s_f64a.p,
                                                (const uint8_t*)ctx->s_i32b.p);
   ++ctx->launches;
+  if (ctx->strict) {  // Factor::setAssignedConstant(false): the factor must be recomputed at its next eval()
+    unset_const_dirty_kernel<<<blocks, threads, 0, s>>>(ctx->fdirty.p, n, ctx->s_i32a.p, (const uint8_t*)ctx->s_i32b.p);
+    ++ctx->launches;
+  }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
   return RDISGPU_OK;
@@ -1174,6 +1209,18 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
   bv.gvinc = b->res_gvinc.p;
   GraphView gv = ctx->gv;
   int launches = 0;
+  if (ctx->strict) {  // the parity instrument: one kernel for every component shape, the reference's own operation order
+    CK(b->strict_dscr.ensure((size_t)std::max<int64_t>(b->total_nv, 1)));
+    if (ctx->kind == KIND_NLPF)
+      solve_strict_kernel<NlpfOps><<<(unsigned)b->nprobs, kStrictThreads, 0, s>>>(gv, bv, b->strict_dscr.p, maxiters, ftol);
+    else
+      solve_strict_kernel<BaOps><<<(unsigned)b->nprobs, kStrictThreads, 0, s>>>(gv, bv, b->strict_dscr.p, maxiters, ftol);
+    CK(cudaGetLastError());
+    b->last_launches = 1;
+    ctx->launches += 1;
+    b->solved = true;
+    return RDISGPU_OK;
+  }
   if (b->n_pt_warps > 0) {
     solve_ba_points_kernel<<<b->n_pt_warps, 32, 0, s>>>(gv, bv, b->d_pt_order, b->d_pt_tasks, maxiters, ftol);
     ++launches;

@@ -8,13 +8,39 @@
     ba_domains(...)      BundleAdjustmentFunction::setDomain, src/bundleadjust/BundleAdjustmentFunction.cpp:402-477
 and the sibling-component problem sets the recursive decomposer produces on them
 (Component::createChildren, src/Component.cpp:508-549; gdfs builder, src/RDISOptimizer.cpp:1049-1059).
-Host-side numpy only; nothing here evaluates a factor.
+Host-side numpy only; nothing here evaluates a factor, and the module has no import inside the package, so
+bench.py's reference arm can load it by path without mapping librdis_b200.so.
 """
 import os
 
 import numpy as np
 
-from .capi import ProblemSet
+
+class ProblemSet:
+    """Host-side description of a batch of subspace problems (CSR style)."""
+
+    def __init__(self, var_off, vids, fac_off, fids):
+        self.var_off = np.ascontiguousarray(var_off, dtype=np.int64)
+        self.vids = np.ascontiguousarray(vids, dtype=np.int32)
+        self.fac_off = np.ascontiguousarray(fac_off, dtype=np.int64)
+        self.fids = np.ascontiguousarray(fids, dtype=np.int64)
+        self.n = len(self.var_off) - 1
+        assert len(self.fac_off) == self.n + 1
+
+    @classmethod
+    def from_lists(cls, problems):
+        """problems: iterable of (vids, fids)."""
+        vo, fo, vs, fs = [0], [0], [], []
+        for v, f in problems:
+            vs.append(np.asarray(v, np.int32)); fs.append(np.asarray(f, np.int64))
+            vo.append(vo[-1] + len(v)); fo.append(fo[-1] + len(f))
+        return cls(vo, np.concatenate(vs) if vs else np.zeros(0, np.int32), fo,
+                   np.concatenate(fs) if fs else np.zeros(0, np.int64))
+
+    def subset(self, idx):
+        return ProblemSet.from_lists([(self.vids[self.var_off[i]:self.var_off[i + 1]],
+                                       self.fids[self.fac_off[i]:self.fac_off[i + 1]]) for i in idx])
+
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 

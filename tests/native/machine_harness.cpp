@@ -78,6 +78,42 @@ struct TestFunction {
   }
 };
 
+// The reference's value cache around the objective, as one "factor" over all variables: Variable::assign only
+// notifies (marks the value dirty) when a coordinate moves by >= 1e-12 (src/Variable.cpp:66-88); operator() returns
+// the cached value unless dirty (src/Factor.cpp:110-119); df() always uses the assigned point.  With it the
+// objective is NOT a function of the point alone, which is what CgdMachine's `faithful` mode exists for.
+struct CachedFunction {
+  TestFunction fn;
+  int n;
+  Vec last;
+  bool assigned = false, dirty = true;
+  double cached = 0;
+  long nf = 0, ng = 0;
+  explicit CachedFunction(const TestFunction& f) : fn(f), n(f.n), last(f.n, 0.0) {}
+  void assign(const Vec& xr) {
+    for (int j = 0; j < n; ++j) {
+      const double v = fn.clampv(j, xr[j]);
+      if (!assigned || !(std::fabs(v - last[j]) < 1e-12)) dirty = true;
+      last[j] = v;
+    }
+    assigned = true;
+  }
+  double operator()(const Vec& xr) {
+    ++nf;
+    assign(xr);
+    if (dirty) {
+      cached = fn(last);
+      dirty = false;
+    }
+    return cached;
+  }
+  void df(const Vec& xr, Vec& g) {
+    ++ng;
+    assign(xr);
+    fn.df(last, g);
+  }
+};
+
 struct Outcome {
   Vec p;
   double fret;
@@ -85,11 +121,12 @@ struct Outcome {
   long nf, ng;
 };
 
-static Outcome run_nested(TestFunction fn, const Vec& x0, int maxiters, double ftol) {
+template <class Fn>
+static Outcome run_nested(Fn fn, const Vec& x0, int maxiters, double ftol) {
 #ifdef USE_REFERENCE_NRC
-  rdis::nrc::Frprmn<TestFunction> cg(fn, maxiters, ftol);
+  rdis::nrc::Frprmn<Fn> cg(fn, maxiters, ftol);
 #else
-  oracle::nr::PolakRibiere<TestFunction> cg(fn, maxiters, ftol);
+  oracle::nr::PolakRibiere<Fn> cg(fn, maxiters, ftol);
 #endif
   try {
     cg.minimize(x0);
@@ -99,12 +136,13 @@ static Outcome run_nested(TestFunction fn, const Vec& x0, int maxiters, double f
 }
 
 // the kernel's loop (solve_kernels.cuh: solve_problem) with one lane
-static Outcome run_machine(TestFunction fn, const Vec& x0, int maxiters, double ftol) {
+template <class Fn>
+static Outcome run_machine(Fn fn, const Vec& x0, int maxiters, double ftol, bool faithful) {
   using namespace rdisgpu;
   const int n = fn.n;
   Vec p = x0, xi(n), g(n), h(n), trial(n), grad(n);
   CgdMachine m;
-  m.start(maxiters, ftol);
+  m.start(maxiters, ftol, faithful);
   while (!m.done()) {
     switch (m.req) {
       case REQ_INIT_GRAD: {
@@ -156,6 +194,8 @@ static Outcome run_machine(TestFunction fn, const Vec& x0, int maxiters, double 
 
 int main(int argc, char** argv) {
   const int trials = argc > 1 ? std::atoi(argv[1]) : 400;
+  const bool cached = argc > 2 && std::atoi(argv[2]) != 0;  // objective behind the reference's value cache
+  int plain_machine_differs = 0;
   std::mt19937_64 rng(12345);
   std::uniform_real_distribution<double> U(-1, 1);
   int bad = 0;
@@ -172,8 +212,21 @@ int main(int argc, char** argv) {
     Vec x0(fn.n);
     for (double& v : x0) v = (fn.kind == 2 ? 6.0 : 2.0) * U(rng);
     const int maxiters = (t % 5 == 0) ? 3 : 25;
-    const Outcome a = run_nested(fn, x0, maxiters, 3e-8);
-    const Outcome b = run_machine(fn, x0, maxiters, 3e-8);
+    Outcome a, b;
+    if (cached) {
+      // the start point is assigned and evaluated by the caller first (CGDSubspaceOptimizer.cpp:33-37)
+      CachedFunction cf(fn);
+      cf(x0);
+      a = run_nested(cf, x0, maxiters, 3e-8);
+      b = run_machine(cf, x0, maxiters, 3e-8, true);
+      const Outcome c = run_machine(cf, x0, maxiters, 3e-8, false);
+      bool same_c = (a.fret == c.fret) && (a.iter == c.iter);
+      for (int j = 0; j < fn.n; ++j) same_c = same_c && (a.p[j] == c.p[j]);
+      if (!same_c) ++plain_machine_differs;
+    } else {
+      a = run_nested(fn, x0, maxiters, 3e-8);
+      b = run_machine(fn, x0, maxiters, 3e-8, false);
+    }
     bool same = (a.fret == b.fret) && (a.iter == b.iter);
     for (int j = 0; j < fn.n; ++j) same = same && (a.p[j] == b.p[j]);
     if (!same) {
@@ -184,5 +237,6 @@ int main(int argc, char** argv) {
     total_machine += b.nf + b.ng;
   }
   std::printf("trials %d mismatches %d  evaluations nested %ld machine %ld\n", trials, bad, total_nested, total_machine);
+  if (cached) std::printf("cached objective: the non-faithful machine departs from the reference on %d trials\n", plain_machine_differs);
   return bad == 0 ? 0 : 1;
 }

@@ -22,13 +22,13 @@ REF_NRC = "/root/reference/external/include/minimize_nrc.h"
 # ------------------------------------------------------------------------------------------
 # NR driver
 # ------------------------------------------------------------------------------------------
-def _harness(tmp_path, use_reference):
+def _harness(tmp_path, use_reference, cached=False):
     exe = str(tmp_path / ("harness_ref" if use_reference else "harness"))
     cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "native", "machine_harness.cpp")]
     if use_reference:
         cmd[1:1] = ["-DUSE_REFERENCE_NRC", "-I" + os.path.dirname(REF_NRC)]
     subprocess.check_call(cmd)
-    out = subprocess.run([exe, "600"], capture_output=True, text=True)
+    out = subprocess.run([exe, "3000" if cached else "600", "1" if cached else "0"], capture_output=True, text=True)
     return out.returncode, out.stdout
 
 
@@ -46,6 +46,45 @@ def test_machine_harness_vs_reference_header(tmp_path):
     rc, out = _harness(tmp_path, True)
     assert rc == 0, out
     assert "mismatches 0" in out
+
+
+@pytest.mark.parametrize("use_reference", [False, True])
+def test_faithful_machine_follows_the_value_cache(tmp_path, use_reference):
+    """Behind the reference's value cache (Variable::assign's 1e-12 change filter + Factor::eval's cached value) the
+    objective is not a function of the point alone.  CgdMachine started `faithful` requests fa = func(0) like
+    minimize_nrc.h:88 and stays bit-identical to the nested driver (3000 problems); the harness also reports on how
+    many of them the non-faithful machine departs."""
+    if use_reference and not os.path.exists(REF_NRC):
+        pytest.skip("reference tree not mounted (GPU box)")
+    rc, out = _harness(tmp_path, use_reference, cached=True)
+    assert rc == 0, out
+    assert "mismatches 0" in out
+
+
+def test_devtrig_twin_differs_from_libm_by_rounding_only(oracle_mod):
+    """The devtrig twin (sin/cos from rdis_b200/csrc/trig.cuh compiled for the host: the routines the device runs)
+    evaluates every factor of the real ladybug graph and of a sinusoid tree within 4 ulp-scale relative distance of
+    the glibc build, and solves well-conditioned point blocks to the same objective (1e-9)."""
+    from rdis_b200 import problems as P
+    spec = P.load_golden_ba()
+    a = oracle_mod.OracleFunction.from_spec(spec)
+    b = oracle_mod.OracleFunction.from_spec(spec, "devtrig")
+    a.set_x(spec["x0"]); b.set_x(spec["x0"])
+    fa, pa = a.eval(per_factor=True)
+    fb, pb = b.eval(per_factor=True)
+    assert np.abs(pa - pb).max() <= 1e-12 * np.abs(pa).max() and abs(fa - fb) <= 1e-13 * abs(fa)
+    assert (pa != pb).any(), "the two math libraries agree on every bit: the twin is not exercising anything"
+    tree = P.sinusoid(6, 3, 4)
+    xt = P.random_start(tree, 2)
+    ta = oracle_mod.OracleFunction.from_spec(tree); tb = oracle_mod.OracleFunction.from_spec(tree, "devtrig")
+    ta.set_x(xt); tb.set_x(xt)
+    ga, gb = ta.grad(), tb.grad()
+    assert np.abs(ga - gb).max() <= 1e-14 * np.abs(ga).max()
+    ps = P.ba_point_problems(spec).subset(range(0, 7776, 97))
+    x0 = spec["x0"]
+    ra = a.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[ps.vids], 25, 3e-8)
+    rb = b.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[ps.vids], 25, 3e-8)
+    assert (np.abs(ra["f_end"] - rb["f_end"]) <= 1e-9 * np.abs(ra["f_end"])).all()
 
 
 def test_restated_driver_equals_reference_driver(oracle_mod):
