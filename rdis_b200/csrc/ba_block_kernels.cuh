@@ -68,6 +68,42 @@ struct TileRt {
   }
 };
 
+// The reference's value cache as seen by ONE block problem: every factor of the problem depends on all of the
+// problem's variables, so Variable::assign's change filter (a move below 1e-12 notifies nobody, src/Variable.cpp:66-88)
+// and Factor::eval's cached value (src/Factor.cpp:110-119) collapse to one dirty flag and one cached SUM per problem
+// (the factors are all recomputed at the same events, and their values are summed in the same order every time).
+// A solve starts with everything dirty (the strict kernels also carry the cache across calls).
+template <int NV>
+struct BlockCache {
+  double last[NV];  // Variable::eval(): the value of the last assign
+  double cached;    // sum of the factors' cached values
+  bool dirty, assigned;
+  __device__ __forceinline__ void reset() {
+    dirty = true;
+    assigned = false;
+    cached = 0.0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) last[j] = 0.0;
+  }
+  // Variable::assign of the clamped point
+  __device__ __forceinline__ void assign(const double* x) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if (!assigned || !(fabs(x[j] - last[j]) < 1e-12)) dirty = true;
+      last[j] = x[j];
+    }
+    assigned = true;
+  }
+  // evalFactors over the list: `fresh` is the sum just computed at the assigned point
+  __device__ __forceinline__ double eval(double fresh) {
+    if (dirty) {
+      cached = fresh;
+      dirty = false;
+    }
+    return cached;
+  }
+};
+
 __device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const BatchView& B, int lg, int pidx, int maxiters,
                                                     double ftol) {
   const TileRt grp(lg);
@@ -117,14 +153,23 @@ __device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const B
   }
 
   CgdMachine mc;
-  mc.start(maxiters, ftol);
+  mc.start(maxiters, ftol, /*faithful=*/true);
   if (!run) mc.req = REQ_DONE;
   double f_init = 0.0;
+  BlockCache<3> cache;
+  cache.reset();
+  double f_at_p = 0.0;  // objective at clamp(p), recomputed by every gradient pass: serves fa = func(0) (minimize_nrc.h:88)
 
   // Every iteration of this loop is one objective evaluation for every unfinished problem of the
-  // warp.  The evaluation and all shuffles run CONVERGED with the full-warp mask (xor / indexed
-  // shuffles below width G never leave a tile), whatever phase each problem's state machine is in;
-  // only the scalar state-machine step at the end diverges between the tiles of a warp.
+  // warp.  The evaluation and all shuffles run CONVERGED with the full-warp mask (indexed shuffles below width G
+  // never leave a tile), whatever phase each problem's state machine is in; only the scalar state-machine step at
+  // the end diverges between the tiles of a warp.
+  //
+  // Every sum is folded in the REFERENCE's order — the factor values left to right in list order
+  // (OptimizableFunction.cpp:108-132), each variable's derivative over its factors in ascending factor id, the first
+  // one copied (State.h:157-194), the directional derivative left to right over the variables (minimize_nrc.h:444) —
+  // so, with the library built without FMA contraction and the correctly rounded quotients of BaOps::partials, a point
+  // block is solved to the same BITS as the reference arithmetic produces (tests: the full real ladybug wave).
   const unsigned kFull = 0xffffffffu;
   while (true) {
     const bool fin = mc.done();
@@ -136,9 +181,9 @@ __device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const B
     const bool live = have && !fin;
     const double alpha = mc.alpha;
     double fv = 0.0, g9 = 0.0, g10 = 0.0, g11 = 0.0;
-    if (live) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) x[9 + j] = clamp_to_domain(along ? (p[j] + alpha * xi[j]) : p[j], dom[j]);
+    for (int j = 0; j < 3; ++j) x[9 + j] = clamp_to_domain(along ? (p[j] + alpha * xi[j]) : p[j], dom[j]);
+    if (live) {
       fv = BaOps::project(x, ob, m);
       if (want_g) {
         double gq[12];
@@ -148,108 +193,101 @@ __device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const B
       if (fc_on) fv = fc_val;  // Factor::eval of an assigned-constant factor, src/Factor.cpp:110-119
     }
 
-    // SubfunctionFD::operator() + Df1dim::df: f and the directional derivative
-    double fs = 0.0, ss = 0.0;
-    if (live) {
-      double sl = 0.0;
-      if (kind == REQ_VALUE_SLOPE) {
-        if (xi[0] != 0.0) sl += g9 * xi[0];
-        if (xi[1] != 0.0) sl += g10 * xi[1];
-        if (xi[2] != 0.0) sl += g11 * xi[2];
-      }
-      fs += fv;
-      ss += sl;
-    }
-    for (int o = G >> 1; o > 0; o >>= 1) {
-      fs += __shfl_xor_sync(kFull, fs, o);
-      ss += __shfl_xor_sync(kFull, ss, o);
-    }
-
-    // full gradient (some problem of the warp asked for one): per variable, the incident factors'
-    // partials folded in ascending factor id (productGradient's accumulation order,
-    // src/State.h:157-194), then the Polak-Ribiere scalars of minimize_nrc.h:654-673
+    // left-to-right folds over the tile's lanes (= the problem's factor list), replicated in every lane
+    double fs = 0.0;
     double gr[3] = {0.0, 0.0, 0.0};
-    double gg = 0.0, dgg = 0.0, tnum = 0.0;
-    if (__any_sync(kFull, grad_kind)) {
-      gr[0] = __shfl_sync(kFull, g9, 0, G);
-      gr[1] = __shfl_sync(kFull, g10, 0, G);
-      gr[2] = __shfl_sync(kFull, g11, 0, G);
-      for (int k = 1; k < G; ++k) {
+    const bool any_g = __any_sync(kFull, want_g);
+    for (int k = 0; k < G; ++k) {
+      const double bf = __shfl_sync(kFull, fv, k, G);
+      if (k < nf) fs = fs + bf;
+      if (any_g) {
         const double b0 = __shfl_sync(kFull, g9, k, G), b1 = __shfl_sync(kFull, g10, k, G), b2 = __shfl_sync(kFull, g11, k, G);
-        if (k < nf) {
+        if (k == 0) {
+          gr[0] = b0; gr[1] = b1; gr[2] = b2;
+        } else if (k < nf) {
           gr[0] = gr[0] + b0; gr[1] = gr[1] + b1; gr[2] = gr[2] + b2;
         }
-      }
-      if (kind == REQ_GRADIENT) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          if ((j & (G - 1)) == r) {  // the lane that owns variable j in the tile partition
-            const double pj = fabs(p[j]);
-            const double t = fabs(gr[j]) * ((pj < 1.0) ? 1.0 : pj);
-            tnum = (t > tnum) ? t : tnum;
-            gg += g[j] * g[j];
-            dgg += (gr[j] + g[j]) * gr[j];
-          }
-        }
-      }
-      for (int o = G >> 1; o > 0; o >>= 1) {
-        gg += __shfl_xor_sync(kFull, gg, o);
-        dgg += __shfl_xor_sync(kFull, dgg, o);
-        const double om = __shfl_xor_sync(kFull, tnum, o);
-        tnum = (om > tnum) ? om : tnum;
       }
     }
 
     // ---- the state machine's step: scalar work, the only part where tiles of a warp diverge ----
-    if (along) {
-      mc.on_eval(fs, ss);
-      if (mc.req == REQ_MOVE) {  // minimize_nrc.h:508-511
-        const double step = mc.alpha;
+    if (!fin) {
+      cache.assign(&x[9]);  // SubfunctionFD::quickAssignVals of this evaluation's point
+      if (along) {
+        const double fcached = cache.eval(fs);
+        double ss = 0.0;  // Df1dim::df: df1 += dft[j] * xi[j]
+        if (kind == REQ_VALUE_SLOPE) ss = ((0.0 + gr[0] * xi[0]) + gr[1] * xi[1]) + gr[2] * xi[2];
+        mc.on_eval(fcached, ss);
+        if (mc.req == REQ_MOVE) {  // minimize_nrc.h:508-511
+          const double step = mc.alpha;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            xi[j] *= step;
+            p[j] += xi[j];
+          }
+          mc.on_moved();
+        }
+      } else if (kind == REQ_INIT_GRAD) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          xi[j] *= step;
-          p[j] += xi[j];
+          const double gneg = -gr[j];
+          g[j] = gneg; h[j] = gneg; xi[j] = gneg;
         }
-        mc.on_moved();
-      }
-    } else if (kind == REQ_INIT_GRAD) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const double gneg = -gr[j];
-        g[j] = gneg; h[j] = gneg; xi[j] = gneg;
-      }
-      f_init = fs;
-      mc.on_init(fs);
-    } else if (kind == REQ_GRADIENT) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) xi[j] = gr[j];
-      mc.on_gradient(tnum, gg, dgg);
-      if (mc.req == REQ_DIRECTION) {  // :681-685
-        const double gam = mc.gam;
+        f_init = cache.eval(fs);
+        f_at_p = fs;
+        mc.on_init(f_init);
+      } else {  // REQ_GRADIENT: func.df(p, xi) — assigns, no Factor::eval
+        f_at_p = fs;
+        double gg = 0.0, dgg = 0.0, tnum = 0.0;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          const double gj = -xi[j];
-          const double hj = gj + gam * h[j];
-          g[j] = gj; h[j] = hj; xi[j] = hj;
+          xi[j] = gr[j];
+          const double pj = fabs(p[j]);
+          const double t = fabs(gr[j]) * ((pj < 1.0) ? 1.0 : pj);
+          tnum = (t > tnum) ? t : tnum;
+          gg += g[j] * g[j];
+          dgg += (gr[j] + g[j]) * gr[j];
         }
-        mc.on_directed();
+        mc.on_gradient(tnum, gg, dgg);
+        if (mc.req == REQ_DIRECTION) {  // :681-685
+          const double gam = mc.gam;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const double gj = -xi[j];
+            const double hj = gj + gam * h[j];
+            g[j] = gj; h[j] = hj; xi[j] = hj;
+          }
+          mc.on_directed();
+        }
       }
+      // fa = func(ax = 0) at the top of a line search: the point is clamp(p), already assigned by the gradient
+      // pass that preceded it, and f_at_p is its objective — answered without another pass
+      if (mc.req == REQ_VALUE && mc.phase == CgdMachine::PH_BR_FA) mc.on_eval(cache.eval(f_at_p), 0.0);
     }
   }
 
   if (!run) return;
-  // ---- commit (CGD.cpp:61-89) ----
+  // ---- commit (CGD.cpp:61-89): quickAssignVals(gdmin.p); if worse than the start, the start is re-assigned and
+  //      re-evaluated (through the cache).  The safety exits (non-finite abscissa, bracket cap) keep p and fret of the
+  //      last completed line search like the reference's own exceptions do. ----
+  double xfin[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) xfin[j] = clamp_to_domain(p[j], dom[j]);
+  cache.assign(xfin);
   double fret = mc.fret;
-  bool restore = (fret > f_init);
-  if (mc.status == ST_NONFINITE || mc.status == ST_BRACKET_CAP) restore = true;
-  if (restore) fret = f_init;
+  const bool restore = (fret > f_init);
+  if (restore) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) xfin[j] = clamp_to_domain(xs[j], dom[j]);
+    cache.assign(xfin);
+    fret = cache.eval(f_init);  // a recomputation at the start point reproduces f_init's bits
+  }
   if (r == 0) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const double val = clamp_to_domain(restore ? xs[j] : p[j], dom[j]);
-      Gv.xbd[v0 + j] = make_double2(val, qnan_f64());
-      Gv.xval[v0 + j] = val;
-      B.xout[P.var_off + j] = val;
+      Gv.xbd[v0 + j] = make_double2(xfin[j], qnan_f64());
+      Gv.xval[v0 + j] = xfin[j];
+      B.xout[P.var_off + j] = xfin[j];
     }
     ResultRec res;
     res.f_init = f_init;
@@ -295,23 +333,28 @@ constexpr int kCamRedWidth = 10;  // f + 9 partials (gradient mode); f + slope u
 
 struct CamShared {
   double p[9], xi[9], g[9], h[9], xs[9];
+  double last[9];  // Variable::eval() of the camera's variables: the point of the previous evaluation (thread 0 only)
   double2 dom[9];
   double wred[kCamMaxWarps][kCamRedWidth];          // warp partials of this CTA (first reduction level)
   double red[2][kCamMaxCluster][kCamRedWidth];      // CTA partials of the whole cluster (second level, double-buffered)
   unsigned long long mbar[2];  // one transaction barrier per reduction buffer (remote st.async completes on it)
+  CgdMachine m;                // advanced by thread 0 of every CTA of the cluster on identical inputs
+  double tot[kCamRedWidth];    // the all-reduced sums of the current evaluation (thread 0 -> nobody else needs them)
 };
 
-// All-reduce of N doubles per thread over the whole cluster, fixed order, two levels:
+// Sum of N doubles per thread over the whole cluster into sh.tot of EVERY CTA (read by thread 0 only), fixed order,
+// two levels:
 //   (1) warp butterfly, warp partials folded per CTA through shared memory (one __syncthreads);
-//   (2) thread d of warp 0 pushes the CTA's partial into slot `cta` of CTA d's buffer with an ASYNCHRONOUS
+//   (2) lane d of warp 0 pushes the CTA's partial into slot `cta` of CTA d's buffer with an ASYNCHRONOUS
 //       store over distributed shared memory that completes a transaction barrier in the receiving CTA
-//       (st.async ... mbarrier::complete_tx); a CTA just waits for its own barrier to have received C*N*8
+//       (st.async ... mbarrier::complete_tx); thread 0 waits for its own barrier to have received C*N*8
 //       bytes and folds the C partials in CTA order: one one-way trip per evaluation, no cluster barrier.
 // The cluster buffers (and their barriers) alternate; re-use two rounds later is safe because a CTA can only
-// send round r+1 after its warp 0 folded round r's warp partials, and nobody finishes round r+1 before every
-// CTA of the cluster has sent it.  `phase` holds the two barriers' parities.
+// send round r+1 after its thread 0 folded round r, and nobody finishes round r+1 before every CTA of the cluster has
+// sent it.  `phase` holds the two barriers' parities.  The caller's __syncthreads after thread 0's scalar step
+// orders the next evaluation's wred writes after this fold.
 template <int N>
-__device__ __forceinline__ void cluster_allreduce(CamShared& sh, int& flip, uint32_t& phase, double (&v)[N], int C, int cta) {
+__device__ __forceinline__ void cluster_reduce_to_thread0(CamShared& sh, int& flip, uint32_t& phase, double (&v)[N], int C, int cta) {
   static_assert(N % 2 == 0, "partials travel as 16-byte pairs");
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -324,44 +367,56 @@ __device__ __forceinline__ void cluster_allreduce(CamShared& sh, int& flip, uint
     for (int i = 0; i < N; ++i) sh.wred[warp][i] = v[i];
   }
   __syncthreads();
+  if (warp != 0) return;
   if (C == 1) {
+    if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = sh.wred[0][i];
-    for (int w = 1; w < nw; ++w) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) v[i] += sh.wred[w][i];
-    }
-    __syncthreads();  // wred is rewritten by the next evaluation
-    return;
-  }
-  if (warp == 0) {
-    if (lane == 0) mbar_arrive_expect_tx(&sh.mbar[flip], (uint32_t)(C * N * 8));
-    if (lane < C) {  // lane d delivers this CTA's partial to CTA d
-      double c[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) c[i] = sh.wred[0][i];
+      for (int i = 0; i < N; ++i) v[i] = sh.wred[0][i];
       for (int w = 1; w < nw; ++w) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) c[i] += sh.wred[w][i];
+        for (int i = 0; i < N; ++i) v[i] += sh.wred[w][i];
       }
-      const uint32_t dst = map_to_cta(smem_addr_u32(&sh.red[flip][cta][0]), (uint32_t)lane);
-      const uint32_t bar = map_to_cta(smem_addr_u32(&sh.mbar[flip]), (uint32_t)lane);
 #pragma unroll
-      for (int i = 0; i < N; i += 2) st_async_v2(dst + 8u * i, c[i], c[i + 1], bar);
+      for (int i = 0; i < N; ++i) sh.tot[i] = v[i];
     }
+    return;
   }
-  mbar_wait_cluster(&sh.mbar[flip], (phase >> flip) & 1u);
+  if (lane == 0) mbar_arrive_expect_tx(&sh.mbar[flip], (uint32_t)(C * N * 8));
+  if (lane < C) {  // lane d delivers this CTA's partial to CTA d
+    double c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) c[i] = sh.wred[0][i];
+    for (int w = 1; w < nw; ++w) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) c[i] += sh.wred[w][i];
+    }
+    const uint32_t dst = map_to_cta(smem_addr_u32(&sh.red[flip][cta][0]), (uint32_t)lane);
+    const uint32_t bar = map_to_cta(smem_addr_u32(&sh.mbar[flip]), (uint32_t)lane);
+#pragma unroll
+    for (int i = 0; i < N; i += 2) st_async_v2(dst + 8u * i, c[i], c[i + 1], bar);
+  }
+  if (lane == 0) {
+    mbar_wait_cluster(&sh.mbar[flip], (phase >> flip) & 1u);
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = sh.red[flip][0][i];
+    for (int s = 1; s < C; ++s) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] += sh.red[flip][s][i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) sh.tot[i] = v[i];
+  }
   phase ^= (1u << flip);
-#pragma unroll
-  for (int i = 0; i < N; ++i) v[i] = sh.red[flip][0][i];
-  for (int s = 1; s < C; ++s) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] += sh.red[flip][s][i];
-  }
   flip ^= 1;
 }
 
 // grid = nprobs * C CTAs, cluster = C CTAs (set at launch), `order` lists the camera-class problems.
+//
+// One evaluation = [all threads] read the request (kind, alpha) and the camera state from shared memory, form the
+// point, the rotation, their observation's value (+ partials), reduce over the cluster; [thread 0 of every CTA] the
+// scalar step: the value cache (BlockCache semantics), the CgdMachine, and the 9-element vector updates it asks for
+// (move, gradient bookkeeping, new direction); one CTA barrier.  Keeping the machine out of the other threads'
+// registers is what lets the observation arithmetic run without spills at 2-3 CTAs per SM.
 __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_cameras_kernel(GraphView Gv, BatchView B, const int32_t* order,
                                                                           int C, int maxiters, double ftol) {
   namespace cgn = cooperative_groups;
@@ -372,7 +427,6 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
   const ProblemDesc P = B.probs[pidx];
   const int nf = P.nf;
   const int32_t v0 = B.vids[P.var_off];
-  const int cam = v0 / 9;
   const int T = blockDim.x;
   const int rank = cta * T + threadIdx.x;
   const int size = C * T;
@@ -382,12 +436,13 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
     mbar_init(&sh.mbar[0], 1);
     mbar_init(&sh.mbar[1], 1);
     mbar_fence_init();
+    sh.m.start(maxiters, ftol, /*faithful=*/true);
   }
-
   if (threadIdx.x < 9) {
     const int j = threadIdx.x;
     const double xv = (B.x0 != nullptr) ? B.x0[P.var_off + j] : Gv.xbd[v0 + j].x;
     sh.p[j] = xv; sh.xs[j] = xv; sh.xi[j] = 0.0; sh.g[j] = 0.0; sh.h[j] = 0.0;
+    sh.last[j] = 0.0;
     sh.dom[j] = __ldg(&Gv.dom[v0 + j]);
   }
   // this thread's first observation: frozen point block + pixel staged in registers
@@ -409,17 +464,17 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
   }
   __syncthreads();
   if (C > 1) cluster.sync();  // every CTA's barriers are initialised before a peer's st.async can reach them
-  (void)cam;
 
-  CgdMachine mc;
-  mc.start(maxiters, ftol);
-  double f_init = 0.0;
+  // thread 0's private scalars: the value cache of the block (BlockCache semantics) and the solve's bookkeeping
+  double f_init = 0.0, c_sum = 0.0, f_at_p = 0.0;
+  bool c_dirty = true, c_assigned = false;
 
-  while (!mc.done()) {
-    const int kind = mc.req;
+  while (true) {
+    const int kind = sh.m.req;
+    if (kind == REQ_DONE) break;
     const bool along = (kind == REQ_VALUE) || (kind == REQ_VALUE_SLOPE);
     const bool want_g = (kind != REQ_VALUE);
-    const double alpha = mc.alpha;
+    const double alpha = sh.m.alpha;
     double x[12];
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
@@ -457,28 +512,13 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
           BaOps::partials(x, m, gq);
           double sl = 0.0;
 #pragma unroll
-          for (int s = 0; s < 9; ++s) {
-            const double d = sh.xi[s];
-            if (d != 0.0) sl += gq[s] * d;
-          }
+          for (int s = 0; s < 9; ++s) sl += gq[s] * sh.xi[s];
           v2[1] += sl;
         }
         if (fc_on) fv = fc_val;
         v2[0] += fv;
       }
-      cluster_allreduce<2>(sh, flip, phase, v2, C, cta);
-      mc.on_eval(v2[0], v2[1]);
-      if (mc.req == REQ_MOVE) {
-        const double step = mc.alpha;
-        if (threadIdx.x < 9) {
-          const int j = threadIdx.x;
-          const double d = sh.xi[j] * step;
-          sh.xi[j] = d;
-          sh.p[j] += d;
-        }
-        __syncthreads();
-        mc.on_moved();
-      }
+      cluster_reduce_to_thread0<2>(sh, flip, phase, v2, C, cta);
     } else {
       double acc[kCamRedWidth];
 #pragma unroll
@@ -496,21 +536,50 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
         if (fc_on) fv = fc_val;
         acc[0] += fv;
       }
-      cluster_allreduce<kCamRedWidth>(sh, flip, phase, acc, C, cta);
-      if (kind == REQ_INIT_GRAD) {
-        if (threadIdx.x < 9) {
-          const int j = threadIdx.x;
-          const double gneg = -acc[1 + j];
+      cluster_reduce_to_thread0<kCamRedWidth>(sh, flip, phase, acc, C, cta);
+    }
+
+    // ---- the scalar step (thread 0 of every CTA, identical inputs in every CTA of the cluster) ----
+    if (threadIdx.x == 0) {
+      CgdMachine mc = sh.m;  // registers for the duration of the step only (one burst of loads instead of dependent ones)
+      // Variable::assign of this evaluation's point (src/Variable.cpp:66-88): a move below 1e-12 notifies nobody
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        if (!c_assigned || !(fabs(x[j] - sh.last[j]) < 1e-12)) c_dirty = true;
+        sh.last[j] = x[j];
+      }
+      c_assigned = true;
+      auto cache_eval = [&](double fresh) {  // Factor::eval over the list, src/Factor.cpp:110-119
+        if (c_dirty) {
+          c_sum = fresh;
+          c_dirty = false;
+        }
+        return c_sum;
+      };
+      if (along) {
+        mc.on_eval(cache_eval(sh.tot[0]), (kind == REQ_VALUE_SLOPE) ? sh.tot[1] : 0.0);
+        if (mc.req == REQ_MOVE) {  // minimize_nrc.h:508-511
+          const double step = mc.alpha;
+          for (int j = 0; j < 9; ++j) {
+            const double d = sh.xi[j] * step;
+            sh.xi[j] = d;
+            sh.p[j] += d;
+          }
+          mc.on_moved();
+        }
+      } else if (kind == REQ_INIT_GRAD) {
+        for (int j = 0; j < 9; ++j) {
+          const double gneg = -sh.tot[1 + j];
           sh.g[j] = gneg; sh.h[j] = gneg; sh.xi[j] = gneg;
         }
-        __syncthreads();
-        f_init = acc[0];
-        mc.on_init(acc[0]);
-      } else {
+        f_at_p = sh.tot[0];
+        f_init = cache_eval(f_at_p);
+        mc.on_init(f_init);
+      } else {  // REQ_GRADIENT: func.df(p, xi), then :656-685
+        f_at_p = sh.tot[0];
         double gg = 0.0, dgg = 0.0, tnum = 0.0;
-#pragma unroll
         for (int j = 0; j < 9; ++j) {
-          const double gr = acc[1 + j];
+          const double gr = sh.tot[1 + j];
           const double pj = fabs(sh.p[j]);
           const double t = fabs(gr) * ((pj < 1.0) ? 1.0 : pj);
           tnum = (t > tnum) ? t : tnum;
@@ -519,46 +588,54 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
           dgg += (gr + gj) * gr;
         }
         mc.on_gradient(tnum, gg, dgg);
-        __syncthreads();  // every thread has read g[] before anyone rewrites it
-        if (threadIdx.x < 9) {
-          const int j = threadIdx.x;
-          if (mc.req == REQ_DIRECTION) {
-            const double gj = -acc[1 + j];
-            const double hj = gj + mc.gam * sh.h[j];
+        if (mc.req == REQ_DIRECTION) {
+          const double gam = mc.gam;
+          for (int j = 0; j < 9; ++j) {
+            const double gj = -sh.tot[1 + j];
+            const double hj = gj + gam * sh.h[j];
             sh.g[j] = gj; sh.h[j] = hj; sh.xi[j] = hj;
-          } else {
-            sh.xi[j] = acc[1 + j];
           }
+          mc.on_directed();
+        } else {
+          for (int j = 0; j < 9; ++j) sh.xi[j] = sh.tot[1 + j];
         }
-        __syncthreads();
-        if (mc.req == REQ_DIRECTION) mc.on_directed();
       }
+      // fa = func(ax = 0) at the top of a line search (minimize_nrc.h:88): clamp(p) is the point the gradient pass
+      // assigned and f_at_p its objective — answered from the cache rules without another pass
+      if (mc.req == REQ_VALUE && mc.phase == CgdMachine::PH_BR_FA) mc.on_eval(cache_eval(f_at_p), 0.0);
+      sh.m = mc;
     }
+    __syncthreads();
   }
 
-  // ---- commit (CGD.cpp:61-89): CTA 0 of the cluster writes ----
-  double fret = mc.fret;
-  bool restore = (fret > f_init);
-  if (mc.status == ST_NONFINITE || mc.status == ST_BRACKET_CAP) restore = true;
-  if (restore) fret = f_init;
-  if (cta == 0) {
-    if (threadIdx.x < 9) {
-      const int j = threadIdx.x;
+  // ---- commit (CGD.cpp:61-89): quickAssignVals(gdmin.p); if worse than the start the start point is re-assigned and
+  //      re-evaluated through the cache.  CTA 0 of the cluster writes. ----
+  if (cta == 0 && threadIdx.x == 0) {
+    const CgdMachine& mc = sh.m;
+    double fret = mc.fret;
+    const bool restore = (fret > f_init);
+    if (restore) {
+      bool chg = c_dirty;
+      for (int j = 0; j < 9; ++j) {  // the two assigns: gdmin.p, then the start point
+        const double pf = clamp_to_domain(sh.p[j], sh.dom[j]), ps = clamp_to_domain(sh.xs[j], sh.dom[j]);
+        if (!(fabs(pf - sh.last[j]) < 1e-12) || !(fabs(ps - pf) < 1e-12)) chg = true;
+      }
+      fret = chg ? f_init : c_sum;  // a recomputation at the start point reproduces f_init's bits
+    }
+    for (int j = 0; j < 9; ++j) {
       const double val = clamp_to_domain(restore ? sh.xs[j] : sh.p[j], sh.dom[j]);
       Gv.xbd[v0 + j] = make_double2(val, qnan_f64());
       Gv.xval[v0 + j] = val;
       B.xout[P.var_off + j] = val;
     }
-    if (threadIdx.x == 0) {
-      ResultRec res;
-      res.f_init = f_init;
-      res.f_end = fret;
-      res.iters = mc.iter;
-      res.status = mc.status;
-      res.n_value = mc.n_value;
-      res.n_slope = mc.n_slope;
-      B.res[pidx] = res;
-    }
+    ResultRec res;
+    res.f_init = f_init;
+    res.f_end = fret;
+    res.iters = mc.iter;
+    res.status = mc.status;
+    res.n_value = mc.n_value;
+    res.n_slope = mc.n_slope;
+    B.res[pidx] = res;
   }
   if (C > 1) cluster.sync();  // no CTA leaves while a peer could still address its shared memory
 }

@@ -200,7 +200,7 @@ __device__ __forceinline__ void resident_terms(const ResView& R, double alpha, b
   const int T = blockDim.x, tid = threadIdx.x;
   for (int t = tid; t < R.nS; t += T) {  // sine class
     const int lv = R.tlv[t];
-    const double raw = along ? __fma_rn(alpha, R.ds[lv], R.xs[lv]) : R.xs[lv];
+    const double raw = along ? __dadd_rn(R.xs[lv], __dmul_rn(alpha, R.ds[lv])) : R.xs[lv];  // Df1dim: p + x*xi, product rounded first (load_var)
     const double xv = clamp_to_domain(raw, make_double2(R.lb[lv], R.ub[lv]));
     if (kGrad) {
       double tv, dt;
@@ -213,7 +213,7 @@ __device__ __forceinline__ void resident_terms(const ResView& R, double alpha, b
   }
   for (int t = R.nS + tid; t < R.nT; t += T) {  // polynomial class
     const int lv = R.tlv[t];
-    const double raw = along ? __fma_rn(alpha, R.ds[lv], R.xs[lv]) : R.xs[lv];
+    const double raw = along ? __dadd_rn(R.xs[lv], __dmul_rn(alpha, R.ds[lv])) : R.xs[lv];  // Df1dim: p + x*xi, product rounded first (load_var)
     const double xv = clamp_to_domain(raw, make_double2(R.lb[lv], R.ub[lv]));
     if (kGrad) {
       double tv, dt;

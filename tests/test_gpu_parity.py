@@ -366,8 +366,11 @@ def test_run_to_run_determinism(gpu):
 def test_ba_block_kernels_match_generic_path(gpu, oracle_mod):
     """The register-resident point-block kernel and the cluster camera-block kernel against the
     generic tile / CTA kernels (`generic_only` routes a context's batches through those): same
-    statuses and iteration counts where the solve is well conditioned, objectives to rounding.
-    (Not to the bit: FMA contraction is decided per compilation context.)"""
+    statuses and iteration counts where the solve is well conditioned, objectives to rounding.  Not to the bit: the
+    block kernels reproduce the reference's value cache (1e-12 change filter) and, for point blocks, its summation
+    order — they are BIT-IDENTICAL to the oracle's devtrig twin, asserted here too — while the generic kernels
+    recompute every factor at every point and fold by trees, so the odd line search bifurcates (a handful per
+    thousand blocks, like the reference itself under such a perturbation: profiles/r02_parity_attribution.json)."""
     from rdis_b200 import Context, problems as P
     spec = P.ba_synthetic(ncams=9, npts=700, nobs=3300, seed=21)
     x0 = spec["x0"]
@@ -386,7 +389,15 @@ def test_ba_block_kernels_match_generic_path(gpu, oracle_mod):
         rel = _relerr(a["f_end"], b["f_end"], 1e-12)
         same = (a["iters"] == b["iters"]) & (a["status"] == b["status"])
         print("point blocks fast-vs-generic: worst rel f_end %.2e, identical iters/status on %d/%d" % (rel.max(), same.sum(), pts.n))
-        assert np.median(rel) <= 1e-10 and rel.max() <= 1e-4 and same.mean() >= 0.97
+        assert np.median(rel) <= 1e-10 and np.quantile(rel, 0.98) <= 1e-6 and same.mean() >= 0.97
+        orc = oracle_mod.OracleFunction.from_spec(spec, "devtrig")
+        if use_const:
+            orc.set_factor_const(fid, val, on)
+        orc.set_x(x0)
+        o = orc.solve_cgd_batch(pts.var_off, pts.vids, pts.fac_off, pts.fids, x0[pts.vids], 25, 3e-8)
+        for key in ("f_init", "f_end", "x"):   # the production point kernel == the reference arithmetic, to the bit
+            assert np.array_equal(a[key].view(np.uint64), o[key].view(np.uint64)), key
+        assert np.array_equal(a["iters"], o["iters"])
         cams = P.ba_camera_problems(spec)
         fast.set_x(x0); slow.set_x(x0)
         a = fast.solve_cgd(cams, x0[cams.vids], 1, 3e-8)
@@ -399,8 +410,8 @@ def test_ba_block_kernels_match_generic_path(gpu, oracle_mod):
         fast.set_x(x0); slow.set_x(x0)
         a = fast.solve_cgd(sub, None, 25, 3e-8)
         b = slow.solve_cgd(sub, None, 25, 3e-8)
-        rel = _relerr(a["f_end"], b["f_end"], 1e-12)   # same band as the full batch above (one
-        assert np.median(rel) <= 1e-10 and rel.max() <= 1e-4  # ill-conditioned block in 700 sits at 1e-6)
+        rel = _relerr(a["f_end"], b["f_end"], 1e-12)   # same band as the full batch above
+        assert np.median(rel) <= 1e-10 and np.quantile(rel, 0.98) <= 1e-6
         c = fast.get_x(); d = slow.get_x()
         moved = np.zeros(spec["V"], bool); moved[sub.vids] = True
         assert np.array_equal(c[~moved], d[~moved])          # bookkeeping: nothing else moved, bit-exact
