@@ -1,34 +1,39 @@
 #!/usr/bin/env python
-"""bench.py — subspace-solves/sec on a ladybug-49-7776-shaped bundle-adjustment factor graph.
+"""bench.py — subspace-solves/sec on ladybug-49-7776 (BASELINE.json's metric and graph).
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-One *step* = one alternating wave of the recursive decomposer's leaf work on a synthetic graph
-with the shape of data/ladybug-problem-49-7776-pre.txt (49 cameras, 7776 points, 31843
-observations): reset the state to x0, solve the 7776 point components given the cameras (one
-sibling batch), then the 49 camera components given the points (second sibling batch) —
-7825 CGDSubspaceOptimizer::optimize calls (SSmaxit 25, ftol 3e-8, the optBA defaults) — and
-accumulate the global objective, which is all-reduced across ranks (the path's only collective).
+One *step* = one alternating wave of the recursive decomposer's leaf work on the reference's own data file
+data/ladybug-problem-49-7776-pre.txt (49 cameras, 7776 points, 31843 observations; committed as the fixture
+tests/golden/ladybug_49_7776.npz), from the file's state (`--randinit 0`): reset the state to x0, solve the 7776
+point components given the cameras (one sibling batch), then the 49 camera components given the points (second
+sibling batch) — 7825 CGDSubspaceOptimizer::optimize calls (SSmaxit 25, ftol 3e-8, the optBA defaults) — and
+accumulate the global objective.
 
-  value   solves/s, device-resident: problem lists and x0 already in HBM, results stay in HBM
-  e2e     the same through rdisgpu_solve_cgd with HOST buffers: index lists + x0 up, results down
-  roofline        the dominant kernel of the step, algorithmic bytes (every objective
-                  evaluation = 32 B/factor + 8 B/variable touched, +8 B/variable with gradients)
-                  over its CUDA-event time; the solves are L2-resident and latency/FP64 bound
-  roofline_sweep  the residual sweep on the cfg4 graph (1,048,575 vars / 4,194,292 factors, 268 MB
-                  per sweep — larger than L2): the HBM-roofline evidence for the sweep kernel
+  value   solves/s, device-resident: index lists and x0 already in HBM, results stay in HBM
+  e2e     N=1: the same step through the C++ plugin a reference maintainer binds — rdis::CudaSubspaceOptimizer::
+          optimizeBatch over rdis::Variable / rdis::Factor host objects (tests/native/host_driver benchwaves):
+          Variable::assign of the start state, index lists + start values up, results down, Variable write-back.
+          N>1: the sharded step through the C-ABI (rdisgpu_solve_cgd_csr) with host buffers and a host all-gather.
+  roofline        the dominant kernel of the step, algorithmic bytes (every objective evaluation =
+                  32 B/factor + 8 B/variable touched, +8 B/variable with gradients) over its CUDA-event time; the
+                  solves are L2-resident and latency / FP64 bound
+  roofline_sweep  the residual sweep on the cfg4 graph (1,048,575 vars / 4,194,292 factors, 268 MB per sweep —
+                  larger than L2): the HBM-roofline evidence for the sweep kernel
   cpu_baseline    the CPU oracle (reference-semantics port, 1 core) on a bounded sample of the wave
 
-Multi-GPU (weak scaling): every rank owns one copy of the ladybug-shaped component set (same seed, equal
-work per GPU); no data path collective besides the objective all-reduce.
+Multi-GPU = STRONG scaling of the ONE sibling set (north_star / BASELINE config 5): the components of each wave are
+dealt to the ranks (LPT by factor count), every rank keeps the whole graph resident, the point wave's results are
+all-gathered (NCCL) into every replica before the camera wave, the objective is all-reduced.  `replicas_weak` keeps
+last round's weak-scaling figure (one whole set per rank) as a secondary key.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
-import threading
+import tempfile
 import time
 
 import numpy as np
@@ -37,7 +42,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MAXITERS, FTOL = 25, 3e-8
-SEED = 20260417
+WORKLOAD = ("optBA ladybug-49-7776 (reference data file: 49 cams, 7776 pts, 31843 obs), file state: one alternating wave = "
+            "7776 point-component + 49 camera-component CGDSubspaceOptimizer solves per step")
+DATA = "reference data/ladybug-problem-49-7776-pre.txt (fixture tests/golden/ladybug_49_7776.npz); synthetic graphs for cfg2 / cfg4 legs"
 
 
 def parse():
@@ -46,10 +53,28 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-sweep", action="store_true", help="skip the cfg4 sweep roofline leg")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the secondary legs (cfg2 / cfg3-full / cfg4 / sweeps / LM)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and parity legs")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU budget of the cpu_baseline sample")
     return ap.parse_args()
+
+
+def config(world):
+    """Identical in both arms at a given N (the driver compares them)."""
+    return {"workload": WORKLOAD, "ssmaxit": MAXITERS, "ssftol": FTOL, "n_gpus": world,
+            "parallelism": "GPU arm: component shard x%d of ONE sibling set (LPT by factor count; graph replicated on every GPU, point "
+                           "results all-gathered before the camera wave, objective all-reduced), strong scaling.  CPU arm: all host "
+                           "threads, one function replica per thread, same total work at every N" % world,
+            "l2": "GPU arm: flushed between steps (256 MiB memset + read pass, untimed); working set 1.4 MB.  CPU arm: n/a"}
+
+
+def load_problems_module():
+    """rdis_b200/problems.py by path: numpy only, so the reference arm never maps librdis_b200.so."""
+    import importlib.util
+    sp = importlib.util.spec_from_file_location("rdis_problems", os.path.join(ROOT, "rdis_b200", "problems.py"))
+    mod = importlib.util.module_from_spec(sp)
+    sp.loader.exec_module(mod)
+    return mod
 
 
 # ------------------------------------------------------------------------------------------
@@ -97,7 +122,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
 
 
-def algorithmic_bytes(spec, ps, res):
+def algorithmic_bytes(ps, res):
     """one objective evaluation over a problem = 32 B per factor + 8 B per distinct
     variable it touches; evaluations that also produce derivatives add 8 B per variable."""
     nf = np.diff(ps.fac_off)
@@ -112,14 +137,17 @@ def algorithmic_bytes(spec, ps, res):
 
 
 def measured_traffic(kernel, key="dram_bytes"):
-    """DRAM bytes per launch (or another recorded metric) of `kernel` from the committed ncu capture
-    (profiles/r01_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(path) as f:
-            return json.load(f).get(kernel, {}).get(key)
-    except Exception:
-        return None
+    """DRAM bytes per launch (or another recorded metric) of `kernel` from the committed ncu captures
+    (profiles/r02_traffic.json, falling back to round 1's), or None."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                v = json.load(f).get(kernel, {}).get(key)
+            if v is not None:
+                return v
+        except Exception:
+            pass
+    return None
 
 
 def peaks():
@@ -128,6 +156,41 @@ def peaks():
         with open(path) as f:
             return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def write_bal(spec, path):
+    """The fixture back in the reference's BAL text format (17 significant digits: the doubles round-trip), for the
+    C++ loader of the plugin (rdis::BundleAdjustmentFunction::load)."""
+    nc, npt, F = int(spec["ncams"]), int(spec["npts"]), int(spec["F"])
+    with open(path, "w") as f:
+        f.write("%d %d %d\n" % (nc, npt, F))
+        obs = spec["obs"].reshape(F, 2)
+        f.write("".join("%d %d %.17g %.17g\n" % (c, p, o[0], o[1]) for c, p, o in zip(spec["cam"], spec["pt"], obs)))
+        f.write("".join("%.17g\n" % v for v in spec["x0"]))
+
+
+def lpt_shard(ps, world):
+    """Deterministic LPT packing of a wave's components onto the ranks by factor count (every evaluation costs one
+    pass over the factors; the evaluation counts are not known before the solve)."""
+    cost = np.diff(ps.fac_off).astype(np.int64)
+    order = np.argsort(-cost, kind="stable")
+    owner = np.empty(ps.n, dtype=np.int64)
+    load = np.zeros(world, dtype=np.int64)
+    if ps.n > 64 * world:
+        owner[order] = np.arange(ps.n) % world          # thousands of small components: dealing the sorted list is LPT-tight
+    else:
+        for i in order:
+            r = int(np.argmin(load))
+            owner[i] = r
+            load[r] += cost[i]
+    return [np.nonzero(owner == r)[0] for r in range(world)]
+
+
+class DevView:
+    """A raw device pointer as a torch tensor (zero copy) through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
 # ------------------------------------------------------------------------------------------
@@ -145,28 +208,50 @@ def run_ours(args):
         raise SystemExit("--gpus must equal WORLD_SIZE")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")   # the host-buffer exchange of the e2e leg
 
-    # ---- workload: one ladybug-shaped component set per rank.  Every rank generates the SAME set (same seed):
-    #      weak scaling with exactly equal work per GPU, so that the per-N numbers measure the system (launch,
-    #      NCCL all-reduce, host contention) and not the luck of a rank's longest line-search chain ----
-    spec = P.ba_synthetic(seed=SEED)
+    # ---- workload: the ONE sibling set of the real graph, its components dealt to the ranks ----
+    spec = P.load_golden_ba()
     x0 = spec["x0"]
+    V = spec["V"]
     pts, cams = P.ba_point_problems(spec), P.ba_camera_problems(spec)
     n_solves = pts.n + cams.n
+    own_p, own_c = lpt_shard(pts, world), lpt_shard(cams, world)
+    my_pts = pts.subset(own_p[rank]) if world > 1 else pts
+    my_cams = cams.subset(own_c[rank]) if world > 1 else cams
     stream = torch.cuda.current_stream()
     ctx = Context.from_spec(spec, device=local_rank, stream=stream.cuda_stream)
     x0_dev = torch.from_numpy(x0).to(dev)
     obj_dev = torch.zeros(1, dtype=torch.float64, device=dev)
-    b_pts, b_cams = ctx.batch(pts), ctx.batch(cams)
+    b_pts, b_cams = ctx.batch(my_pts), ctx.batch(my_cams)
     flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    # exchange of the point wave: every rank's solved point values -> every replica (all-gather of equal-sized slices;
+    # the pad repeats a rank's first variable, so the scatter writes the same value twice)
+    state_ptr, _ = ctx.device_state()
+    state = torch.as_tensor(DevView(state_ptr, (V, 2)), device=dev)
+    if world > 1:
+        nmax = max(len(pts.subset(o).vids) for o in own_p)
+        pad = lambda v: np.concatenate([v, np.full(nmax - len(v), v[0], v.dtype)])
+        vid_all = torch.from_numpy(np.concatenate([pad(pts.subset(o).vids) for o in own_p]).astype(np.int32)).to(dev)
+        my_vid = torch.from_numpy(pad(my_pts.vids).astype(np.int64)).to(dev)
+        recv = torch.empty(world * nmax, dtype=torch.float64, device=dev)
 
-    def step_resident():
+    def step_resident(timers=None):
         obj_dev.zero_()
-        ctx.set_x_device(x0_dev.data_ptr(), spec["V"])
+        ctx.set_x_device(x0_dev.data_ptr(), V)
         b_pts.solve(None, MAXITERS, FTOL)
         b_pts.objective_device(obj_dev.data_ptr())
+        if timers is not None:
+            timers[1].record(stream)
+        if world > 1:
+            send = state[:, 0].index_select(0, my_vid)
+            dist.all_gather_into_tensor(recv, send)
+            ctx.set_x_device(recv.data_ptr(), world * nmax, vid_all.data_ptr())
+        if timers is not None:
+            timers[2].record(stream)
         b_cams.solve(None, MAXITERS, FTOL)
         b_cams.objective_device(obj_dev.data_ptr())
         if world > 1:
@@ -182,8 +267,7 @@ def run_ours(args):
     # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -192,169 +276,89 @@ def run_ours(args):
         flush.zero_()                     # untimed: evicts the previous step's working set from L2 ...
         flush.sum()                       # ... and a read pass leaves clean lines (no write-backs inside the timing)
         ev[k][0].record(stream)
-        obj_dev.zero_()
-        ctx.set_x_device(x0_dev.data_ptr(), spec["V"])
-        b_pts.solve(None, MAXITERS, FTOL)
-        b_pts.objective_device(obj_dev.data_ptr())
-        ev[k][1].record(stream)           # splits the step into its two solve launches
-        b_cams.solve(None, MAXITERS, FTOL)
-        b_cams.objective_device(obj_dev.data_ptr())
-        if world > 1:
-            dist.all_reduce(obj_dev)
-        ev[k][2].record(stream)
+        step_resident(ev[k])
+        ev[k][3].record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    ms_steps = np.array([e[0].elapsed_time(e[2]) for e in ev])
+    ms_steps = np.array([e[0].elapsed_time(e[3]) for e in ev])
     ms_pts = np.array([e[0].elapsed_time(e[1]) for e in ev])
-    ms_cams = np.array([e[1].elapsed_time(e[2]) for e in ev])
+    ms_xchg = np.array([e[1].elapsed_time(e[2]) for e in ev])
+    ms_cams = np.array([e[2].elapsed_time(e[3]) for e in ev])
     total_ms = float(ms_steps.sum())
+    per_rank = None
     if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        t = torch.tensor([total_ms, float(ms_pts.mean()), float(ms_xchg.mean()), float(ms_cams.mean())], dtype=torch.float64, device=dev)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [[float(v) for v in a.tolist()] for a in allt]
+        total_ms = max(a[0] for a in per_rank)
     objective = float(obj_dev.item())
-    value = world * n_solves * args.steps / (total_ms * 1e-3)
+    value = n_solves * args.steps / (total_ms * 1e-3)
 
     # ---- results of the last step (for the roofline's evaluation counts and the residual-eval rate) ----
     r_pts, r_cams = b_pts.fetch(), b_cams.fetch()
-    evals = float(np.sum(r_pts["n_feval"] * np.diff(pts.fac_off)) + np.sum(r_cams["n_feval"] * np.diff(cams.fac_off)))
-    resid_evals_per_s = world * evals * args.steps / (total_ms * 1e-3)
-
-    # ---- e2e: host buffers through rdisgpu_solve_cgd ----
-    x0_pin = torch.from_numpy(x0).pin_memory()
-    x0_pts_pin = torch.from_numpy(x0[pts.vids]).pin_memory().numpy()
-    x0_cams_pin = torch.from_numpy(x0[cams.vids]).pin_memory().numpy()
-
-    def step_e2e():
-        ctx.set_x(x0_pin.numpy())                                   # H2D of the state
-        ra = ctx.solve_cgd(pts, x0_pts_pin, MAXITERS, FTOL)         # H2D lists + x0, D2H results
-        rb = ctx.solve_cgd(cams, x0_cams_pin, MAXITERS, FTOL)
-        return float(ra["f_end"].sum() + rb["f_end"].sum())
-
-    for _ in range(2):
-        step_e2e()
-    e2e_steps = max(3, min(args.steps, 10))
+    evals = float(np.sum(r_pts["n_feval"] * np.diff(my_pts.fac_off)) + np.sum(r_cams["n_feval"] * np.diff(my_cams.fac_off)))
     if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        obj_e2e = step_e2e()
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e_value = world * n_solves * e2e_steps / t_e2e
-    # state + per batch: one index blob (24 B ProblemDesc + 3 x 4 B order lists + 12 B warp task per problem,
-    # 4 B per variable id and factor id) + start values; back: 32 B result record per problem + final values
-    h2d = 8 * spec["V"] + sum(4 * len(p.vids) + 4 * len(p.fids) + 8 * len(p.vids) + 48 * p.n for p in (pts, cams))
-    d2h = sum(8 * len(p.vids) + 32 * p.n for p in (pts, cams))
+        t = torch.tensor([evals], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        evals = float(t.item())
+    resid_evals_per_s = evals * args.steps / (total_ms * 1e-3)
 
-    # ---- the same wave with the Levenberg-Marquardt subspace solver (BASELINE config 3: per-component LM);
-    #      host buffers through rdisgpu_solve_lm_csr, so this is an end-to-end figure ----
-    def step_lm():
-        ctx.set_x(x0_pin.numpy())
-        ra = ctx.solve_lm(pts, x0_pts_pin, MAXITERS, FTOL)
-        rb = ctx.solve_lm(cams, x0_cams_pin, MAXITERS, FTOL)
-        return float(ra["f_end"].sum() + rb["f_end"].sum()), ra, rb
-
-    for _ in range(2):
-        step_lm()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        obj_lm, lm_a, lm_b = step_lm()
-    torch.cuda.synchronize()
-    t_lm = time.perf_counter() - t0
-    lm_info = {"value": n_solves * e2e_steps / t_lm, "unit": "solves/s (per GPU, host buffers, rdisgpu_solve_lm_csr)",
-               "ms_per_step": t_lm / e2e_steps * 1e3, "objective": obj_lm,
-               "iters_mean": float(np.concatenate([lm_a["iters"], lm_b["iters"]]).mean()),
-               "stop_histogram": np.bincount(np.concatenate([lm_a["stop"], lm_b["stop"]]), minlength=8).tolist(),
-               "parity": "unpinned upstream (levmar not vendored); tested against oracle/lm_oracle.hpp"}
+    # ---- e2e ----
+    e2e = e2e_leg(args, spec, pts, cams, own_p, own_c, ctx, rank, world, local_rank, host_group, dist, torch, dev)
 
     out = None
     if rank == 0:
         peak, peak_src = peaks()
         dom_is_pts = ms_pts.mean() >= ms_cams.mean()
-        dom_ps, dom_res, dom_ms = (pts, r_pts, ms_pts.mean()) if dom_is_pts else (cams, r_cams, ms_cams.mean())
-        abytes = algorithmic_bytes(spec, dom_ps, dom_res)
+        dom_ps, dom_res, dom_ms = (my_pts, r_pts, ms_pts.mean()) if dom_is_pts else (my_cams, r_cams, ms_cams.mean())
+        dom_name = "solve_ba_points_kernel" if dom_is_pts else "solve_ba_cameras_kernel"
+        abytes = algorithmic_bytes(dom_ps, dom_res)
         achieved = abytes / (dom_ms * 1e-3) / 1e9
+        cfg = config(world)
         out = {
             "metric": "subspace-solves/sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "ladybug-49-7776-shaped BA graph (49 cams, 7776 pts, 31843 obs) per GPU: "
-                                   "7776 point-component + 49 camera-component CGD solves per step",
-                       "ssmaxit": MAXITERS, "ssftol": FTOL, "parallelism": "component-shard x%d (one copy of the component set per rank, objective all-reduced)" % world,
-                       "l2": "flushed between steps (256 MiB memset + read pass, untimed)", "seed": SEED,
-                       "mapping": {"points": b_pts.info(), "cameras": b_cams.info()}},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": DATA, "config": cfg,
             "residual_evals_per_sec": resid_evals_per_s,
             "objective_after_step": objective,
-            "kernel_ms": {"solve_ba_points_kernel": float(ms_pts.mean()), "solve_ba_cameras_kernel": float(ms_cams.mean())},
+            "mapping": {"points": b_pts.info(), "cameras": b_cams.info()},
+            "kernel_ms": {"solve_ba_points_kernel": float(ms_pts.mean()), "solve_ba_cameras_kernel": float(ms_cams.mean()),
+                          "exchange_allgather_scatter": float(ms_xchg.mean())},
+            "per_rank_ms": None if per_rank is None else {"columns": ["total over the timed steps", "points wave", "exchange", "cameras wave"], "rows": per_rank},
+            "limiting": "the longest line-search chain of one camera component (cameras wave) — per-rank work shrinks with N, the chain does not",
             "wall_s_timed_region": t_wall,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "objective": obj_e2e},
-            "lm_wave": lm_info,
+            "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic("solve_ba_points_kernel" if dom_is_pts else "solve_ba_cameras_kernel"),
-                         "kernel": "solve_ba_points_kernel (point components)" if dom_is_pts
-                         else "solve_ba_cameras_kernel (camera components)",
+                         "traffic": measured_traffic(dom_name), "kernel": dom_name,
                          "algorithmic_bytes_per_launch": abytes, "launch_ms": float(dom_ms), "peak_source": peak_src,
-                         "fp64_pipe_active_pct_ncu": measured_traffic("solve_ba_points_kernel" if dom_is_pts else "solve_ba_cameras_kernel",
-                                                                      "fp64_pipe_active_pct"),
-                         "note": "working set 1.4 MB: L2-resident (DRAM traffic ~1.6 MB per launch), a serial chain of <=1000 dependent "
-                                 "evaluations per problem: latency bound (fp64 pipe 25 % of the measured 33.9 TFLOP/s while active); "
-                                 "see roofline_sweep for the HBM-bound kernel"},
+                         "fp64_pipe_active_pct_ncu": measured_traffic(dom_name, "fp64_pipe_active_pct"),
+                         "note": "working set 1.4 MB: L2-resident, a serial chain of <=1000 dependent evaluations per problem: "
+                                 "latency bound, HBM is not the limiter here; see roofline_sweep for the HBM-bound kernel"},
         }
-    # ---- residual-evals/sec of the all-factor BA sweep (evalFactors over the whole graph): at ladybug size it is
-    #      launch-bound (1.2 MB); 100 copies of the graph (122 MB algorithmic > L2) show the streaming regime ----
-    if rank == 0 and not args.no_sweep:
-        out["ba_residual_sweep"] = ba_sweep_rates(spec, local_rank, stream, dev)
-    # ---- throughput regime: 8 independent copies of the problem (optBA's --nsamples restarts) in ONE batch ----
-    if rank == 0 and not args.no_sweep:
-        K = 8
-        spec_k = P.ba_replicate(spec, K)
-        pts_k, cams_k = P.ba_point_problems(spec_k), P.ba_camera_problems(spec_k)
-        ctx_k = Context.from_spec(spec_k, device=local_rank, stream=stream.cuda_stream)
-        xk = torch.from_numpy(spec_k["x0"]).to(dev)
-        bpk, bck = ctx_k.batch(pts_k), ctx_k.batch(cams_k)
-        tk = []
-        for it in range(5):
-            ctx_k.set_x_device(xk.data_ptr(), spec_k["V"])
-            torch.cuda.synchronize()
-            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            bpk.solve(None, MAXITERS, FTOL)
-            bck.solve(None, MAXITERS, FTOL)
-            e.record(stream)
-            torch.cuda.synchronize()
-            tk.append(a.elapsed_time(e))
-        ms_k = float(np.median(tk[2:]))
-        out["batched_samples"] = {"what": "%d independent copies of the ladybug-shaped problem in one graph: %d point + %d camera components "
-                                          "per wave (NOT the headline workload: shows the throughput regime of the same kernels)" % (K, pts_k.n, cams_k.n),
-                                  "ms_per_wave": ms_k, "solves_per_sec": (pts_k.n + cams_k.n) / (ms_k * 1e-3), "camera_mapping": bck.info()}
-        del bpk, bck, ctx_k
-    # ---- BASELINE config 2: optSinusoid d=1000, the whole graph as ONE subspace problem (rank 0) ----
-    if rank == 0 and not args.no_sweep:
-        out["cfg2_full_solve"] = cfg2_full_solve(local_rank, stream, with_cpu=not args.no_cpu)
-    # ---- BASELINE config 4: sibling-component shard of the 1e6-variable / 4e6-factor graph (all ranks) ----
+    # ---- secondary legs ----
     if not args.no_sweep:
+        rw = replicas_weak(spec, pts, cams, local_rank, stream, dev, world, dist, torch)
         c4 = cfg4_sibling_wave(local_rank, stream, rank, world, dist if world > 1 else None, dev)
         if rank == 0:
+            out["replicas_weak"] = rw
             out["cfg4_sibling_wave"] = c4
-    # ---- the HBM-bound kernel: residual sweep on the cfg4 graph (rank 0) ----
+            out["cfg4_sibling_wave_ms"] = c4["ms"]
     if rank == 0 and not args.no_sweep:
+        out["lm_wave"] = lm_wave(ctx, spec, pts, cams, x0, torch)
+        out["ba_residual_sweep"] = ba_sweep_rates(spec, local_rank, stream, dev)
+        out["batched_samples"] = batched_samples(spec, local_rank, stream, dev, torch)
+        out["cfg2_full_solve"] = cfg2_full_solve(local_rank, stream, with_cpu=not args.no_cpu)
+        out["cfg3_full"] = cfg3_full(spec, local_rank, stream, with_cpu=not args.no_cpu)
         out["roofline_sweep"] = sweep_roofline(local_rank, stream)
     if rank == 0 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(spec, pts, cams, x0, args.cpu_seconds)
-        out["ladybug_parity"] = ladybug_parity(local_rank, stream)
+        out["parity"] = parity_leg(spec, pts, cams, local_rank, stream)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -362,12 +366,184 @@ def run_ours(args):
         print(json.dumps(out))
 
 
+def e2e_leg(args, spec, pts, cams, own_p, own_c, ctx, rank, world, local_rank, host_group, dist, torch, dev):
+    x0 = spec["x0"]
+    V = spec["V"]
+    n_solves = pts.n + cams.n
+    e2e_steps = max(3, min(args.steps, 10))
+    # bytes per step.  up: the start state (8 B/variable), per batch one index blob (24 B ProblemDesc + 3 x 4 B order lists +
+    # 12 B warp task per problem, 4 B per variable id and factor id) + start values; down: 32 B result record per problem +
+    # final values.  The plugin uploads (4 B id + 8 B value) for the variables the host changed instead of the dense state.
+    h2d = 8 * V + sum(4 * len(p.vids) + 4 * len(p.fids) + 8 * len(p.vids) + 48 * p.n for p in (pts, cams))
+    d2h = sum(8 * len(p.vids) + 32 * p.n for p in (pts, cams))
+    if world == 1:
+        res = {"value": None, "unit": "solves/s", "h2d_bytes_per_step": int(h2d + 4 * V), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps}
+        drv = os.path.join(ROOT, "tests", "native", "host_driver")
+        with tempfile.TemporaryDirectory() as td:
+            bal = os.path.join(td, "ladybug.txt")
+            write_bal(spec, bal)
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+            p = subprocess.run([drv, "benchwaves", bal, str(e2e_steps), "3"], capture_output=True, text=True, env=env)
+        if p.returncode != 0:
+            raise RuntimeError("host_driver benchwaves failed: " + p.stderr[-400:])
+        d = json.loads(p.stdout.strip().splitlines()[-1])
+        res.update({"value": d["solves_per_s"], "ms_per_step": d["ms_per_step"], "objective": d["objective_after_step"],
+                    "through": "rdis::CudaSubspaceOptimizer::optimizeBatch over host Variable/Factor objects (librdis_host.so, "
+                               "tests/native/host_driver benchwaves): Variable::assign of x0, 2 sibling batches, Variable write-back; wall clock",
+                    "dispatch_ms_once": d["dispatch_ms"]})
+        # the same step through the bare C-ABI from ctypes (what round 1 reported as e2e)
+        x0_pts, x0_cams = x0[pts.vids].copy(), x0[cams.vids].copy()
+
+        def step_capi():
+            ctx.set_x(x0)
+            ra = ctx.solve_cgd(pts, x0_pts, MAXITERS, FTOL)
+            xc = ctx.get_x(cams.vids)
+            rb = ctx.solve_cgd(cams, xc, MAXITERS, FTOL)
+            return float(rb["f_end"].sum())
+        for _ in range(2):
+            step_capi()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            obj = step_capi()
+        t = time.perf_counter() - t0
+        res["c_abi_ctypes"] = {"value": n_solves * e2e_steps / t, "ms_per_step": t / e2e_steps * 1e3, "objective": obj}
+        return res
+    # N > 1: every rank solves its shard through rdisgpu_solve_cgd_csr with host buffers; the point results travel
+    # host-to-host (gloo all-gather) and are uploaded into every replica before the camera wave
+    my_pts, my_cams = pts.subset(own_p[rank]), cams.subset(own_c[rank])
+    x0_pts = x0[my_pts.vids].copy()
+    nmax = max(len(pts.subset(o).vids) for o in own_p)
+    vid_all = np.concatenate([np.concatenate([pts.subset(o).vids, np.full(nmax - len(pts.subset(o).vids), pts.subset(o).vids[0], np.int32)]) for o in own_p])
+    send = torch.zeros(nmax, dtype=torch.float64)
+    recv = torch.zeros(world * nmax, dtype=torch.float64)
+
+    def step():
+        ctx.set_x(x0)
+        ra = ctx.solve_cgd(my_pts, x0_pts, MAXITERS, FTOL)
+        send[:len(ra["x"])] = torch.from_numpy(ra["x"])
+        send[len(ra["x"]):] = float(ra["x"][0])
+        dist.all_gather_into_tensor(recv, send, group=host_group)
+        ctx.set_x(recv.numpy(), vid_all)
+        rb = ctx.solve_cgd(my_cams, None, MAXITERS, FTOL)
+        part = torch.tensor([float(rb["f_end"].sum())], dtype=torch.float64)
+        dist.all_reduce(part, group=host_group)
+        return float(part.item())
+    for _ in range(2):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        obj = step()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_e2e = float(t.item())
+    return {"value": n_solves * e2e_steps / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d + 8 * V * (world - 1) + 12 * world * nmax),
+            "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3, "objective": obj,
+            "through": "rdisgpu_solve_cgd_csr with host buffers on every rank (ctypes), point results all-gathered host-to-host (gloo), "
+                       "objective all-reduced; wall clock, max over ranks"}
+
+
+def replicas_weak(spec, pts, cams, device, stream, dev, world, dist, torch):
+    """Last round's multi-GPU figure, kept as a secondary key: every rank solves one WHOLE copy of the sibling set
+    (weak scaling; objective all-reduced)."""
+    from rdis_b200 import Context
+    ctx = Context.from_spec(spec, device=device, stream=stream.cuda_stream)
+    x0_dev = torch.from_numpy(spec["x0"]).to(dev)
+    obj = torch.zeros(1, dtype=torch.float64, device=dev)
+    bp, bc = ctx.batch(pts), ctx.batch(cams)
+    steps = 10
+    ms = []
+    for it in range(steps + 3):
+        obj.zero_()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        a.record(stream)
+        ctx.set_x_device(x0_dev.data_ptr(), spec["V"])
+        bp.solve(None, MAXITERS, FTOL)
+        bp.objective_device(obj.data_ptr())
+        bc.solve(None, MAXITERS, FTOL)
+        bc.objective_device(obj.data_ptr())
+        if world > 1:
+            dist.all_reduce(obj)
+        e.record(stream)
+        torch.cuda.synchronize()
+        if it >= 3:
+            ms.append(a.elapsed_time(e))
+    t = torch.tensor([float(np.sum(ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot = float(t.item())
+    return {"what": "one whole copy of the ladybug sibling set per rank (weak scaling), objective all-reduced", "n_gpus": world,
+            "value": world * (pts.n + cams.n) * steps / (tot * 1e-3), "unit": "solves/s", "ms_per_step": tot / steps, "scaling": "weak"}
+
+
+def lm_wave(ctx, spec, pts, cams, x0, torch):
+    """The same wave with the Levenberg-Marquardt subspace solver (BASELINE config 3: per-component LM); host buffers
+    through rdisgpu_solve_lm_csr."""
+    x0p, x0c = x0[pts.vids].copy(), x0[cams.vids].copy()
+
+    def step(maxit):
+        ctx.set_x(x0)
+        ra = ctx.solve_lm(pts, x0p, maxit, FTOL)
+        rb = ctx.solve_lm(cams, x0c, maxit, FTOL)
+        return float(ra["f_end"].sum() + rb["f_end"].sum()), ra, rb
+    res = {}
+    for label, maxit in (("ssmaxit_25", MAXITERS), ("itmax_200", 200)):
+        for _ in range(2):
+            step(maxit)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            obj, a, b = step(maxit)
+        torch.cuda.synchronize()
+        t = (time.perf_counter() - t0) / 3
+        res[label] = {"value": (pts.n + cams.n) / t, "unit": "solves/s (host buffers, rdisgpu_solve_lm_csr)", "ms_per_step": t * 1e3,
+                      "objective": obj, "iters_mean": float(np.concatenate([a["iters"], b["iters"]]).mean()),
+                      "stop_histogram": np.bincount(np.concatenate([a["stop"], b["stop"]]), minlength=8).tolist()}
+    res["stop_codes"] = "levmar: 1 small gradient, 2 small step, 3 itmax, 4 singular, 5 no further reduction, 6 small ||e||, 7 non-finite"
+    res["parity"] = "unpinned upstream (levmar not vendored); tested against oracle/lm_oracle.hpp"
+    return res
+
+
+def batched_samples(spec, device, stream, dev, torch):
+    """Throughput regime: 8 independent copies of the problem (optBA's --nsamples restarts) in ONE batch."""
+    from rdis_b200 import Context, problems as P
+    K = 8
+    spec_k = P.ba_replicate(spec, K)
+    pts_k, cams_k = P.ba_point_problems(spec_k), P.ba_camera_problems(spec_k)
+    ctx_k = Context.from_spec(spec_k, device=device, stream=stream.cuda_stream)
+    xk = torch.from_numpy(spec_k["x0"]).to(dev)
+    bpk, bck = ctx_k.batch(pts_k), ctx_k.batch(cams_k)
+    tk = []
+    for it in range(5):
+        ctx_k.set_x_device(xk.data_ptr(), spec_k["V"])
+        torch.cuda.synchronize()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        bpk.solve(None, MAXITERS, FTOL)
+        bck.solve(None, MAXITERS, FTOL)
+        e.record(stream)
+        torch.cuda.synchronize()
+        tk.append(a.elapsed_time(e))
+    ms_k = float(np.median(tk[2:]))
+    return {"what": "%d independent copies of the ladybug problem in one graph: %d point + %d camera components per wave (NOT the "
+                    "headline workload: shows the throughput regime of the same kernels)" % (K, pts_k.n, cams_k.n),
+            "ms_per_wave": ms_k, "solves_per_sec": (pts_k.n + cams_k.n) / (ms_k * 1e-3), "camera_mapping": bck.info()}
+
+
 def ba_sweep_rates(spec, device, stream, dev):
+    """residual-evals/sec of the all-factor BA sweep (evalFactors over the whole graph) and of the residual +
+    Jacobian-rows sweep (the LM path's 128 F + 8 V bytes): at ladybug size both are launch-bound (1.2 / 4.3 MB); 100
+    copies of the point cloud (> L2) show the streaming regime."""
     import torch
     from rdis_b200 import Context, problems as P
     peak, _ = peaks()
     res = {}
-    for name, K in (("ladybug_shaped", 1), ("x100_points_same_49_cameras", 100), ("x100_independent_copies_4900_cameras", -100)):
+    for name, K in (("ladybug", 1), ("x100_points_same_49_cameras", 100), ("x100_independent_copies_4900_cameras", -100)):
         sp = spec if K == 1 else (P.ba_replicate_points(spec, K) if K > 0 else P.ba_replicate(spec, -K))
         ctx = Context.from_spec(sp, device=device, stream=stream.cuda_stream)
         ctx.set_x(sp["x0"])
@@ -388,6 +564,20 @@ def ba_sweep_rates(spec, device, stream, dev):
         res[name] = {"factors": int(sp["F"]), "variables": int(sp["V"]), "ms_per_sweep": ms, "residual_evals_per_sec": sp["F"] / (ms * 1e-3),
                      "algorithmic_bytes": abytes, "achieved_GBps": abytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": abytes / (ms * 1e-3) / 1e9 / peak,
                      "sum": float(tot.item())}
+        if hasattr(ctx, "factor_rows_device"):
+            rows = torch.empty(sp["F"] * 12, dtype=torch.float64, device=dev)
+            for _ in range(3):
+                ctx.factor_rows_device(pf.data_ptr(), rows.data_ptr())
+            torch.cuda.synchronize()
+            a.record(stream)
+            for _ in range(reps):
+                ctx.factor_rows_device(pf.data_ptr(), rows.data_ptr())
+            e.record(stream)
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(e) / reps
+            rb = 128.0 * sp["F"] + 8.0 * sp["V"]
+            res[name]["jacobian_rows"] = {"ms_per_sweep": ms, "algorithmic_bytes": rb, "achieved_GBps": rb / (ms * 1e-3) / 1e9,
+                                          "frac_of_hbm_peak": rb / (ms * 1e-3) / 1e9 / peak, "residual_evals_per_sec": sp["F"] / (ms * 1e-3)}
         del ctx
     res["kernels"] = "ba_camera_table_kernel + ba_sweep_kernel (back-to-back launches, per-factor values written)"
     return res
@@ -398,7 +588,6 @@ def cfg2_full_solve(device, stream, with_cpu=True):
     default-shaped tree h=6 k=3 arity 3 (V=1093, F=3278), every variable and every factor in ONE subspace problem, SSmaxit 25,
     ftol 3e-8, seeded start.  One CTA solves it resident in shared memory (nlpf_resident.cuh); the CPU oracle solves
     the same problem from the same start on one core."""
-    import time
     import torch
     from rdis_b200 import Context, problems as P
     res = {}
@@ -419,23 +608,84 @@ def cfg2_full_solve(device, stream, with_cpu=True):
             e.record(stream)
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(e))
-        r = b.fetch(want_x=True)
-        info = b.info()
-        rec = {"V": int(spec["V"]), "F": int(spec["F"]), "ms_per_solve": float(np.min(ts[1:])), "f_init": float(r["f_init"][0]),
-               "f_end": float(r["f_end"][0]), "iters": int(r["iters"][0]), "evaluations": int(r["n_feval"][0] + r["n_geval"][0]),
-               "resident": bool(info["resident_problems"] == 1), "resident_smem_bytes": info["resident_smem_bytes"]}
+        r = b.fetch(want_x=False)
+        row = {"V": int(spec["V"]), "F": int(spec["F"]), "gpu_ms": float(min(ts[1:])), "f_init": float(r["f_init"][0]),
+               "f_end": float(r["f_end"][0]), "iters": int(r["iters"][0]), "evaluations": int(r["n_feval"][0]), "mapping": b.info()}
         if with_cpu:
             from oracle import oracle_py as O
             orc = O.OracleFunction.from_spec(spec)
             orc.set_x(x0)
+            o = orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0, MAXITERS, FTOL)
+            row.update({"cpu_oracle_ms": o["seconds"] * 1e3, "f_end_cpu": float(o["f_end"][0]),
+                        "rel_diff": float(abs(r["f_end"][0] - o["f_end"][0]) / abs(o["f_end"][0])),
+                        "speedup_vs_1_core": o["seconds"] * 1e3 / float(min(ts[1:]))})
+            sc = Context.from_spec(spec, device=device, stream=stream.cuda_stream)
+            sc.set_option("strict", 1)
+            sc.set_x(x0)
+            od = O.OracleFunction.from_spec(spec, "devtrig")
+            od.set_x(x0)
+            rs = sc.solve_cgd(ps, x0, MAXITERS, FTOL)
+            odr = od.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0, MAXITERS, FTOL)
+            row["strict_bit_identical_to_devtrig_oracle"] = bool(rs["f_end"][0] == odr["f_end"][0] and np.array_equal(rs["x"], odr["x"]))
+        res[name] = row
+        del b, ctx
+    return res
+
+
+def cfg3_full(spec, device, stream, with_cpu=True):
+    """BASELINE config 3 shape (i): the solves RDIS poses FIRST on ladybug (src/RDISOptimizer.cpp:1049-1067,1755-1764) — a
+    top-level block of round(0.2 V) variables (10 camera blocks + 1555 point blocks = 4755 variables, every factor whose
+    variables are assigned) and the whole graph as one problem (V = 23769, F = 31843), through the cooperative-grid
+    kernel.  Timed at SSmaxit 25; parity against the CPU oracle at SSmaxit 1 (one line search: the CPU needs ~1 s per
+    evaluation of the whole graph), production and strict mode."""
+    import torch
+    from rdis_b200 import Context, problems as P
+    x0 = spec["x0"]
+    ncams = spec["ncams"]
+    cam_sel, pt_sel = np.arange(10), np.arange(1555)
+    vids = np.sort(np.concatenate([(9 * cam_sel[:, None] + np.arange(9)).ravel(), (9 * ncams + 3 * pt_sel[:, None] + np.arange(3)).ravel()])).astype(np.int32)
+    fids = np.nonzero(np.isin(spec["cam"], cam_sel) | np.isin(spec["pt"], pt_sel))[0].astype(np.int64)
+    block = P.ProblemSet([0, len(vids)], vids, [0, len(fids)], fids)
+    res = {}
+    for name, ps in (("top_level_block_4755_vars", block), ("whole_graph_23769_vars", P.full_problem(spec))):
+        ctx = Context.from_spec(spec, device=device, stream=stream.cuda_stream)
+        b = ctx.batch(ps)
+        ts = []
+        for it in range(3):
+            ctx.set_x(x0)
+            torch.cuda.synchronize()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            b.solve(None, MAXITERS, FTOL)
+            e.record(stream)
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(e))
+        r = b.fetch(want_x=False)
+        row = {"nv": int(len(ps.vids)), "nf": int(len(ps.fids)), "gpu_ms_ssmaxit25": float(min(ts[1:])), "f_init": float(r["f_init"][0]),
+               "f_end": float(r["f_end"][0]), "evaluations": int(r["n_feval"][0]), "us_per_evaluation": float(min(ts[1:])) * 1e3 / max(int(r["n_feval"][0]), 1),
+               "mapping": b.info(), "kernel": "solve_grid_kernel<BaOps> (cooperative grid)"}
+        if with_cpu:
+            from oracle import oracle_py as O
+            xs = x0[ps.vids]
+            od = O.OracleFunction.from_spec(spec, "devtrig")
+            od.set_x(x0)
+            o = od.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, xs, 1, FTOL)
+            ctx.set_x(x0)
+            r1 = ctx.solve_cgd(ps, xs, 1, FTOL)
+            sc = Context.from_spec(spec, device=device, stream=stream.cuda_stream)
+            sc.set_option("strict", 1)
+            sc.set_x(x0)
             t0 = time.perf_counter()
-            o = orc.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[ps.vids], MAXITERS, FTOL)
-            rec["cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
-            rec["cpu_f_end"] = float(o["f_end"][0])
-            rec["rel_diff_f_end"] = abs(rec["f_end"] - rec["cpu_f_end"]) / max(abs(rec["cpu_f_end"]), 1e-300)
-        res[name] = rec
-        b.close()
-        del ctx
+            rs = sc.solve_cgd(ps, xs, 1, FTOL)
+            ts_strict = time.perf_counter() - t0
+            row["parity_ssmaxit1"] = {"cpu_oracle_s": o["seconds"], "f_end_cpu_devtrig": float(o["f_end"][0]), "f_end_gpu": float(r1["f_end"][0]),
+                                      "rel_diff_production": float(abs(r1["f_end"][0] - o["f_end"][0]) / abs(o["f_end"][0])),
+                                      "strict_bit_identical": bool(rs["f_end"][0] == o["f_end"][0] and np.array_equal(rs["x"], o["x"])),
+                                      "strict_host_call_ms": ts_strict * 1e3, "evaluations": int(r1["n_feval"][0]),
+                                      "cpu_seconds_per_evaluation": o["seconds"] / max(int(r1["n_feval"][0]), 1)}
+            row["estimated_cpu_s_ssmaxit25"] = o["seconds"] / max(int(r1["n_feval"][0]), 1) * int(r["n_feval"][0])
+        res[name] = row
+        del b, ctx
     return res
 
 
@@ -486,7 +736,6 @@ def cfg4_sibling_wave(device, stream, rank, world, dist, dev):
     if rank == 0:
         # the callers either side of the solve on the same graph (host buffers in and out, wall clock around the C call):
         # sibling membership (rdisgpu_components) and interval bounds of every factor (rdisgpu_bounds)
-        import time
         assigned = np.zeros(spec["V"], np.uint8); assigned[:1023] = 1     # the top 10 tree levels
         ctx.set_x(x0)
         ctx.components(assigned)
@@ -571,59 +820,32 @@ def sweep_roofline(device, stream):
     return out
 
 
-def ladybug_parity(device, stream):
-    """The same wave on the REAL ladybug-49-7776 graph (the reference's data file as parsed by the oracle's BAL
-    loader, committed as tests/golden/ladybug_49_7776.npz; x0 = the file's state, `--randinit 0`): GPU objective
-    against the CPU oracle per component.  All 7776 point components, and a sample of the camera components
-    (each costs ~0.4 s of CPU)."""
-    from rdis_b200 import Context, problems as P
+def parity_leg(spec, pts, cams, device, stream):
+    """The step's results against the CPU oracle on the SAME inputs (the real graph, the file's state), production
+    kernels: the point wave against the devtrig twin (bit identity expected) and the glibc oracle (1e-6), the full
+    step objective of the strict mode against the devtrig twin's sequence (bit identity expected).  The camera wave's
+    per-component comparison lives in profiles/r02_parity_gpu.json (tools/parity_gpu.py: minutes of CPU)."""
+    from rdis_b200 import Context
     from oracle import oracle_py as O
-    spec = P.load_golden_ba()
     x0 = spec["x0"]
-    pts, cams = P.ba_point_problems(spec), P.ba_camera_problems(spec)
     ctx = Context.from_spec(spec, device=device, stream=stream.cuda_stream)
     ctx.set_x(x0)
     f0 = ctx.eval()
-    t0 = time.perf_counter()
     rp = ctx.solve_cgd(pts, x0[pts.vids], MAXITERS, FTOL)
-    t_pts = time.perf_counter() - t0
     x1 = ctx.get_x()
-    t0 = time.perf_counter()
     rc = ctx.solve_cgd(cams, x1[cams.vids], MAXITERS, FTOL)
-    t_cams = time.perf_counter() - t0
-    f2 = ctx.eval()
-    orc = O.OracleFunction.from_spec(spec)
-    orc.set_x(x0)
-    op = orc.solve_cgd_batch(pts.var_off, pts.vids, pts.fac_off, pts.fids, x0[pts.vids], MAXITERS, FTOL)
-    rel_p = np.abs(rp["f_end"] - op["f_end"]) / np.maximum(np.abs(op["f_end"]), 1e-12)
-    # the reference's OWN sensitivity on these problems: the same CPU source compiled with FMA contraction
-    twin = None
-    try:
-        ot = O.OracleFunction.from_spec(spec, "fma")
-        ot.set_x(x0)
-        tp = ot.solve_cgd_batch(pts.var_off, pts.vids, pts.fac_off, pts.fids, x0[pts.vids], MAXITERS, FTOL)
-        rel_t = np.abs(tp["f_end"] - op["f_end"]) / np.maximum(np.abs(op["f_end"]), 1e-12)
-        twin = {"what": "CPU oracle recompiled with -mfma -ffp-contract=fast vs the CPU oracle (no FMA, like the reference build)",
-                "rel_diff_of_sums": float(abs(tp["f_end"].sum() - op["f_end"].sum()) / abs(op["f_end"].sum())),
-                "per_component_rel_diff_max": float(rel_t.max()), "components_within_1e-6": int((rel_t <= 1e-6).sum()),
-                "unstable_components_shared_with_gpu": int(((rel_t > 1e-6) & (rel_p > 1e-6)).sum())}
-    except Exception as e:  # host CPU without FMA
-        twin = {"unavailable": str(e)[:200]}
-    sample = cams.subset(range(0, cams.n, 8))
-    orc.set_x(x1)   # cameras start from the GPU's point solution, so that the two runs solve the same problems
-    oc = orc.solve_cgd_batch(sample.var_off, sample.vids, sample.fac_off, sample.fids, x1[sample.vids], MAXITERS, FTOL)
-    rel_c = np.abs(rc["f_end"][::8] - oc["f_end"]) / np.maximum(np.abs(oc["f_end"]), 1e-12)
-    return {"graph": "data/ladybug-problem-49-7776-pre.txt (tests/golden/ladybug_49_7776.npz), x0 = file state",
-            "objective_start": f0, "objective_after_points_then_cameras": f2,
-            "point_wave": {"sum_f_end_gpu": float(rp["f_end"].sum()), "sum_f_end_cpu_oracle": float(op["f_end"].sum()),
-                           "rel_diff_of_sums": float(abs(rp["f_end"].sum() - op["f_end"].sum()) / abs(op["f_end"].sum())),
-                           "per_component_rel_diff_median": float(np.median(rel_p)), "per_component_rel_diff_max": float(rel_p.max()),
-                           "components_within_1e-6": int((rel_p <= 1e-6).sum()), "components": int(pts.n),
-                           "host_call_ms": t_pts * 1e3, "cpu_oracle_s": op["seconds"], "reference_rounding_twin": twin},
-            "camera_wave_sample": {"components": int(sample.n), "per_component_rel_diff": [float(v) for v in rel_c],
-                                   "note": "25-iteration camera solves stop unconverged and are ill-conditioned; the reference's own "
-                                           "result moves by 1e-7..3e-2 under an FMA rounding perturbation (tests/test_gpu_parity.py)",
-                                   "host_call_ms": t_cams * 1e3, "cpu_oracle_s": oc["seconds"]}}
+    out = {"graph": "data/ladybug-problem-49-7776-pre.txt (tests/golden/ladybug_49_7776.npz), x0 = file state", "objective_start": f0,
+           "objective_after_points_then_cameras_production": float(rc["f_end"].sum())}
+    for variant, label in (("devtrig", "oracle_devtrig"), ("restated", "oracle_glibc")):
+        orc = O.OracleFunction.from_spec(spec, variant)
+        orc.set_x(x0)
+        op = orc.solve_cgd_batch(pts.var_off, pts.vids, pts.fac_off, pts.fids, x0[pts.vids], MAXITERS, FTOL)
+        rel = np.abs(rp["f_end"] - op["f_end"]) / np.maximum(np.abs(op["f_end"]), 1e-300)
+        out["point_wave_vs_" + label] = {"components": int(pts.n), "bit_identical": int((rp["f_end"] == op["f_end"]).sum()),
+                                         "within_1e-6": int((rel <= 1e-6).sum()), "max_rel": float(rel.max()),
+                                         "rel_diff_of_sums": float(abs(rp["f_end"].sum() - op["f_end"].sum()) / abs(op["f_end"].sum())),
+                                         "cpu_oracle_s": op["seconds"]}
+    return out
 
 
 def cpu_baseline(spec, pts, cams, x0, budget_s):
@@ -667,11 +889,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from rdis_b200 import problems  # host-side generators only (numpy); no kernel is launched on this arm
+    problems = load_problems_module()  # numpy only: librdis_b200.so is never mapped on this arm
     from oracle import oracle_py as O
     O.build()
     variant = "refnrc" if O.have_refnrc() else "restated"
-    spec = problems.ba_synthetic(seed=SEED)
+    spec = problems.load_golden_ba()
     x0 = spec["x0"]
     pts, cams = problems.ba_point_problems(spec), problems.ba_camera_problems(spec)
     nthreads = max(1, os.cpu_count() or 1)
@@ -711,13 +933,11 @@ def run_reference(args):
     wave_s = float(np.mean(wave))
     value = (pts.n + cams.n) / wave_s
     sample = ("each step: %d of %d point + %d of %d camera components on %d threads (one function replica per thread), "
-              "scaled to the 7825-solve wave" % (ps_pt.n, pts.n, ps_cam.n, cams.n, nthreads))
+              "scaled to the 7825-solve wave; the total work is the same at every N (strong scaling)" % (ps_pt.n, pts.n, ps_cam.n, cams.n, nthreads))
     out = {"impl": "reference", "metric": "subspace-solves/sec", "value": value, "unit": "solves/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wave_s * 1e3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "ladybug-49-7776-shaped BA graph (49 cams, 7776 pts, 31843 obs): "
-                                  "7776 point-component + 49 camera-component CGD solves per step",
-                      "ssmaxit": MAXITERS, "ssftol": FTOL, "seed": SEED},
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": DATA,
+           "config": config(args.gpus),
            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": nthreads,
                             "kind": "port", "sample": sample,
                             "driver": "reference minimize_nrc.h (oracle/_ref)" if variant == "refnrc" else "restated NR driver"},

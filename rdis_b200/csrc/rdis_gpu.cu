@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -966,6 +967,49 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
     }
   }
 
+  // sibling check, second half: a factor of problem p may read variables of p and FROZEN variables only.  A variable
+  // owned by another problem of the batch would be rewritten concurrently by that problem's thread group (the
+  // reference sees it as an assigned, fixed value): not a sibling set -> RDISGPU_ERR_OVERLAP.
+  {
+    const bool ba = (ctx->kind == KIND_BA);
+    const int32_t pbase = 9 * ctx->ncams;
+    std::atomic<int> foreign{0};
+    auto check_range = [&](int64_t p0, int64_t p1) {
+      for (int64_t p = p0; p < p1 && !foreign.load(std::memory_order_relaxed); ++p) {
+        const ProblemDesc& D = b->h_probs[p];
+        const int32_t* pf = fids + D.fac_off;
+        for (int k = 0; k < D.nf; ++k) {
+          if (ba) {
+            const int32_t cb = 9 * ctx->h_cam[pf[k]], qb = pbase + 3 * ctx->h_pt[pf[k]];
+            for (int sl = 0; sl < 12; ++sl) {
+              const int32_t v = (sl < 9) ? cb + sl : qb + (sl - 9);
+              if (ctx->vmark[v] == epoch && ctx->vowner[v] != (int32_t)p) foreign.store(1, std::memory_order_relaxed);
+            }
+          } else {
+            for (int32_t e = ctx->h_rp32[pf[k]]; e < ctx->h_rp32[pf[k] + 1]; ++e) {
+              const int32_t v = ctx->h_evid32[e];
+              if (ctx->vmark[v] == epoch && ctx->vowner[v] != (int32_t)p) foreign.store(1, std::memory_order_relaxed);
+            }
+          }
+        }
+      }
+    };
+    const unsigned hwc = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (tf >= 200000 && nprobs >= 2 * (int64_t)hwc && hwc > 1) {
+      std::vector<std::thread> pool;
+      const int64_t per = (nprobs + hwc - 1) / hwc;
+      for (unsigned t = 0; t < hwc; ++t) {
+        const int64_t p0 = std::min<int64_t>(nprobs, (int64_t)t * per), p1 = std::min<int64_t>(nprobs, p0 + per);
+        if (p0 < p1) pool.emplace_back(check_range, p0, p1);
+      }
+      for (std::thread& th : pool) th.join();
+    } else {
+      check_range(0, nprobs);
+    }
+    if (foreign.load())
+      return ctx->fail(RDISGPU_ERR_OVERLAP, "batch: a factor of one problem reads a variable owned by another problem of the batch");
+  }
+
   // size classes: tiles of 1..32 lanes, CTAs of 64..256 threads, cooperative grid
   const int kTileMax = 32, kBlockMax = 4096;
   std::vector<std::vector<int32_t>> tile_lists(6), block_lists(3);
@@ -1050,8 +1094,7 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
           for (int32_t e = ctx->h_rp32[pf[k]]; e < ctx->h_rp32[pf[k] + 1]; ++e) {
             const int32_t v = ctx->h_evid32[e];
             if (ctx->vmark[v] != epoch) ++c.nFz;                       // frozen variable: a constant term
-            else if (ctx->vowner[v] != (int32_t)p) c.ok = false;        // not a sibling set: leave it to the generic path
-            ++c.nE;
+            ++c.nE;                                                     // (foreign owners were rejected above)
           }
         }
         cnt[(size_t)p] = c;

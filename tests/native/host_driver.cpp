@@ -4,9 +4,11 @@
 //   children <file>            ComponentBatcher::createChildren over the unassigned variables (no GPU needed)
 //   children_gpu <file>        ComponentBatcher::createChildrenOnDevice: the same listing through rdisgpu_components
 //   wave <file> <maxiters>     one sibling wave through CudaSubspaceOptimizer::optimizeBatch
+//   benchwaves <bal> <steps> <warmup>   bench.py's end-to-end leg (timed alternating waves on a BAL file)
 //   single <file> <maxiters>   the same wave, one CudaSubspaceOptimizer::optimize call per child
 //                              (the reference's sibling loop, src/RDISOptimizer.cpp:291-314)
 // Output is plain text with %.17g numbers; the Python side compares it with the ctypes path and the oracle.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +18,7 @@
 
 #include "rdis_builders.h"
 #include "rdis_host.h"
+#include "../../include/rdis_gpu.h"
 
 using namespace rdis;
 
@@ -139,6 +142,65 @@ int main(int argc, char** argv) {
         std::printf("wave %d %s components %zu sum %.17g objective %.17g\n", rd, points ? "points" : "cameras", kids.size(), total,
                     fn.eval());
       }
+      return 0;
+    }
+    if (std::string(argv[1]) == "benchwaves") {
+      // benchwaves <bal file> <steps> <warmup> [strict]: bench.py's end-to-end leg.  One step = what the tree search
+      // does for one alternating wave through the plugin surface with HOST objects: Variable::assign of the start state
+      // (queued, uploaded by the adapter), CudaSubspaceOptimizer::optimizeBatch over the point components (index
+      // lists + start values up, results down, Variable write-back), the same over the camera components.  Wall
+      // clock around the steps; the sibling sets are built once before (their cost is printed as dispatch_ms).
+      BundleAdjustmentFunction fn;
+      if (!fn.load(argv[2])) return 1;
+      const int steps = argc > 3 ? std::atoi(argv[3]) : 10, warmup = argc > 4 ? std::atoi(argv[4]) : 3;
+      fn.init(0);
+      if (argc > 5 && std::string(argv[5]) == "strict") rdisgpu_set_option(fn.device(), "strict", 1);
+      CudaSubspaceOptimizer ssopt(fn);
+      ParameterMap opts;
+      opts["SSmaxit"] = 25;
+      opts["SSftol"] = 3e-8;
+      ssopt.setParameters(opts);
+      const NumericVec& x0 = fn.getInitialState();
+      VariablePtrVec& vars = fn.getVariables();
+      for (Variable* v : vars) v->assign(x0[(size_t)v->getID()]);
+      const VariableID npv = 9 * fn.getNumCameras();
+      std::vector<ComponentProblem> waves[2];
+      const auto d0 = std::chrono::steady_clock::now();
+      for (int side = 0; side < 2; ++side) {  // 0: points open (cameras fixed), 1: cameras open
+        VariableIDVec open;
+        for (Variable* v : vars)
+          if ((v->getID() >= npv) == (side == 0)) {
+            v->unassign();
+            open.push_back(v->getID());
+          }
+        std::vector<ChildComponent> kids;
+        ComponentBatcher::createChildren(fn, open, kids);
+        waves[side].resize(kids.size());
+        for (size_t k = 0; k < kids.size(); ++k) ComponentBatcher::leafProblem(fn, kids[k], x0, waves[side][k]);
+        for (VariableID vid : open) vars[(size_t)vid]->assign(x0[(size_t)vid]);
+      }
+      const double dispatch_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - d0).count();
+      double total_ms = 0, objective = 0, pts_sum = 0;
+      for (int it = 0; it < warmup + steps; ++it) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (Variable* v : vars) v->assign(x0[(size_t)v->getID()]);
+        for (int side = 0; side < 2; ++side) {
+          for (ComponentProblem& p : waves[side])
+            for (size_t i = 0; i < p.vars.size(); ++i) p.xval[i] = (side == 0) ? x0[(size_t)p.vars[i]->getID()] : p.vars[i]->eval();
+          const double tot = ssopt.optimizeBatch(waves[side], false);
+          if (side == 0) pts_sum = tot; else objective = tot;
+        }
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (it >= warmup) total_ms += ms;
+      }
+      size_t nsolves = waves[0].size() + waves[1].size(), nv = 0, nf = 0;
+      for (int side = 0; side < 2; ++side)
+        for (const ComponentProblem& p : waves[side]) { nv += p.vars.size(); nf += p.factors.size(); }
+      std::printf("{\"solves_per_step\": %zu, \"steps\": %d, \"warmup\": %d, \"ms_per_step\": %.6f, \"solves_per_s\": %.3f, "
+                  "\"objective_after_step\": %.17g, \"point_wave_sum\": %.17g, \"dispatch_ms\": %.3f, \"vars_in_problems\": %zu, "
+                  "\"factors_in_problems\": %zu, \"V\": %lld}\n",
+                  nsolves, steps, warmup, total_ms / steps, nsolves * steps / (total_ms * 1e-3), objective, pts_sum, dispatch_ms, nv, nf,
+                  fn.getNumVars());
       return 0;
     }
     if (std::string(argv[1]) == "sinusoid") {  // sinusoid <height> <branches> <maxArity> <odd>

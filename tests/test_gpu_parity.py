@@ -321,6 +321,27 @@ def test_edge_cases(gpu, oracle_mod):
                                  (pts.vids[0:3], pts.fids[pts.fac_off[1]:pts.fac_off[2]])])
     with pytest.raises(RdisGpuError):
         ctx.solve_cgd(bad, x0[bad.vids])
+    # ... and so is a batch in which a factor of one problem reads a variable another problem of the batch owns (a
+    # point block and the camera block that observes it are not siblings: the reference would hold one of them fixed)
+    cams = P.ba_camera_problems(spec)
+    c0 = int(spec["cam"][pts.fids[pts.fac_off[0]]])
+    mixed = ProblemSet.from_lists([(pts.vids[0:3], pts.fids[pts.fac_off[0]:pts.fac_off[1]]),
+                                   (cams.vids[9 * c0:9 * c0 + 9], cams.fids[cams.fac_off[c0]:cams.fac_off[c0 + 1]][1:])])
+    with pytest.raises(RdisGpuError, match="owned by another problem"):
+        ctx.solve_cgd(mixed, x0[mixed.vids])
+    tree = P.sinusoid(5, 2, 4)
+    tctx = Context.from_spec(tree)
+    tctx.set_x(P.random_start(tree, 1))
+    halves = P.sinusoid_subtree_problems(tree, 1)          # the root's two subtrees: proper siblings once the root is assigned
+    tctx.solve_cgd(halves, None)
+    V = tree["V"]
+    allf = np.arange(tree["F"], dtype=np.int64)
+    lo = np.arange(0, V // 2, dtype=np.int32); hi = np.arange(V // 2, V, dtype=np.int32)
+    first = np.array([f for f in allf if tree["vid"][tree["rowptr"][f]:tree["rowptr"][f + 1]].min() < V // 2], np.int64)
+    rest = np.setdiff1d(allf, first)
+    torn = ProblemSet.from_lists([(lo, first), (hi, rest)])  # an arbitrary cut of the variable ids: factors straddle it
+    with pytest.raises(RdisGpuError, match="owned by another problem"):
+        tctx.solve_cgd(torn, None)
     # a start point outside the domain is clamped on entry (quickAssignVals, sanitize=true)
     one = pts.subset([0])
     far = x0[one.vids] + 1e9
