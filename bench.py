@@ -608,7 +608,7 @@ def cfg2_full_solve(device, stream, with_cpu=True):
             e.record(stream)
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(e))
-        r = b.fetch(want_x=False)
+        r = b.fetch()
         row = {"V": int(spec["V"]), "F": int(spec["F"]), "gpu_ms": float(min(ts[1:])), "f_init": float(r["f_init"][0]),
                "f_end": float(r["f_end"][0]), "iters": int(r["iters"][0]), "evaluations": int(r["n_feval"][0]), "mapping": b.info()}
         if with_cpu:
@@ -628,7 +628,8 @@ def cfg2_full_solve(device, stream, with_cpu=True):
             odr = od.solve_cgd_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0, MAXITERS, FTOL)
             row["strict_bit_identical_to_devtrig_oracle"] = bool(rs["f_end"][0] == odr["f_end"][0] and np.array_equal(rs["x"], odr["x"]))
         res[name] = row
-        del b, ctx
+        b.close()
+        del ctx
     return res
 
 
@@ -660,7 +661,7 @@ def cfg3_full(spec, device, stream, with_cpu=True):
             e.record(stream)
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(e))
-        r = b.fetch(want_x=False)
+        r = b.fetch()
         row = {"nv": int(len(ps.vids)), "nf": int(len(ps.fids)), "gpu_ms_ssmaxit25": float(min(ts[1:])), "f_init": float(r["f_init"][0]),
                "f_end": float(r["f_end"][0]), "evaluations": int(r["n_feval"][0]), "us_per_evaluation": float(min(ts[1:])) * 1e3 / max(int(r["n_feval"][0]), 1),
                "mapping": b.info(), "kernel": "solve_grid_kernel<BaOps> (cooperative grid)"}
@@ -685,7 +686,8 @@ def cfg3_full(spec, device, stream, with_cpu=True):
                                       "cpu_seconds_per_evaluation": o["seconds"] / max(int(r1["n_feval"][0]), 1)}
             row["estimated_cpu_s_ssmaxit25"] = o["seconds"] / max(int(r1["n_feval"][0]), 1) * int(r["n_feval"][0])
         res[name] = row
-        del b, ctx
+        b.close()
+        del ctx
     return res
 
 

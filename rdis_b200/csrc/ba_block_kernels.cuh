@@ -353,8 +353,18 @@ struct CamShared {
 // send round r+1 after its thread 0 folded round r, and nobody finishes round r+1 before every CTA of the cluster has
 // sent it.  `phase` holds the two barriers' parities.  The caller's __syncthreads after thread 0's scalar step
 // orders the next evaluation's wred writes after this fold.
+#ifdef RDIS_CAM_PROFILE
+#define CAMPROF(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); prof[i] += t_ - tlast; tlast = t_; } } while (0)
+#define CAMPROF_ARGS , long long* prof, long long& tlast
+#define CAMPROF_PASS , prof, tlast
+#else
+#define CAMPROF(i) do { } while (0)
+#define CAMPROF_ARGS
+#define CAMPROF_PASS
+#endif
+
 template <int N>
-__device__ __forceinline__ void cluster_reduce_to_thread0(CamShared& sh, int& flip, uint32_t& phase, double (&v)[N], int C, int cta) {
+__device__ __forceinline__ void cluster_reduce_to_thread0(CamShared& sh, int& flip, uint32_t& phase, double (&v)[N], int C, int cta CAMPROF_ARGS) {
   static_assert(N % 2 == 0, "partials travel as 16-byte pairs");
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -366,7 +376,9 @@ __device__ __forceinline__ void cluster_reduce_to_thread0(CamShared& sh, int& fl
 #pragma unroll
     for (int i = 0; i < N; ++i) sh.wred[warp][i] = v[i];
   }
+  CAMPROF(1);  // evaluation + warp butterfly (thread 0's view)
   __syncthreads();
+  CAMPROF(2);  // waiting for the CTA's other warps
   if (warp != 0) return;
   if (C == 1) {
     if (lane == 0) {
@@ -395,8 +407,10 @@ __device__ __forceinline__ void cluster_reduce_to_thread0(CamShared& sh, int& fl
 #pragma unroll
     for (int i = 0; i < N; i += 2) st_async_v2(dst + 8u * i, c[i], c[i + 1], bar);
   }
+  CAMPROF(3);  // fold of the warp partials + st.async issue
   if (lane == 0) {
     mbar_wait_cluster(&sh.mbar[flip], (phase >> flip) & 1u);
+    CAMPROF(4);  // waiting for the peers' partials
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = sh.red[flip][0][i];
     for (int s = 1; s < C; ++s) {
@@ -469,9 +483,21 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
   double f_init = 0.0, c_sum = 0.0, f_at_p = 0.0;
   bool c_dirty = true, c_assigned = false;
 
+#ifdef RDIS_CAM_PROFILE
+  long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long profx[3] = {0, 0, 0};
+  int nslope = 0;
+  long long tlast = clock64();
+  const long long tstart = tlast;
+  int nev = 0;
+#endif
   while (true) {
     const int kind = sh.m.req;
     if (kind == REQ_DONE) break;
+    CAMPROF(0);  // barrier release -> request read
+#ifdef RDIS_CAM_PROFILE
+    ++nev;
+#endif
     const bool along = (kind == REQ_VALUE) || (kind == REQ_VALUE_SLOPE);
     const bool want_g = (kind != REQ_VALUE);
     const double alpha = sh.m.alpha;
@@ -483,6 +509,9 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
     }
     BaOps::Fwd m;
     BaOps::rotation(x[0], x[1], x[2], m);
+#ifdef RDIS_CAM_PROFILE
+    if (threadIdx.x == 0 && m.s != 2.0) { const long long t_ = clock64(); profx[0] += t_ - tlast; tlast = t_; }
+#endif
 
     // this thread's observations: round 0 from registers, later rounds (more observations than
     // threads in the cluster) re-read their frozen block through L1/L2
@@ -518,7 +547,10 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
         if (fc_on) fv = fc_val;
         v2[0] += fv;
       }
-      cluster_reduce_to_thread0<2>(sh, flip, phase, v2, C, cta);
+#ifdef RDIS_CAM_PROFILE
+      if (threadIdx.x == 0 && v2[0] != -1.0) { const long long t_ = clock64(); profx[want_g ? 2 : 1] += t_ - tlast; tlast = t_; if (want_g) ++nslope; }
+#endif
+      cluster_reduce_to_thread0<2>(sh, flip, phase, v2, C, cta CAMPROF_PASS);
     } else {
       double acc[kCamRedWidth];
 #pragma unroll
@@ -536,10 +568,11 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
         if (fc_on) fv = fc_val;
         acc[0] += fv;
       }
-      cluster_reduce_to_thread0<kCamRedWidth>(sh, flip, phase, acc, C, cta);
+      cluster_reduce_to_thread0<kCamRedWidth>(sh, flip, phase, acc, C, cta CAMPROF_PASS);
     }
 
     // ---- the scalar step (thread 0 of every CTA, identical inputs in every CTA of the cluster) ----
+    CAMPROF(5);  // fold of the cluster's partials
     if (threadIdx.x == 0) {
       CgdMachine mc = sh.m;  // registers for the duration of the step only (one burst of loads instead of dependent ones)
       // Variable::assign of this evaluation's point (src/Variable.cpp:66-88): a move below 1e-12 notifies nobody
@@ -549,6 +582,7 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
         sh.last[j] = x[j];
       }
       c_assigned = true;
+      CAMPROF(6);  // machine copy-in + Variable::assign bookkeeping
       auto cache_eval = [&](double fresh) {  // Factor::eval over the list, src/Factor.cpp:110-119
         if (c_dirty) {
           c_sum = fresh;
@@ -603,10 +637,22 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
       // fa = func(ax = 0) at the top of a line search (minimize_nrc.h:88): clamp(p) is the point the gradient pass
       // assigned and f_at_p its objective — answered from the cache rules without another pass
       if (mc.req == REQ_VALUE && mc.phase == CgdMachine::PH_BR_FA) mc.on_eval(cache_eval(f_at_p), 0.0);
+      CAMPROF(7);  // machine step + vector updates
       sh.m = mc;
+      CAMPROF(8);  // machine copy-out
     }
     __syncthreads();
+    CAMPROF(9);  // closing barrier
   }
+#ifdef RDIS_CAM_PROFILE
+  if (threadIdx.x == 0 && cta == 0 && (blockIdx.x / C) < 4)
+    printf("camprof prob %d: x+rotation %lld per eval; value-only obs pass %lld per value eval (%d); value+slope obs pass %lld per slope eval (%d); eval includes butterfly\n",
+           pidx, profx[0] / nev, profx[1] / (nev - nslope > 0 ? nev - nslope : 1), nev - nslope, profx[2] / (nslope > 0 ? nslope : 1), nslope);
+  if (threadIdx.x == 0 && cta == 0 && (blockIdx.x / C) < 4)
+    printf("camprof prob %d nf %d evals %d cycles/eval %lld | req %lld eval %lld bar1 %lld wfold+send %lld peerwait %lld cfold %lld copyin+assign %lld machine %lld copyout %lld bar2 %lld\n",
+           pidx, nf, nev, (clock64() - tstart) / (nev > 0 ? nev : 1), prof[0] / nev, prof[1] / nev, prof[2] / nev, prof[3] / nev, prof[4] / nev,
+           prof[5] / nev, prof[6] / nev, prof[7] / nev, prof[8] / nev, prof[9] / nev);
+#endif
 
   // ---- commit (CGD.cpp:61-89): quickAssignVals(gdmin.p); if worse than the start the start point is re-assigned and
   //      re-evaluated through the cache.  CTA 0 of the cluster writes. ----
