@@ -322,117 +322,53 @@ __global__ void __launch_bounds__(32) solve_ba_points_kernel(GraphView Gv, Batch
 #ifndef RDIS_CAM_THREADS
 #define RDIS_CAM_THREADS 192
 #endif
-#ifndef RDIS_CAM_MIN_CTAS
-#define RDIS_CAM_MIN_CTAS 2
+#ifndef RDIS_CAM_MAXREG
+#define RDIS_CAM_MAXREG 128  // 3 CTAs of 128 + 32 threads per SM (measured: 3.28 ms per ladybug camera wave against 3.64 at 168)
 #endif
-// 2 CTAs per SM at <= 168 registers: clusters can be wide enough for one observation per thread
-constexpr int kCamMaxThreads = RDIS_CAM_THREADS;
+constexpr int kCamMaxThreads = RDIS_CAM_THREADS;          // WORKER threads of a CTA (one more warp runs the solve's scalar side)
 constexpr int kCamMaxCluster = 8;
-constexpr int kCamMaxWarps = kCamMaxThreads / 32;
-constexpr int kCamRedWidth = 10;  // f + 9 partials (gradient mode); f + slope use the first two
+constexpr int kCamMaxWorkerWarps = kCamMaxThreads / 32;
+constexpr int kCamMaxRows = kCamMaxCluster * kCamMaxWorkerWarps;  // warp partials of a whole cluster
+constexpr int kCamRedWidth = 10;  // f + 9 partials (gradient evaluations); f + slope use the first two
 
-struct CamShared {
-  double p[9], xi[9], g[9], h[9], xs[9];
-  double last[9];  // Variable::eval() of the camera's variables: the point of the previous evaluation (thread 0 only)
-  double2 dom[9];
-  double wred[kCamMaxWarps][kCamRedWidth];          // warp partials of this CTA (first reduction level)
-  double red[2][kCamMaxCluster][kCamRedWidth];      // CTA partials of the whole cluster (second level, double-buffered)
-  unsigned long long mbar[2];  // one transaction barrier per reduction buffer (remote st.async completes on it)
-  CgdMachine m;                // advanced by thread 0 of every CTA of the cluster on identical inputs
-  double tot[kCamRedWidth];    // the all-reduced sums of the current evaluation (thread 0 -> nobody else needs them)
+// What the scalar warp publishes for one evaluation and the worker warps read.
+struct CamRequest {
+  int kind, pad;
+  double x[9];                      // the evaluation's point, clamped into the domain (quickAssignVals)
+  double a0, a1, a2, theta, s, c;   // BaOps::rotation of it: computed once per evaluation, not once per observation
+  double xi[9];                     // the search direction (directional derivative of slope evaluations)
 };
 
-// Sum of N doubles per thread over the whole cluster into sh.tot of EVERY CTA (read by thread 0 only), fixed order,
-// two levels:
-//   (1) warp butterfly, warp partials folded per CTA through shared memory (one __syncthreads);
-//   (2) lane d of warp 0 pushes the CTA's partial into slot `cta` of CTA d's buffer with an ASYNCHRONOUS
-//       store over distributed shared memory that completes a transaction barrier in the receiving CTA
-//       (st.async ... mbarrier::complete_tx); thread 0 waits for its own barrier to have received C*N*8
-//       bytes and folds the C partials in CTA order: one one-way trip per evaluation, no cluster barrier.
-// The cluster buffers (and their barriers) alternate; re-use two rounds later is safe because a CTA can only
-// send round r+1 after its thread 0 folded round r, and nobody finishes round r+1 before every CTA of the cluster has
-// sent it.  `phase` holds the two barriers' parities.  The caller's __syncthreads after thread 0's scalar step
-// orders the next evaluation's wred writes after this fold.
-#ifdef RDIS_CAM_PROFILE
-#define CAMPROF(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); prof[i] += t_ - tlast; tlast = t_; } } while (0)
-#define CAMPROF_ARGS , long long* prof, long long& tlast
-#define CAMPROF_PASS , prof, tlast
-#else
-#define CAMPROF(i) do { } while (0)
-#define CAMPROF_ARGS
-#define CAMPROF_PASS
-#endif
+struct CamShared {
+  CamRequest rq;
+  alignas(16) double red[2][kCamMaxRows][kCamRedWidth];  // (16-byte pairs travel by st.async.v2) warp partials of the whole cluster, indexed by the warp's rank in the cluster; double-buffered
+  unsigned long long mbar[2];                // one transaction barrier per buffer (the peers' st.async complete on it)
+};
 
-template <int N>
-__device__ __forceinline__ void cluster_reduce_to_thread0(CamShared& sh, int& flip, uint32_t& phase, double (&v)[N], int C, int cta CAMPROF_ARGS) {
-  static_assert(N % 2 == 0, "partials travel as 16-byte pairs");
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) sh.wred[warp][i] = v[i];
-  }
-  CAMPROF(1);  // evaluation + warp butterfly (thread 0's view)
-  __syncthreads();
-  CAMPROF(2);  // waiting for the CTA's other warps
-  if (warp != 0) return;
-  if (C == 1) {
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) v[i] = sh.wred[0][i];
-      for (int w = 1; w < nw; ++w) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) v[i] += sh.wred[w][i];
-      }
-#pragma unroll
-      for (int i = 0; i < N; ++i) sh.tot[i] = v[i];
-    }
-    return;
-  }
-  if (lane == 0) mbar_arrive_expect_tx(&sh.mbar[flip], (uint32_t)(C * N * 8));
-  if (lane < C) {  // lane d delivers this CTA's partial to CTA d
-    double c[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) c[i] = sh.wred[0][i];
-    for (int w = 1; w < nw; ++w) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) c[i] += sh.wred[w][i];
-    }
-    const uint32_t dst = map_to_cta(smem_addr_u32(&sh.red[flip][cta][0]), (uint32_t)lane);
-    const uint32_t bar = map_to_cta(smem_addr_u32(&sh.mbar[flip]), (uint32_t)lane);
-#pragma unroll
-    for (int i = 0; i < N; i += 2) st_async_v2(dst + 8u * i, c[i], c[i + 1], bar);
-  }
-  CAMPROF(3);  // fold of the warp partials + st.async issue
-  if (lane == 0) {
-    mbar_wait_cluster(&sh.mbar[flip], (phase >> flip) & 1u);
-    CAMPROF(4);  // waiting for the peers' partials
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = sh.red[flip][0][i];
-    for (int s = 1; s < C; ++s) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) v[i] += sh.red[flip][s][i];
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) sh.tot[i] = v[i];
-  }
-  phase ^= (1u << flip);
-  flip ^= 1;
-}
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// grid = nprobs * C CTAs, cluster = C CTAs (set at launch), `order` lists the camera-class problems.
+// grid = nprobs * C CTAs, cluster = C CTAs (set at launch), blockDim = T worker threads + one scalar warp, C*T >= the
+// largest factor list of the batch (one observation per worker thread); `order` lists the camera-class problems.
 //
-// One evaluation = [all threads] read the request (kind, alpha) and the camera state from shared memory, form the
-// point, the rotation, their observation's value (+ partials), reduce over the cluster; [thread 0 of every CTA] the
-// scalar step: the value cache (BlockCache semantics), the CgdMachine, and the 9-element vector updates it asks for
-// (move, gradient bookkeeping, new direction); one CTA barrier.  Keeping the machine out of the other threads'
-// registers is what lets the observation arithmetic run without spills at 2-3 CTAs per SM.
-__global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_cameras_kernel(GraphView Gv, BatchView B, const int32_t* order,
-                                                                          int C, int maxiters, double ftol) {
+// WARP-SPECIALISED.  The solve is a chain of <= ~1200 dependent objective evaluations; what can be shortened is what
+// happens between two of them, so the scalar side never shares a thread with the observation arithmetic:
+//   scalar warp (the last warp of every CTA; identical in every CTA of the cluster on identical inputs)
+//       lane 0 keeps the CgdMachine and the value cache (BlockCache semantics), lane j < 9 variable j of the camera
+//       (p, xi, g, h, domain) in REGISTERS for the whole solve; per evaluation it forms the clamped point lane-parallel
+//       and its rotation (sqrt, 3 divisions, sincos: once, not once per observation), publishes the request through
+//       shared memory and releases the workers with a named barrier; then waits on the buffer's transaction barrier,
+//       folds the cluster's warp partials with a lane-parallel fixed tree and steps.
+//   worker warps: read the request, evaluate their observation (BaOps::project / partials, the operands of the frozen
+//       point block staged in registers for the life of the solve), butterfly-reduce inside the warp, and lanes < C
+//       push the warp's partial into the slot [warp's rank in the cluster] of every CTA with ASYNCHRONOUS stores over
+//       distributed shared memory that complete the receiving CTA's transaction barrier (st.async ... complete_tx):
+//       one one-way trip, no CTA barrier and no cluster barrier on the way.
+// The fold order is a function of the observation index only (warp partial = butterfly over 32 consecutive
+// observations; partials folded by rank mod 4 into four chains, chains combined pairwise), so the result does not
+// depend on the cluster shape the launch picked.
+__global__ void __maxnreg__(RDIS_CAM_MAXREG) solve_ba_cameras_kernel(GraphView Gv, BatchView B, const int32_t* order,
+                                                                               int C, int maxiters, double ftol) {
   namespace cgn = cooperative_groups;
   cgn::cluster_group cluster = cgn::this_cluster();
   __shared__ CamShared sh;
@@ -441,247 +377,306 @@ __global__ void __launch_bounds__(kCamMaxThreads, RDIS_CAM_MIN_CTAS) solve_ba_ca
   const ProblemDesc P = B.probs[pidx];
   const int nf = P.nf;
   const int32_t v0 = B.vids[P.var_off];
-  const int T = blockDim.x;
-  const int rank = cta * T + threadIdx.x;
-  const int size = C * T;
-  int flip = 0;
-  uint32_t phase = 0;
+  const int T = (int)blockDim.x - 32;        // worker threads
+  const int W = T >> 5;                       // worker warps per CTA
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool scalar_warp = (warp == W);
+  const int nthreads = (int)blockDim.x;
   if (threadIdx.x == 0) {
     mbar_init(&sh.mbar[0], 1);
     mbar_init(&sh.mbar[1], 1);
     mbar_fence_init();
-    sh.m.start(maxiters, ftol, /*faithful=*/true);
-  }
-  if (threadIdx.x < 9) {
-    const int j = threadIdx.x;
-    const double xv = (B.x0 != nullptr) ? B.x0[P.var_off + j] : Gv.xbd[v0 + j].x;
-    sh.p[j] = xv; sh.xs[j] = xv; sh.xi[j] = 0.0; sh.g[j] = 0.0; sh.h[j] = 0.0;
-    sh.last[j] = 0.0;
-    sh.dom[j] = __ldg(&Gv.dom[v0 + j]);
-  }
-  // this thread's first observation: frozen point block + pixel staged in registers
-  const bool have = (rank < nf);
-  double q0 = 0.0, q1 = 0.0, q2 = 0.0;
-  double2 ob0 = make_double2(0.0, 0.0);
-  bool fc_on0 = false;
-  double fc_val0 = 0.0;
-  const int32_t pbase = 9 * Gv.ncams;
-  if (have) {
-    const int32_t fid = B.fids[P.fac_off + rank];
-    const int32_t pt = __ldg(&Gv.pt[fid]);
-    ob0 = __ldg(&Gv.obs[fid]);
-    q0 = Gv.xbd[pbase + 3 * pt].x; q1 = Gv.xbd[pbase + 3 * pt + 1].x; q2 = Gv.xbd[pbase + 3 * pt + 2].x;
-    if (Gv.fconst_on != nullptr && Gv.fconst_on[fid]) {
-      fc_on0 = true;
-      fc_val0 = Gv.fconst_val[fid];
-    }
   }
   __syncthreads();
   if (C > 1) cluster.sync();  // every CTA's barriers are initialised before a peer's st.async can reach them
 
-  // thread 0's private scalars: the value cache of the block (BlockCache semantics) and the solve's bookkeeping
-  double f_init = 0.0, c_sum = 0.0, f_at_p = 0.0;
-  bool c_dirty = true, c_assigned = false;
-
-#ifdef RDIS_CAM_PROFILE
-  long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  long long profx[3] = {0, 0, 0};
-  int nslope = 0;
-  long long tlast = clock64();
-  const long long tstart = tlast;
-  int nev = 0;
-#endif
-  while (true) {
-    const int kind = sh.m.req;
-    if (kind == REQ_DONE) break;
-    CAMPROF(0);  // barrier release -> request read
-#ifdef RDIS_CAM_PROFILE
-    ++nev;
-#endif
-    const bool along = (kind == REQ_VALUE) || (kind == REQ_VALUE_SLOPE);
-    const bool want_g = (kind != REQ_VALUE);
-    const double alpha = sh.m.alpha;
+  if (!scalar_warp) {
+    // ------------------------------------------------------------------ workers
+    const int rank = cta * T + threadIdx.x;   // = index of this thread's observation in the problem's factor list
+    const int grow = cta * W + warp;          // this warp's rank in the cluster = its row of the reduction buffers
+    const bool have = (rank < nf);
     double x[12];
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const double pj = sh.p[j];
-      x[j] = clamp_to_domain(along ? (pj + alpha * sh.xi[j]) : pj, sh.dom[j]);
-    }
-    BaOps::Fwd m;
-    BaOps::rotation(x[0], x[1], x[2], m);
-#ifdef RDIS_CAM_PROFILE
-    if (threadIdx.x == 0 && m.s != 2.0) { const long long t_ = clock64(); profx[0] += t_ - tlast; tlast = t_; }
-#endif
-
-    // this thread's observations: round 0 from registers, later rounds (more observations than
-    // threads in the cluster) re-read their frozen block through L1/L2
-    auto stage = [&](int k, double2& ob, bool& fc_on, double& fc_val) {
-      if (k == rank) {
-        x[9] = q0; x[10] = q1; x[11] = q2; ob = ob0; fc_on = fc_on0; fc_val = fc_val0;
-      } else {
-        const int32_t fid = B.fids[P.fac_off + k];
-        const int32_t pt = __ldg(&Gv.pt[fid]);
-        ob = __ldg(&Gv.obs[fid]);
-        x[9] = Gv.xbd[pbase + 3 * pt].x; x[10] = Gv.xbd[pbase + 3 * pt + 1].x; x[11] = Gv.xbd[pbase + 3 * pt + 2].x;
-        fc_on = (Gv.fconst_on != nullptr) && Gv.fconst_on[fid];
-        fc_val = fc_on ? Gv.fconst_val[fid] : 0.0;
+    double2 ob = make_double2(0.0, 0.0);
+    bool fc_on = false;
+    double fc_val = 0.0;
+    x[9] = x[10] = x[11] = 0.0;
+    if (have) {  // the frozen point block + pixel: registers for the life of the solve
+      const int32_t pbase = 9 * Gv.ncams;
+      const int32_t fid = B.fids[P.fac_off + rank];
+      const int32_t pt = __ldg(&Gv.pt[fid]);
+      ob = __ldg(&Gv.obs[fid]);
+      x[9] = Gv.xbd[pbase + 3 * pt].x; x[10] = Gv.xbd[pbase + 3 * pt + 1].x; x[11] = Gv.xbd[pbase + 3 * pt + 2].x;
+      if (Gv.fconst_on != nullptr && Gv.fconst_on[fid]) {
+        fc_on = true;
+        fc_val = Gv.fconst_val[fid];
       }
-    };
-
-    if (along) {
-      double v2[2] = {0.0, 0.0};
-      for (int k = rank; k < nf; k += size) {
-        double2 ob;
-        bool fc_on;
-        double fc_val;
-        stage(k, ob, fc_on, fc_val);
-        double fv = BaOps::project(x, ob, m);
-        if (want_g) {
+    }
+    int flip = 0;
+#ifdef RDIS_CAM_PROFILE
+    long long wp[4] = {0, 0, 0, 0}, wl = clock64();
+    int wn = 0;
+#define WKPROF(i) do { const long long t_ = clock64(); wp[i] += t_ - wl; wl = t_; } while (0)
+#else
+#define WKPROF(i) do { } while (0)
+#endif
+    while (true) {
+      named_bar_sync(1, nthreads);  // the request is published
+      WKPROF(0);  // waiting for the request
+      const int kind = sh.rq.kind;
+      if (kind == REQ_DONE) break;
+#ifdef RDIS_CAM_PROFILE
+      ++wn;
+#endif
+      BaOps::Fwd m;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) x[j] = sh.rq.x[j];
+      m.a0 = sh.rq.a0; m.a1 = sh.rq.a1; m.a2 = sh.rq.a2; m.theta = sh.rq.theta; m.s = sh.rq.s; m.c = sh.rq.c;
+      const uint32_t bar = smem_addr_u32(&sh.mbar[flip]);
+      if (kind == REQ_VALUE || kind == REQ_VALUE_SLOPE) {
+        double v0s = 0.0, v1s = 0.0;
+        if (have) {
+          double fv = BaOps::project(x, ob, m);
+          if (kind == REQ_VALUE_SLOPE) {
+            double gq[12];
+            BaOps::partials(x, m, gq);
+            double sl = 0.0;
+#pragma unroll
+            for (int s = 0; s < 9; ++s) sl += gq[s] * sh.rq.xi[s];
+            v1s = sl;
+          }
+          if (fc_on) fv = fc_val;  // Factor::eval of an assigned-constant factor, src/Factor.cpp:110-119
+          v0s = fv;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          v0s += __shfl_xor_sync(0xffffffffu, v0s, o);
+          v1s += __shfl_xor_sync(0xffffffffu, v1s, o);
+        }
+        WKPROF(1);  // evaluation + butterfly
+        if (lane < C) {
+          const uint32_t dst = (C > 1) ? map_to_cta(smem_addr_u32(&sh.red[flip][grow][0]), (uint32_t)lane) : smem_addr_u32(&sh.red[flip][grow][0]);
+          const uint32_t rbar = (C > 1) ? map_to_cta(bar, (uint32_t)lane) : bar;
+          st_async_v2(dst, v0s, v1s, rbar);
+        }
+        WKPROF(2);  // send
+      } else {
+        double acc[kCamRedWidth];
+#pragma unroll
+        for (int i = 0; i < kCamRedWidth; ++i) acc[i] = 0.0;
+        if (have) {
+          double fv = BaOps::project(x, ob, m);
           double gq[12];
           BaOps::partials(x, m, gq);
-          double sl = 0.0;
 #pragma unroll
-          for (int s = 0; s < 9; ++s) sl += gq[s] * sh.xi[s];
-          v2[1] += sl;
+          for (int s = 0; s < 9; ++s) acc[1 + s] = gq[s];
+          if (fc_on) fv = fc_val;
+          acc[0] = fv;
         }
-        if (fc_on) fv = fc_val;
-        v2[0] += fv;
-      }
-#ifdef RDIS_CAM_PROFILE
-      if (threadIdx.x == 0 && v2[0] != -1.0) { const long long t_ = clock64(); profx[want_g ? 2 : 1] += t_ - tlast; tlast = t_; if (want_g) ++nslope; }
-#endif
-      cluster_reduce_to_thread0<2>(sh, flip, phase, v2, C, cta CAMPROF_PASS);
-    } else {
-      double acc[kCamRedWidth];
 #pragma unroll
-      for (int i = 0; i < kCamRedWidth; ++i) acc[i] = 0.0;
-      for (int k = rank; k < nf; k += size) {
-        double2 ob;
-        bool fc_on;
-        double fc_val;
-        stage(k, ob, fc_on, fc_val);
-        double fv = BaOps::project(x, ob, m);
-        double gq[12];
-        BaOps::partials(x, m, gq);
+        for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int s = 0; s < 9; ++s) acc[1 + s] += gq[s];
-        if (fc_on) fv = fc_val;
-        acc[0] += fv;
+          for (int i = 0; i < kCamRedWidth; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        }
+        if (lane < C) {
+          const uint32_t dst = (C > 1) ? map_to_cta(smem_addr_u32(&sh.red[flip][grow][0]), (uint32_t)lane) : smem_addr_u32(&sh.red[flip][grow][0]);
+          const uint32_t rbar = (C > 1) ? map_to_cta(bar, (uint32_t)lane) : bar;
+#pragma unroll
+          for (int i = 0; i < kCamRedWidth; i += 2) st_async_v2(dst + 8u * i, acc[i], acc[i + 1], rbar);
+        }
       }
-      cluster_reduce_to_thread0<kCamRedWidth>(sh, flip, phase, acc, C, cta CAMPROF_PASS);
+      flip ^= 1;
     }
-
-    // ---- the scalar step (thread 0 of every CTA, identical inputs in every CTA of the cluster) ----
-    CAMPROF(5);  // fold of the cluster's partials
-    if (threadIdx.x == 0) {
-      CgdMachine mc = sh.m;  // registers for the duration of the step only (one burst of loads instead of dependent ones)
-      // Variable::assign of this evaluation's point (src/Variable.cpp:66-88): a move below 1e-12 notifies nobody
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        if (!c_assigned || !(fabs(x[j] - sh.last[j]) < 1e-12)) c_dirty = true;
-        sh.last[j] = x[j];
+#ifdef RDIS_CAM_PROFILE
+    if (threadIdx.x == 0 && cta == 0 && (blockIdx.x / C) < 4)
+      printf("camprof worker prob %d evals %d | wait-for-request %lld eval+butterfly %lld send %lld\n", pidx, wn, wp[0] / (wn ? wn : 1), wp[1] / (wn ? wn : 1), wp[2] / (wn ? wn : 1));
+#endif
+  } else {
+    // ------------------------------------------------------------------ the scalar warp
+    // lane j < 9 owns variable j of the camera (p, xi, g, h, the start value, the last assigned value, the domain: one
+    // register each); lane 0 also owns the state machine and the value cache.  Scalars travel by shuffles.
+    const unsigned kFull = 0xffffffffu;
+    const int rows = C * W;
+    const bool vl = (lane < 9);
+    CgdMachine mc;
+    double pj = 0.0, xij = 0.0, gj = 0.0, hj = 0.0, xsj = 0.0, lastj = 0.0;
+    double2 domj = make_double2(0.0, 0.0);
+    if (vl) {
+      pj = xsj = (B.x0 != nullptr) ? B.x0[P.var_off + lane] : Gv.xbd[v0 + lane].x;
+      domj = __ldg(&Gv.dom[v0 + lane]);
+    }
+    double f_init = 0.0, c_sum = 0.0, f_at_p = 0.0;
+    bool c_dirty = true, c_assigned = false;
+    auto cache_eval = [&](double fresh) {  // Factor::eval over the list, src/Factor.cpp:110-119
+      if (c_dirty) {
+        c_sum = fresh;
+        c_dirty = false;
       }
-      c_assigned = true;
-      CAMPROF(6);  // machine copy-in + Variable::assign bookkeeping
-      auto cache_eval = [&](double fresh) {  // Factor::eval over the list, src/Factor.cpp:110-119
-        if (c_dirty) {
-          c_sum = fresh;
-          c_dirty = false;
+      return c_sum;
+    };
+    mc.start(maxiters, ftol, /*faithful=*/true);
+    int flip = 0;
+    uint32_t phase = 0;
+#ifdef RDIS_CAM_PROFILE
+    long long prof[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+    const long long tstart = tlast;
+    int nev = 0;
+#define SCPROF(i) do { const long long t_ = clock64(); prof[i] += t_ - tlast; tlast = t_; } while (0)
+#else
+#define SCPROF(i) do { } while (0)
+#endif
+    // Publishes the machine's request — the clamped point (lane-parallel), its rotation (lane 0), the direction — does
+    // Variable::assign's bookkeeping, releases the workers.  Returns the request kind (uniform).
+    auto publish = [&]() -> int {
+      const int kind = __shfl_sync(kFull, mc.req, 0);
+      const double alpha = __shfl_sync(kFull, mc.alpha, 0);
+      if (lane == 0) sh.rq.kind = kind;
+      if (kind != REQ_DONE) {
+        const bool along = (kind == REQ_VALUE) || (kind == REQ_VALUE_SLOPE);
+        double xj = 0.0;
+        bool chg = false;
+        if (vl) {
+          xj = clamp_to_domain(along ? (pj + alpha * xij) : pj, domj);
+          chg = !c_assigned || !(fabs(xj - lastj) < 1e-12);  // Variable::assign, src/Variable.cpp:66-88
+          lastj = xj;
+          sh.rq.x[lane] = xj;
+          sh.rq.xi[lane] = xij;
         }
-        return c_sum;
-      };
+        if (__any_sync(kFull, chg)) c_dirty = true;
+        c_assigned = true;
+        const double r0 = __shfl_sync(kFull, xj, 0), r1 = __shfl_sync(kFull, xj, 1), r2 = __shfl_sync(kFull, xj, 2);
+        if (lane == 0) {
+          BaOps::Fwd m;
+          BaOps::rotation(r0, r1, r2, m);
+          sh.rq.a0 = m.a0; sh.rq.a1 = m.a1; sh.rq.a2 = m.a2; sh.rq.theta = m.theta; sh.rq.s = m.s; sh.rq.c = m.c;
+        }
+      }
+      __syncwarp();
+      named_bar_arrive(1, nthreads);
+      return kind;
+    };
+    int kind = publish();
+    SCPROF(0);
+    while (kind != REQ_DONE) {
+#ifdef RDIS_CAM_PROFILE
+      ++nev;
+#endif
+      const bool along = (kind == REQ_VALUE) || (kind == REQ_VALUE_SLOPE);
+      const int N = along ? 2 : kCamRedWidth;
+      if (lane == 0) mbar_arrive_expect_tx(&sh.mbar[flip], (uint32_t)(rows * N * 8));
+      mbar_wait_cluster(&sh.mbar[flip], (phase >> flip) & 1u);
+      SCPROF(1);  // workers' evaluation + flight
+      phase ^= (1u << flip);
+      // Fold of the cluster's warp partials in an order that is a function of the row index (= observation index / 32)
+      // only: rows are dealt to lane groups by index modulo a constant, each group adds its rows in ascending order, the
+      // groups are combined by a fixed tree.  Rows past C*W do not exist (they would hold exact zeros).
+      double t0 = 0.0, t1 = 0.0, tot = 0.0;  // f, slope (line evaluations); column sums in lanes 0..9 (gradient evaluations)
       if (along) {
-        mc.on_eval(cache_eval(sh.tot[0]), (kind == REQ_VALUE_SLOPE) ? sh.tot[1] : 0.0);
-        if (mc.req == REQ_MOVE) {  // minimize_nrc.h:508-511
-          const double step = mc.alpha;
-          for (int j = 0; j < 9; ++j) {
-            const double d = sh.xi[j] * step;
-            sh.xi[j] = d;
-            sh.p[j] += d;
-          }
-          mc.on_moved();
+        const int col = lane & 1, grp = lane >> 1;  // 16 groups x 2 columns
+        double sacc = 0.0;
+        for (int r = grp; r < rows; r += 16) sacc += sh.red[flip][r][col];
+#pragma unroll
+        for (int o = 2; o < 32; o <<= 1) sacc += __shfl_xor_sync(kFull, sacc, o);
+        t0 = __shfl_sync(kFull, sacc, 0);
+        t1 = __shfl_sync(kFull, sacc, 1);
+      } else {
+        const int col = lane % kCamRedWidth, grp = lane / kCamRedWidth;  // 3 groups x 10 columns (lanes 30, 31 idle)
+        double sacc = 0.0;
+        if (grp < 3)
+          for (int r = grp; r < rows; r += 3) sacc += sh.red[flip][r][col];
+        const double s1 = __shfl_sync(kFull, sacc, (lane + 10) & 31), s2 = __shfl_sync(kFull, sacc, (lane + 20) & 31);
+        tot = (sacc + s1) + s2;  // meaningful in lanes 0..9
+        t0 = __shfl_sync(kFull, tot, 0);
+      }
+      const double gr_own = __shfl_sync(kFull, tot, (lane + 1) & 31);  // lane j < 9: d f / d x_j
+      flip ^= 1;
+      SCPROF(2);  // fold
+      // ---- the step: lane 0 advances the machine; the 9-element vector updates it asks for run lane-parallel ----
+      if (along) {
+        if (lane == 0) mc.on_eval(cache_eval(t0), (kind == REQ_VALUE_SLOPE) ? t1 : 0.0);
+        if (__shfl_sync(kFull, mc.req, 0) == REQ_MOVE) {  // minimize_nrc.h:508-511
+          const double step = __shfl_sync(kFull, mc.alpha, 0);
+          xij *= step;
+          pj += xij;
+          if (lane == 0) mc.on_moved();
         }
       } else if (kind == REQ_INIT_GRAD) {
-        for (int j = 0; j < 9; ++j) {
-          const double gneg = -sh.tot[1 + j];
-          sh.g[j] = gneg; sh.h[j] = gneg; sh.xi[j] = gneg;
+        if (vl) {
+          const double gneg = -gr_own;
+          gj = gneg; hj = gneg; xij = gneg;
         }
-        f_at_p = sh.tot[0];
-        f_init = cache_eval(f_at_p);
-        mc.on_init(f_init);
-      } else {  // REQ_GRADIENT: func.df(p, xi), then :656-685
-        f_at_p = sh.tot[0];
+        if (lane == 0) {
+          f_at_p = t0;
+          f_init = cache_eval(f_at_p);
+          mc.on_init(f_init);
+        }
+      } else {  // REQ_GRADIENT: func.df(p, xi), then :656-685 (left-to-right sums over the variables, by lane 0)
+        if (vl) xij = gr_own;
         double gg = 0.0, dgg = 0.0, tnum = 0.0;
+#pragma unroll
         for (int j = 0; j < 9; ++j) {
-          const double gr = sh.tot[1 + j];
-          const double pj = fabs(sh.p[j]);
-          const double t = fabs(gr) * ((pj < 1.0) ? 1.0 : pj);
-          tnum = (t > tnum) ? t : tnum;
-          const double gj = sh.g[j];
-          gg += gj * gj;
-          dgg += (gr + gj) * gr;
+          const double pv = __shfl_sync(kFull, pj, j), gv = __shfl_sync(kFull, gj, j), grv = __shfl_sync(kFull, tot, 1 + j);
+          const double pa = fabs(pv);
+          const double tt = fabs(grv) * ((pa < 1.0) ? 1.0 : pa);
+          tnum = (tt > tnum) ? tt : tnum;
+          gg += gv * gv;
+          dgg += (grv + gv) * grv;
         }
-        mc.on_gradient(tnum, gg, dgg);
-        if (mc.req == REQ_DIRECTION) {
-          const double gam = mc.gam;
-          for (int j = 0; j < 9; ++j) {
-            const double gj = -sh.tot[1 + j];
-            const double hj = gj + gam * sh.h[j];
-            sh.g[j] = gj; sh.h[j] = hj; sh.xi[j] = hj;
+        if (lane == 0) {
+          f_at_p = t0;
+          mc.on_gradient(tnum, gg, dgg);
+        }
+        if (__shfl_sync(kFull, mc.req, 0) == REQ_DIRECTION) {
+          const double gam = __shfl_sync(kFull, mc.gam, 0);
+          if (vl) {
+            const double gn = -xij;
+            const double hn = gn + gam * hj;
+            gj = gn; hj = hn; xij = hn;
           }
-          mc.on_directed();
-        } else {
-          for (int j = 0; j < 9; ++j) sh.xi[j] = sh.tot[1 + j];
+          if (lane == 0) mc.on_directed();
         }
       }
       // fa = func(ax = 0) at the top of a line search (minimize_nrc.h:88): clamp(p) is the point the gradient pass
       // assigned and f_at_p its objective — answered from the cache rules without another pass
-      if (mc.req == REQ_VALUE && mc.phase == CgdMachine::PH_BR_FA) mc.on_eval(cache_eval(f_at_p), 0.0);
-      CAMPROF(7);  // machine step + vector updates
-      sh.m = mc;
-      CAMPROF(8);  // machine copy-out
+      if (lane == 0 && mc.req == REQ_VALUE && mc.phase == CgdMachine::PH_BR_FA) mc.on_eval(cache_eval(f_at_p), 0.0);
+      SCPROF(3);  // machine step
+      kind = publish();
+      SCPROF(0);  // point + rotation + publish
     }
-    __syncthreads();
-    CAMPROF(9);  // closing barrier
-  }
 #ifdef RDIS_CAM_PROFILE
-  if (threadIdx.x == 0 && cta == 0 && (blockIdx.x / C) < 4)
-    printf("camprof prob %d: x+rotation %lld per eval; value-only obs pass %lld per value eval (%d); value+slope obs pass %lld per slope eval (%d); eval includes butterfly\n",
-           pidx, profx[0] / nev, profx[1] / (nev - nslope > 0 ? nev - nslope : 1), nev - nslope, profx[2] / (nslope > 0 ? nslope : 1), nslope);
-  if (threadIdx.x == 0 && cta == 0 && (blockIdx.x / C) < 4)
-    printf("camprof prob %d nf %d evals %d cycles/eval %lld | req %lld eval %lld bar1 %lld wfold+send %lld peerwait %lld cfold %lld copyin+assign %lld machine %lld copyout %lld bar2 %lld\n",
-           pidx, nf, nev, (clock64() - tstart) / (nev > 0 ? nev : 1), prof[0] / nev, prof[1] / nev, prof[2] / nev, prof[3] / nev, prof[4] / nev,
-           prof[5] / nev, prof[6] / nev, prof[7] / nev, prof[8] / nev, prof[9] / nev);
+    if (lane == 0 && cta == 0 && (blockIdx.x / C) < 4)
+      printf("camprof prob %d nf %d evals %d cycles/eval %lld | publish %lld workers+flight %lld fold %lld machine %lld\n", pidx, nf, nev,
+             (clock64() - tstart) / (nev > 0 ? nev : 1), prof[0] / nev, prof[1] / nev, prof[2] / nev, prof[3] / nev);
 #endif
-
-  // ---- commit (CGD.cpp:61-89): quickAssignVals(gdmin.p); if worse than the start the start point is re-assigned and
-  //      re-evaluated through the cache.  CTA 0 of the cluster writes. ----
-  if (cta == 0 && threadIdx.x == 0) {
-    const CgdMachine& mc = sh.m;
-    double fret = mc.fret;
-    const bool restore = (fret > f_init);
-    if (restore) {
-      bool chg = c_dirty;
-      for (int j = 0; j < 9; ++j) {  // the two assigns: gdmin.p, then the start point
-        const double pf = clamp_to_domain(sh.p[j], sh.dom[j]), ps = clamp_to_domain(sh.xs[j], sh.dom[j]);
-        if (!(fabs(pf - sh.last[j]) < 1e-12) || !(fabs(ps - pf) < 1e-12)) chg = true;
+    // ---- commit (CGD.cpp:61-89): quickAssignVals(gdmin.p); if worse than the start the start point is re-assigned and
+    //      re-evaluated through the cache.  The scalar warp of CTA 0 writes. ----
+    {
+      const double fret0 = __shfl_sync(kFull, mc.fret, 0);
+      const double finit0 = __shfl_sync(kFull, f_init, 0);
+      const bool restore = (fret0 > finit0);
+      const double pf = clamp_to_domain(pj, domj), ps = clamp_to_domain(xsj, domj);
+      const bool chgj = vl && (!(fabs(pf - lastj) < 1e-12) || !(fabs(ps - pf) < 1e-12));  // the two assigns: gdmin.p, then the start
+      const bool chg = __any_sync(kFull, chgj);
+      if (cta == 0) {
+        if (vl) {
+          const double val = restore ? ps : pf;
+          Gv.xbd[v0 + lane] = make_double2(val, qnan_f64());
+          Gv.xval[v0 + lane] = val;
+          B.xout[P.var_off + lane] = val;
+        }
+        if (lane == 0) {
+          double fret = mc.fret;
+          if (restore) fret = (chg || c_dirty) ? f_init : c_sum;  // a recomputation at the start point reproduces f_init's bits
+          ResultRec res;
+          res.f_init = f_init;
+          res.f_end = fret;
+          res.iters = mc.iter;
+          res.status = mc.status;
+          res.n_value = mc.n_value;
+          res.n_slope = mc.n_slope;
+          B.res[pidx] = res;
+        }
       }
-      fret = chg ? f_init : c_sum;  // a recomputation at the start point reproduces f_init's bits
     }
-    for (int j = 0; j < 9; ++j) {
-      const double val = clamp_to_domain(restore ? sh.xs[j] : sh.p[j], sh.dom[j]);
-      Gv.xbd[v0 + j] = make_double2(val, qnan_f64());
-      Gv.xval[v0 + j] = val;
-      B.xout[P.var_off + j] = val;
-    }
-    ResultRec res;
-    res.f_init = f_init;
-    res.f_end = fret;
-    res.iters = mc.iter;
-    res.status = mc.status;
-    res.n_value = mc.n_value;
-    res.n_slope = mc.n_slope;
-    B.res[pidx] = res;
   }
   if (C > 1) cluster.sync();  // no CTA leaves while a peer could still address its shared memory
 }

@@ -112,6 +112,7 @@ struct rdisgpu_ctx {
   int32_t mark_epoch = 0;
   rdisgpu_batch* scratch_batch = nullptr;  // reused by the one-shot solve entry points
   bool generic_only = false;  // rdisgpu_set_option("generic_only"): bypass the BA block kernels (tests)
+  int cam_cluster_opt = 0;    // rdisgpu_set_option("camera_cluster"): pin the cluster width of the camera-block kernel (0 = choose)
   bool strict = false;        // rdisgpu_set_option("strict"): every solve through strict_kernels.cuh (bit-exact parity instrument)
   DevBuf<double> fcache;      // strict mode: the reference's per-factor value cache ...
   DevBuf<uint8_t> fdirty, vchg;  // ... its dirty flags, and Variable::assign's change flags
@@ -322,6 +323,11 @@ int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return RDISGPU_ERR_ARG;
   if (std::strcmp(name, "generic_only") == 0) {
     ctx->generic_only = (value != 0);
+    return RDISGPU_OK;
+  }
+  if (std::strcmp(name, "camera_cluster") == 0) {
+    if (value < 0 || value > kCamMaxCluster) return ctx->fail(RDISGPU_ERR_ARG, "set_option: camera_cluster must be 0..8");
+    ctx->cam_cluster_opt = (int)value;
     return RDISGPU_OK;
   }
   if (std::strcmp(name, "strict") == 0) {
@@ -1036,7 +1042,7 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
         while ((1 << lg) < D.nf) ++lg;
         pt_lists[lg].push_back((int32_t)p);
         fast[p] = 1;
-      } else if (D.nv == 9 && pvv[0] < pbase && pvv[0] % 9 == 0) {
+      } else if (D.nv == 9 && D.nf <= kCamMaxCluster * kCamMaxThreads && pvv[0] < pbase && pvv[0] % 9 == 0) {
         bool ok = true;
         for (int j = 1; j < 9 && ok; ++j) ok = (pvv[j] == pvv[0] + j);
         const int32_t cam = pvv[0] / 9;
@@ -1271,18 +1277,21 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
   }
   if (b->n_cam > 0) {
     if (b->cam_C == 0) {
-      // widest cluster such that every camera block of the batch is resident at once
-      for (int C = kCamMaxCluster; C >= 1 && b->cam_C == 0; --C) {
+      // one observation per worker thread (C*T >= the longest factor list): the widest cluster — fewest observations per
+      // SM, shortest evaluation — such that every camera block of the batch is resident at once; rdisgpu_set_option
+      // "camera_cluster" pins C (experiments)
+      for (int C = (ctx->cam_cluster_opt > 0 ? ctx->cam_cluster_opt : kCamMaxCluster); C >= 1 && b->cam_C == 0; --C) {
         int T = ((b->cam_nf_max + C - 1) / C + 31) / 32 * 32;
-        T = std::min(std::max(T, 64), kCamMaxThreads);
-        if (C == 1) {
-          b->cam_C = 1;
+        T = std::max(T, 32);
+        if (T > kCamMaxThreads) continue;  // cannot cover the list with this few CTAs (classification guarantees C = 8 can)
+        if (C == 1 || ctx->cam_cluster_opt > 0) {
+          b->cam_C = C;
           b->cam_T = T;
           break;
         }
         cudaLaunchConfig_t qc = {};
         qc.gridDim = dim3((unsigned)(b->n_cam * C));
-        qc.blockDim = dim3((unsigned)T);
+        qc.blockDim = dim3((unsigned)(T + 32));
         qc.stream = s;
         cudaLaunchAttribute qa[1];
         qa[0].id = cudaLaunchAttributeClusterDimension;
@@ -1297,15 +1306,23 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
           cudaGetLastError();
           continue;
         }
-        if (nclusters >= b->n_cam) {
+        // all clusters resident at once, give or take 3 % of them: GPC granularity leaves 48 slots for ladybug's 49
+        // clusters of 8, and the straggler costs less than a narrower cluster for everybody (measured)
+        if ((int64_t)nclusters * 32 >= (int64_t)b->n_cam * 31) {
           b->cam_C = C;
           b->cam_T = T;
         }
       }
+      if (b->cam_C == 0) {  // more camera blocks than the chip holds clusters of any covering shape: the narrowest covering one, in waves
+        int C = 1;
+        while ((b->cam_nf_max + C - 1) / C > kCamMaxThreads) ++C;
+        b->cam_C = C;
+        b->cam_T = std::max(32, ((b->cam_nf_max + C - 1) / C + 31) / 32 * 32);
+      }
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(b->n_cam * b->cam_C));
-    cfg.blockDim = dim3((unsigned)b->cam_T);
+    cfg.blockDim = dim3((unsigned)(b->cam_T + 32));  // + the scalar warp
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
