@@ -530,6 +530,17 @@ def test_solve_lm_blocks(gpu, oracle_mod):
 
 
 @pytest.mark.gpu
+def test_corrected_quotients_are_exact(built_lib):
+    """QuotBy<kCorrected> (one reciprocal + a correction step per quotient: what the production BA gradient uses for the
+    reference's 24 divisions per observation) returns the division's own bits on 2^28 operand pairs."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "rdis_b200", "host"), "all"], stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(root, "tests", "native", "quot_check")], capture_output=True, text=True)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_inline_trig_is_bit_identical(built_lib):
     """rdis_sin / rdis_cos / rdis_sincos (the inline kernels the NLPF terms use) == the CUDA library's
     sin / cos to the bit on 8 M values incl. the slow-path threshold and the special values."""
