@@ -216,6 +216,13 @@ RDISGPU_API int rdisgpu_components(rdisgpu_ctx* ctx, const uint8_t* assigned, in
 RDISGPU_API int rdisgpu_bounds(rdisgpu_ctx* ctx, const uint8_t* assigned, int64_t nf, const int64_t* fid, double* lower,
                                double* upper, double sum[2]);
 
+/* The residual + Jacobian-rows sweep over ALL factors of a bundle-adjustment graph, device pointers, asynchronous on the
+ * context's stream: per_factor_dev[F] (nullable) the factor values, rows_dev[12 F] the 12 partial derivatives of every
+ * factor in slot order (rot xyz, trans xyz, focal, k1, k2, point xyz), *sum_dev (nullable) the total.  This is what
+ * LMSSOpt::evalFunc / evalJacf produce one factor at a time (src/optimizers/LMSubspaceOptimizer.cpp:176-278, through
+ * BundleAdjustmentFactor::computeGradient, src/bundleadjust/BundleAdjustmentFactor.cpp:351-554); 128 B/factor + 8 B/variable. */
+RDISGPU_API int rdisgpu_factor_rows_device(rdisgpu_ctx* ctx, double* sum_dev, double* per_factor_dev, double* rows_dev);
+
 /* ---- introspection (tests / bench) ------------------------------------------------------ */
 RDISGPU_API int64_t rdisgpu_num_vars(const rdisgpu_ctx* ctx);
 RDISGPU_API int64_t rdisgpu_num_factors(const rdisgpu_ctx* ctx);

@@ -21,7 +21,7 @@ EXPORTS = (
     "rdisgpu_create", "rdisgpu_destroy", "rdisgpu_last_error", "rdisgpu_set_stream", "rdisgpu_synchronize", "rdisgpu_set_option",
     "rdisgpu_set_vars", "rdisgpu_add_nlpf", "rdisgpu_add_ba", "rdisgpu_finalize",
     "rdisgpu_set_x", "rdisgpu_get_x", "rdisgpu_set_factor_const",
-    "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_eval_device", "rdisgpu_grad_device", "rdisgpu_factor_grad",
+    "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_eval_device", "rdisgpu_grad_device", "rdisgpu_factor_grad", "rdisgpu_factor_rows_device",
     "rdisgpu_solve_cgd", "rdisgpu_solve_cgd_csr", "rdisgpu_solve_lm_csr", "rdisgpu_batch_create", "rdisgpu_batch_create_csr", "rdisgpu_batch_info", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
     "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches", "rdisgpu_batch_resident_info", "rdisgpu_components", "rdisgpu_bounds",
     "rdisgpu_num_vars", "rdisgpu_num_factors", "rdisgpu_device_state", "rdisgpu_launch_count", "rdisgpu_version",
@@ -67,6 +67,7 @@ def load_library(path=LIB_PATH):
         "rdisgpu_eval_device": (C.c_int, [vp, i64, vp, vp, vp]),
         "rdisgpu_grad_device": (C.c_int, [vp, i64, vp, i64, vp, vp]),
         "rdisgpu_factor_grad": (C.c_int, [vp, i64, vp, i32, vp]),
+        "rdisgpu_factor_rows_device": (C.c_int, [vp, vp, vp, vp]),
         "rdisgpu_solve_cgd": (C.c_int, [vp, C.POINTER(Problem), i64, C.c_int, dbl, C.POINTER(Result)]),
         "rdisgpu_batch_create": (C.c_int, [vp, C.POINTER(Problem), i64, C.POINTER(vp)]),
         "rdisgpu_batch_create_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, C.POINTER(vp)]),
@@ -243,6 +244,12 @@ class Context:
         self._ck(self._lib.rdisgpu_eval_device(self._h, nf, C.c_void_p(fid_dev_ptr) if fid_dev_ptr else None,
                                                C.c_void_p(sum_dev_ptr) if sum_dev_ptr else None,
                                                C.c_void_p(per_factor_dev_ptr) if per_factor_dev_ptr else None))
+
+    def factor_rows_device(self, per_factor_dev_ptr, rows_dev_ptr, sum_dev_ptr=None):
+        """Asynchronous residual + Jacobian-rows sweep over all factors of a BA graph (raw device pointers)."""
+        self._ck(self._lib.rdisgpu_factor_rows_device(self._h, C.c_void_p(sum_dev_ptr) if sum_dev_ptr else None,
+                                                      C.c_void_p(per_factor_dev_ptr) if per_factor_dev_ptr else None,
+                                                      C.c_void_p(rows_dev_ptr)))
 
     def grad_device(self, g_dev_ptr, vid_dev_ptr=None, nv=0, fid_dev_ptr=None, nf=0):
         """Asynchronous gradient sweep, raw device pointers (None = all variables / all factors)."""

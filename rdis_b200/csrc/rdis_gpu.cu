@@ -697,6 +697,33 @@ static int upload_fids(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, DevBuf<
   return RDISGPU_OK;
 }
 
+// The all-factor bundle-adjustment sweep (ba_sweep.cuh): values, optionally the 12 partials of every observation.
+static int launch_ba_sweep(rdisgpu_ctx* ctx, int blocks, double* per_factor_dev, double* rows_dev, double* dsum) {
+  cudaStream_t s = ctx->stream;
+  const int threads = 256;
+  if (ctx->ncams <= kBaSmemCams) {
+    const size_t smem = (size_t)ctx->ncams * kBaSmemRow * sizeof(double);
+    if (smem > 48 * 1024 && !ctx->ba_smem_optin) {
+      CK(cudaFuncSetAttribute(ba_sweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBaSmemCams * kBaSmemRow * sizeof(double))));
+      CK(cudaFuncSetAttribute(ba_sweep_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBaSmemCams * kBaSmemRow * sizeof(double))));
+      ctx->ba_smem_optin = true;
+    }
+    if (rows_dev)
+      ba_sweep_kernel<true, true><<<blocks, threads, smem, s>>>(ctx->gv, nullptr, per_factor_dev, rows_dev, ctx->s_partials.p, ctx->s_counter.p, dsum);
+    else
+      ba_sweep_kernel<true, false><<<blocks, threads, smem, s>>>(ctx->gv, nullptr, per_factor_dev, nullptr, ctx->s_partials.p, ctx->s_counter.p, dsum);
+  } else {
+    CK(ctx->cam_table.ensure((size_t)ctx->ncams));
+    ba_camera_table_kernel<<<(ctx->ncams + 127) / 128, 128, 0, s>>>(ctx->gv, ctx->cam_table.p);
+    ++ctx->launches;
+    if (rows_dev)
+      ba_sweep_kernel<false, true><<<blocks, threads, 0, s>>>(ctx->gv, ctx->cam_table.p, per_factor_dev, rows_dev, ctx->s_partials.p, ctx->s_counter.p, dsum);
+    else
+      ba_sweep_kernel<false, false><<<blocks, threads, 0, s>>>(ctx->gv, ctx->cam_table.p, per_factor_dev, nullptr, ctx->s_partials.p, ctx->s_counter.p, dsum);
+  }
+  return RDISGPU_OK;
+}
+
 // Enqueues one residual sweep: fid_dev (device, nullable = all factors), per_factor_dev (device, nullable);
 // the total lands in *dsum_out (device scratch of the context).  No copies, no waiting.
 static int enqueue_eval(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, double* per_factor_dev, double** dsum_out,
@@ -714,19 +741,8 @@ static int enqueue_eval(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, do
     nlpf_tile_sweep_kernel<false><<<blocks, kTileThreads + 32, sizeof(TileSmem), s>>>(
         ctx->gv, ctx->tiles.p, ctx->ntiles, per_factor_dev, ctx->s_partials.p, ctx->s_counter.p, dsum);
   else if (ba_all) {
-    CK(ctx->cam_table.ensure((size_t)ctx->ncams));
-    ba_camera_table_kernel<<<(ctx->ncams + 127) / 128, 128, 0, s>>>(ctx->gv, ctx->cam_table.p);
-    ++ctx->launches;
-    if (ctx->ncams <= kBaSmemCams) {
-      const size_t smem = (size_t)ctx->ncams * sizeof(CameraRow);
-      if (smem > 48 * 1024 && !ctx->ba_smem_optin) {
-        CK(cudaFuncSetAttribute(ba_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBaSmemCams * sizeof(CameraRow))));
-        ctx->ba_smem_optin = true;
-      }
-      ba_sweep_kernel<true><<<blocks, threads, smem, s>>>(ctx->gv, ctx->cam_table.p, per_factor_dev, ctx->s_partials.p, ctx->s_counter.p, dsum);
-    } else {
-      ba_sweep_kernel<false><<<blocks, threads, 0, s>>>(ctx->gv, ctx->cam_table.p, per_factor_dev, ctx->s_partials.p, ctx->s_counter.p, dsum);
-    }
+    int rc = launch_ba_sweep(ctx, blocks, per_factor_dev, nullptr, dsum);
+    if (rc) return rc;
   } else if (ctx->kind == KIND_NLPF)
     eval_sweep_kernel<NlpfOps><<<blocks, threads, 0, s>>>(ctx->gv, fid_dev, nf, per_factor_dev, ctx->s_partials.p,
                                                           ctx->s_counter.p, dsum);
@@ -886,6 +902,22 @@ int rdisgpu_factor_grad(rdisgpu_ctx* ctx, int64_t nf, const int64_t* fid, int32_
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(rows, ctx->s_f64b.p, (size_t)nf * arity_max * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return RDISGPU_OK;
+}
+
+int rdisgpu_factor_rows_device(rdisgpu_ctx* ctx, double* sum_dev, double* per_factor_dev, double* rows_dev) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "factor_rows_device before finalize");
+  if (ctx->kind != KIND_BA) return ctx->fail(RDISGPU_ERR_ARG, "factor_rows_device: bundle-adjustment graphs only (use rdisgpu_grad_device)");
+  if (!is_device_ptr(rows_dev) || (per_factor_dev && !is_device_ptr(per_factor_dev)) || (sum_dev && !is_device_ptr(sum_dev)))
+    return ctx->fail(RDISGPU_ERR_ARG, "factor_rows_device: device pointers required");
+  CK(cudaSetDevice(ctx->device));
+  const int blocks = (int)std::min<int64_t>(((ctx->F + kBaSweepUnroll - 1) / kBaSweepUnroll + 255) / 256, (int64_t)ctx->sm_count * 2);
+  CK(ctx->s_partials.ensure((size_t)blocks + 1));
+  int rc = launch_ba_sweep(ctx, blocks, per_factor_dev, rows_dev, sum_dev ? sum_dev : ctx->s_partials.p + blocks);
+  if (rc) return rc;
+  ++ctx->launches;
+  CK(cudaGetLastError());
   return RDISGPU_OK;
 }
 

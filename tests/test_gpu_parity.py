@@ -530,6 +530,35 @@ def test_solve_lm_blocks(gpu, oracle_mod):
 
 
 @pytest.mark.gpu
+def test_ba_rows_sweep_matches_list_path(gpu, oracle_mod):
+    """rdisgpu_factor_rows_device (the pipelined all-factor residual + Jacobian-rows sweep) against the per-factor list
+    path (rdisgpu_factor_grad / rdisgpu_eval, bit for bit: same expressions) and the oracle (1e-11), on a graph with
+    assigned-constant factors; the sweep's total against the sum of its values."""
+    import torch
+    from rdis_b200 import Context, problems as P
+    spec = P.ba_synthetic(ncams=11, npts=900, nobs=4001, seed=5)
+    ctx = Context.from_spec(spec)
+    ctx.set_x(spec["x0"])
+    fid = np.array([0, 17, 4000], np.int64)
+    ctx.set_factor_const(fid, np.array([1.5, -2.0, 0.25]), np.ones(3, np.uint8))
+    F = spec["F"]
+    pf = torch.zeros(F, dtype=torch.float64, device="cuda")
+    rows = torch.zeros(F * 12, dtype=torch.float64, device="cuda")
+    tot = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ctx.factor_rows_device(pf.data_ptr(), rows.data_ptr(), tot.data_ptr())
+    torch.cuda.synchronize()
+    _, want_pf = ctx.eval(per_factor=True)
+    want_rows = ctx.factor_grad(np.arange(F), 12)
+    assert np.array_equal(pf.cpu().numpy().view(np.uint64), want_pf.view(np.uint64))
+    assert np.array_equal(rows.cpu().numpy().reshape(F, 12).view(np.uint64), want_rows.view(np.uint64))
+    assert abs(float(tot.item()) - want_pf.sum()) <= 1e-12 * abs(want_pf.sum())
+    orc = oracle_mod.OracleFunction.from_spec(spec)
+    orc.set_x(spec["x0"])
+    ref = np.stack([orc.factor_grad(j, 12) for j in range(0, F, 7)])
+    got = rows.cpu().numpy().reshape(F, 12)[::7]
+    assert (np.abs(got - ref) <= 1e-11 * np.abs(ref).max(axis=1, keepdims=True) + 1e-300).all()
+
+
 def test_corrected_quotients_are_exact(built_lib):
     """QuotBy<kCorrected> (one reciprocal + a correction step per quotient: what the production BA gradient uses for the
     reference's 24 divisions per observation) returns the division's own bits on 2^28 operand pairs."""
