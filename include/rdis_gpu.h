@@ -223,6 +223,13 @@ RDISGPU_API int rdisgpu_bounds(rdisgpu_ctx* ctx, const uint8_t* assigned, int64_
  * BundleAdjustmentFactor::computeGradient, src/bundleadjust/BundleAdjustmentFactor.cpp:351-554); 128 B/factor + 8 B/variable. */
 RDISGPU_API int rdisgpu_factor_rows_device(rdisgpu_ctx* ctx, double* sum_dev, double* per_factor_dev, double* rows_dev);
 
+/* Interval bounds of MANY factor lists in one call: list l = fid[list_off[l] .. list_off[l+1]), sums[2l] / sums[2l+1] = lower /
+ * upper bound of the list's sum, folded on the device in list order.  This is Component::computeBounds for every child of a
+ * decomposition at once (src/Component.cpp:240-241,592-599 -> src/OptimizableFunction.cpp:181-216), what the branch & bound
+ * bookkeeping of the sibling loop reads (src/RDISOptimizer.cpp:291-314,894-934). */
+RDISGPU_API int rdisgpu_bounds_lists(rdisgpu_ctx* ctx, const uint8_t* assigned, int64_t nlists, const int64_t* list_off, const int64_t* fid,
+                                     double* sums);
+
 /* ---- introspection (tests / bench) ------------------------------------------------------ */
 RDISGPU_API int64_t rdisgpu_num_vars(const rdisgpu_ctx* ctx);
 RDISGPU_API int64_t rdisgpu_num_factors(const rdisgpu_ctx* ctx);

@@ -23,7 +23,7 @@ EXPORTS = (
     "rdisgpu_set_x", "rdisgpu_get_x", "rdisgpu_set_factor_const",
     "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_eval_device", "rdisgpu_grad_device", "rdisgpu_factor_grad", "rdisgpu_factor_rows_device",
     "rdisgpu_solve_cgd", "rdisgpu_solve_cgd_csr", "rdisgpu_solve_lm_csr", "rdisgpu_batch_create", "rdisgpu_batch_create_csr", "rdisgpu_batch_info", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
-    "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches", "rdisgpu_batch_resident_info", "rdisgpu_components", "rdisgpu_bounds",
+    "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches", "rdisgpu_batch_resident_info", "rdisgpu_components", "rdisgpu_bounds", "rdisgpu_bounds_lists",
     "rdisgpu_num_vars", "rdisgpu_num_factors", "rdisgpu_device_state", "rdisgpu_launch_count", "rdisgpu_version",
 )
 
@@ -75,6 +75,7 @@ def load_library(path=LIB_PATH):
         "rdisgpu_solve_lm_csr": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
         "rdisgpu_components": (C.c_int, [vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]),
         "rdisgpu_bounds": (C.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+        "rdisgpu_bounds_lists": (C.c_int, [vp, vp, i64, vp, vp, vp]),
         "rdisgpu_batch_info": (C.c_int, [vp, vp]),
         "rdisgpu_batch_resident_info": (C.c_int, [vp, vp]),
         "rdisgpu_batch_solve_cgd": (C.c_int, [vp, vp, C.c_int, dbl]),
@@ -272,6 +273,15 @@ class Context:
         lo = np.empty(n); hi = np.empty(n); tot = np.zeros(2)
         self._ck(self._lib.rdisgpu_bounds(self._h, _p(a), n, None if f is None else _p(f), _p(lo), _p(hi), _p(tot)))
         return lo, hi, (float(tot[0]), float(tot[1]))
+
+    def bounds_lists(self, assigned, list_off, fids):
+        """rdisgpu_bounds_lists: sums[nlists, 2] = (lower, upper) of every factor list, folded on the device in list order."""
+        a = _arr(assigned, np.uint8)
+        off = _arr(list_off, np.int64)
+        f = _arr(fids, np.int64)
+        out = np.zeros((len(off) - 1, 2))
+        self._ck(self._lib.rdisgpu_bounds_lists(self._h, _p(a), len(off) - 1, _p(off), _p(f), _p(out)))
+        return out
 
     # ---- component membership ----------------------------------------------------------
     def components(self, assigned):

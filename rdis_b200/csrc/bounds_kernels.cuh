@@ -98,4 +98,43 @@ __global__ void __launch_bounds__(128) factor_bounds_kernel(GraphView G, const u
   }
 }
 
+// Bounds of MANY factor lists in one launch (the unassigned bounds of every child of a decomposition,
+// Component::computeBounds, src/Component.cpp:592-599 -> OptimizableFunction::computeBounds, OptimizableFunction.cpp:181-216):
+// one warp per list, 32 factors at a time bounded lane-parallel, then folded by lane 0's replica IN LIST ORDER
+// (bounds = Product(bounds, fb) factor by factor, :194-211) — the sum the reference computes, not a tree.
+template <class Ops>
+__global__ void __launch_bounds__(128) list_bounds_kernel(GraphView G, const uint8_t* assigned, const int64_t* list_off, const int32_t* fids,
+                                                          int64_t nlists, double* sums) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t l = warp0; l < nlists; l += nwarps) {
+    const int64_t k0 = list_off[l], k1 = list_off[l + 1];
+    double lo = 0.0, hi = 0.0;  // semiring Product identity
+    for (int64_t kb = k0; kb < k1; kb += 32) {
+      const int64_t k = kb + lane;
+      Ival b = iv_point(0.0);
+      if (k < k1) {
+        const int64_t f = fids[k];
+        bool all_assigned = true;
+        b = (G.kind == KIND_NLPF) ? nlpf_factor_bounds(G, assigned, f, all_assigned) : ba_factor_bounds(G, assigned, f, all_assigned);
+        if (G.fconst_on != nullptr && G.fconst_on[f]) {
+          b = iv_point(G.fconst_val[f]);
+        } else if (all_assigned) {
+          double sl;
+          b = iv_point(Ops::template value<false>(G, f, 0.0, false, sl));
+        }
+      }
+      const int cnt = (int)((k1 - kb < 32) ? (k1 - kb) : 32);
+      for (int i = 0; i < cnt; ++i) {
+        lo += __shfl_sync(0xffffffffu, b.lo, i);
+        hi += __shfl_sync(0xffffffffu, b.hi, i);
+      }
+    }
+    if (lane == 0) {
+      sums[2 * l] = lo;
+      sums[2 * l + 1] = hi;
+    }
+  }
+}
+
 }  // namespace rdisgpu

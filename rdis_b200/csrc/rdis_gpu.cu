@@ -1750,6 +1750,40 @@ int rdisgpu_bounds(rdisgpu_ctx* ctx, const uint8_t* assigned, int64_t nf, const 
   return RDISGPU_OK;
 }
 
+int rdisgpu_bounds_lists(rdisgpu_ctx* ctx, const uint8_t* assigned, int64_t nlists, const int64_t* list_off, const int64_t* fid,
+                         double* sums) {
+  if (!ctx) return RDISGPU_ERR_ARG;
+  if (!ctx->finalized) return ctx->fail(RDISGPU_ERR_STATE, "bounds_lists before finalize");
+  if (!assigned || nlists < 0 || (nlists > 0 && (!list_off || !sums))) return ctx->fail(RDISGPU_ERR_ARG, "bounds_lists: bad argument");
+  if (nlists == 0) return RDISGPU_OK;
+  const int64_t nf = list_off[nlists];
+  if (list_off[0] != 0 || nf < 0 || (nf > 0 && !fid)) return ctx->fail(RDISGPU_ERR_ARG, "bounds_lists: malformed offsets");
+  for (int64_t l = 0; l < nlists; ++l)
+    if (list_off[l + 1] < list_off[l]) return ctx->fail(RDISGPU_ERR_ARG, "bounds_lists: offsets must be non-decreasing");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (nf > 0) {
+    int rc = upload_fids(ctx, nf, fid, ctx->s_i32a);
+    if (rc) return rc;
+  }
+  CK(ctx->cc_assigned.ensure((size_t)ctx->V));
+  CK(cudaMemcpyAsync(ctx->cc_assigned.p, assigned, (size_t)ctx->V, cudaMemcpyHostToDevice, s));
+  CK(ctx->lm_off.ensure((size_t)nlists + 1));
+  CK(cudaMemcpyAsync(ctx->lm_off.p, list_off, (size_t)(nlists + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  CK(ctx->s_f64a.ensure((size_t)nlists * 2));
+  const int threads = 128;
+  const int blocks = (int)std::min<int64_t>((nlists * 32 + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
+  if (ctx->kind == KIND_NLPF)
+    list_bounds_kernel<NlpfOps><<<blocks, threads, 0, s>>>(ctx->gv, ctx->cc_assigned.p, ctx->lm_off.p, ctx->s_i32a.p, nlists, ctx->s_f64a.p);
+  else
+    list_bounds_kernel<BaOps><<<blocks, threads, 0, s>>>(ctx->gv, ctx->cc_assigned.p, ctx->lm_off.p, ctx->s_i32a.p, nlists, ctx->s_f64a.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(sums, ctx->s_f64a.p, (size_t)nlists * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return RDISGPU_OK;
+}
+
 int rdisgpu_batch_info(const rdisgpu_batch* b, int32_t out[8]) {
   if (!b || !out) return RDISGPU_ERR_ARG;
   int n_generic = 0;

@@ -3,6 +3,7 @@
 #include "rdis_host.h"
 
 #include <algorithm>
+#include <limits>
 #include <cassert>
 #include <iostream>
 #include <numeric>
@@ -259,6 +260,22 @@ NumericInterval OptimizableFunction::computeBounds(const FactorPtrVec& fctrs, Va
   return out;
 }
 
+void OptimizableFunction::computeBoundsBatch(const std::vector<FactorPtrVec>& lists, std::vector<NumericInterval>& out) {
+  out.assign(lists.size(), NumericInterval{0.0, 0.0});
+  if (lists.empty()) return;
+  std::vector<int64_t> off(1, 0), fid;
+  for (const FactorPtrVec& l : lists) {
+    for (const Factor* f : l) fid.push_back(f->getID());
+    off.push_back((int64_t)fid.size());
+  }
+  flushAssignments();
+  std::vector<uint8_t> assigned(variables.size());
+  for (size_t v = 0; v < variables.size(); ++v) assigned[v] = variables[v]->isAssigned() ? 1 : 0;
+  std::vector<double> sums(2 * lists.size(), 0.0);
+  check(rdisgpu_bounds_lists(ctx, assigned.data(), (int64_t)lists.size(), off.data(), fid.data(), sums.data()), "rdisgpu_bounds_lists");
+  for (size_t l = 0; l < lists.size(); ++l) out[l] = NumericInterval{sums[2 * l], sums[2 * l + 1]};
+}
+
 // ------------------------------------------------------------------------------------------
 // SubspaceOptimizer
 // ------------------------------------------------------------------------------------------
@@ -481,6 +498,66 @@ void ComponentBatcher::createChildrenOnDevice(OptimizableFunction& func, const V
     if (a.vars.size() != b.vars.size()) return a.vars.size() < b.vars.size();
     return a.vars.front() < b.vars.front();
   });
+}
+
+void ComponentBatcher::optimizeSiblings(CudaSubspaceOptimizer& ssopt, OptimizableFunction& func, std::vector<ComponentProblem>& children,
+                                        const std::vector<NumericInterval>& uab, Numeric parentFmin, Numeric childFmin0, bool useBounds,
+                                        SiblingWave& out) {
+  const size_t n = children.size();
+  if (uab.size() != n) throw std::invalid_argument("optimizeSiblings: one unassigned bound per child");
+  out.outcome.assign(n, SIB_PRUNED);
+  out.value.assign(n, std::numeric_limits<Numeric>::quiet_NaN());
+  out.evaluated = 0;
+  // the state to roll back to for children the reference would not have optimised
+  std::vector<NumericVec> before(n);
+  std::vector<std::vector<char>> wasAssigned(n);
+  for (size_t k = 0; k < n; ++k) {
+    before[k] = children[k].xval;
+    for (const Variable* v : children[k].vars) wasAssigned[k].push_back(v->isAssigned() ? 1 : 0);
+  }
+  ssopt.optimizeBatch(children, false);  // speculative: every sibling, one device call
+
+  // replay of the sequential loop (src/RDISOptimizer.cpp:291-314)
+  Numeric childFmin = childFmin0;
+  Numeric assignedLB = 0;
+  for (size_t k = 0; k < n; ++k) assignedLB += uab[k].lower();  // no child evaluated yet (Component.cpp:322-336)
+  std::vector<char> rollback(n, 1);
+  for (size_t k = 0; k < n; ++k) {
+    const Numeric fmin_k = childFmin + uab[k].lower();           // Component::computeFMin
+    Numeric fx;
+    if (useBounds && fmin_k < uab[k].lower()) {                  // checkUnassignedBound: not optimised, set to its bound
+      out.outcome[k] = SIB_BOUND_SKIPPED;
+      fx = uab[k].lower();
+    } else {
+      out.outcome[k] = SIB_OPTIMISED;
+      fx = children[k].fval;
+      rollback[k] = 0;
+    }
+    out.value[k] = fx;
+    ++out.evaluated;
+    childFmin += uab[k].lower();                                 // Component::onChildEvaluated
+    childFmin -= fx;
+    assignedLB += fx - uab[k].lower();
+    if (k + 1 < n && useBounds && parentFmin <= assignedLB) break;  // checkAssignedBound: the rest is never visited
+  }
+  out.childFmin = childFmin;
+  out.assignedLower = assignedLB;
+  // roll back what the reference would not have touched: host objects and, through Variable::assign, the device mirror
+  for (size_t k = 0; k < n; ++k) {
+    if (!rollback[k]) continue;
+    ComponentProblem& p = children[k];
+    for (size_t i = 0; i < p.vars.size(); ++i) {
+      if (wasAssigned[k][i]) {
+        p.vars[i]->assign(before[k][i]);
+      } else if (p.vars[i]->isAssigned()) {
+        p.vars[i]->unassign();
+      }
+      p.xval[i] = before[k][i];
+    }
+    p.fval = out.value[k];
+    p.deltaFval = 0;
+  }
+  func.flushAssignments();
 }
 
 void ComponentBatcher::leafProblem(OptimizableFunction& func, const ChildComponent& child, const NumericVec& fallback,

@@ -234,6 +234,9 @@ class OptimizableFunction {
   // Factor::computeBounds (assigned variables as points, the rest as their domain hull) — through rdisgpu_bounds.
   virtual NumericInterval computeBounds(const FactorPtrVec& fctrs, VariableID assignedVID = -1);
   NumericInterval computeBounds() { return computeBounds(factors, -1); }
+  // The same for MANY factor lists in one device call (every child of a decomposition: Component::computeBounds,
+  // src/Component.cpp:240-241,592-599), each list's interval sum folded on the device in list order (rdisgpu_bounds_lists).
+  virtual void computeBoundsBatch(const std::vector<FactorPtrVec>& lists, std::vector<NumericInterval>& out);
 
   // hook the reference calls after every Variable::assign made by a subspace optimizer (no-op there,
   // src/OptimizableFunction.h:65-69); here the host->device mirroring is driven by Variable::assign itself
@@ -337,6 +340,31 @@ class ComponentBatcher {
   // million-variable graphs, where the host union-find over heap objects is the slow part.  Needs init().
   static void createChildrenOnDevice(OptimizableFunction& func, const VariableIDVec& componentVars,
                                      std::vector<ChildComponent>& children);
+  // The reference's sibling loop WITH branch & bound (src/RDISOptimizer.cpp:291-314) over ONE batched device call.
+  // Sequentially the reference (a) gives child k the budget fmin_k = childFmin + uab_k.lower (Component::computeFMin,
+  // src/Component.cpp:389-395) and skips its optimisation when fmin_k < uab_k.lower (checkUnassignedBound,
+  // RDISOptimizer.cpp:894-913: the child is set to its lower bound), (b) after every child replaces the child's lower
+  // bound by its value in childFmin and in the parent's assigned bound (Component::onChildEvaluated,
+  // src/Component.cpp:252-343), and (c) leaves the loop as soon as the parent's fmin <= its assigned lower bound
+  // (checkAssignedBound, RDISOptimizer.cpp:916-934): later siblings are never optimised.  All three decisions depend on
+  // the VALUES of earlier siblings, so a wave cannot know in advance which children the reference would have solved.
+  // Siblings share no variable and no factor, so each child's solve is independent of the others: the wave is solved
+  // speculatively in one batch, the reference's decisions are then REPLAYED in sibling order on the results, and the
+  // children the reference would not have optimised are rolled back (host and device state restored).  The outcome is
+  // identical to the sequential loop; the price is the wasted speculative solves.
+  enum SiblingOutcome { SIB_OPTIMISED = 0, SIB_BOUND_SKIPPED = 1, SIB_PRUNED = 2 };
+  struct SiblingWave {
+    std::vector<int> outcome;        // per child, SiblingOutcome
+    std::vector<Numeric> value;      // per child: f(x_end), the lower bound (skipped), or NaN (pruned: never evaluated)
+    Numeric childFmin = 0;           // the parent's estimator after the loop
+    Numeric assignedLower = 0;       // the parent's assigned lower bound after the loop
+    size_t evaluated = 0;            // children the loop visited (optimised or skipped)
+  };
+  // children: in the reference's sibling order; uab: their unassigned bounds; parentFmin / childFmin0: Component::fmin and
+  // the childFmin decompose() computed (fmin - partialEval - sum of lower bounds); useBounds = RDISOptimizer::useBounds.
+  static void optimizeSiblings(CudaSubspaceOptimizer& ssopt, OptimizableFunction& func, std::vector<ComponentProblem>& children,
+                               const std::vector<NumericInterval>& uab, Numeric parentFmin, Numeric childFmin0, bool useBounds,
+                               SiblingWave& out);
   // The subspace problem of optimising ALL variables of a child (a leaf visit):
   // gdfs = the child's factors whose other variables are all assigned (src/RDISOptimizer.cpp:1049-1059),
   // start values = current values of the variables that are assigned, else `fallback[vid]`.

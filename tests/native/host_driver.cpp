@@ -5,6 +5,7 @@
 //   children_gpu <file>        ComponentBatcher::createChildrenOnDevice: the same listing through rdisgpu_components
 //   wave <file> <maxiters>     one sibling wave through CudaSubspaceOptimizer::optimizeBatch
 //   benchwaves <bal> <steps> <warmup>   bench.py's end-to-end leg (timed alternating waves on a BAL file)
+//   siblings[_seq] <file> <maxiters> <useBounds> <parentFmin> <childFmin0>   the sibling loop with branch & bound, batched / sequential
 //   single <file> <maxiters>   the same wave, one CudaSubspaceOptimizer::optimize call per child
 //                              (the reference's sibling loop, src/RDISOptimizer.cpp:291-314)
 // Output is plain text with %.17g numbers; the Python side compares it with the ctypes path and the oracle.
@@ -14,6 +15,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <limits>
 #include <memory>
 
 #include "rdis_builders.h"
@@ -243,6 +245,66 @@ int main(int argc, char** argv) {
     }
     const int maxiters = argc > 3 ? std::atoi(argv[3]) : 25;
     L.fn->init(0);
+    if (mode == "siblings" || mode == "siblings_seq") {
+      // siblings[_seq] <file> <maxiters> <useBounds> <parentFmin> <childFmin0>: the sibling loop with branch & bound —
+      // batched (ComponentBatcher::optimizeSiblings: one device call + replay) or the reference's own sequential form
+      // (one CudaSubspaceOptimizer::optimize per child it actually visits, src/RDISOptimizer.cpp:291-314)
+      const bool useBounds = argc > 4 && std::atoi(argv[4]) != 0;
+      const double parentFmin = argc > 5 ? std::atof(argv[5]) : 0.0, childFmin0 = argc > 6 ? std::atof(argv[6]) : 0.0;
+      CudaSubspaceOptimizer ssopt(*L.fn);
+      ParameterMap opts;
+      opts["SSmaxit"] = maxiters;
+      opts["SSftol"] = 3e-8;
+      ssopt.setParameters(opts);
+      std::vector<ComponentProblem> probs(kids.size());
+      std::vector<FactorPtrVec> lists(kids.size());
+      for (size_t k = 0; k < kids.size(); ++k) {
+        ComponentBatcher::leafProblem(*L.fn, kids[k], L.x0, probs[k]);
+        for (FactorID f : kids[k].factors) lists[k].push_back(L.fn->getFactors()[(size_t)f]);
+      }
+      std::vector<NumericInterval> uab;
+      L.fn->computeBoundsBatch(lists, uab);  // children's variables are unassigned here: Component::computeBounds at creation
+      ComponentBatcher::SiblingWave w;
+      if (mode == "siblings") {
+        ComponentBatcher::optimizeSiblings(ssopt, *L.fn, probs, uab, parentFmin, childFmin0, useBounds, w);
+      } else {
+        const size_t n = probs.size();
+        w.outcome.assign(n, ComponentBatcher::SIB_PRUNED);
+        w.value.assign(n, std::numeric_limits<double>::quiet_NaN());
+        double childFmin = childFmin0, assignedLB = 0;
+        for (size_t k = 0; k < n; ++k) assignedLB += uab[k].lower();
+        for (size_t k = 0; k < n; ++k) {
+          const double fmin_k = childFmin + uab[k].lower();
+          double fx;
+          if (useBounds && fmin_k < uab[k].lower()) {
+            w.outcome[k] = ComponentBatcher::SIB_BOUND_SKIPPED;
+            fx = uab[k].lower();
+          } else {
+            w.outcome[k] = ComponentBatcher::SIB_OPTIMISED;
+            fx = probs[k].fval = ssopt.optimize(probs[k].vars, probs[k].factors, probs[k].xval, probs[k].deltaFval, false);
+          }
+          w.value[k] = fx;
+          ++w.evaluated;
+          childFmin += uab[k].lower();
+          childFmin -= fx;
+          assignedLB += fx - uab[k].lower();
+          if (k + 1 < n && useBounds && parentFmin <= assignedLB) break;
+        }
+        w.childFmin = childFmin;
+        w.assignedLower = assignedLB;
+      }
+      std::printf("siblings %zu evaluated %zu childFmin %.17g assignedLower %.17g\n", probs.size(), w.evaluated, w.childFmin, w.assignedLower);
+      for (size_t k = 0; k < probs.size(); ++k)
+        std::printf("child %zu outcome %d value %.17g uab %.17g %.17g\n", k, w.outcome[k], w.value[k], uab[k].lower(), uab[k].upper());
+      // the state the loop leaves behind: host objects and the device mirror (read back through the C-ABI)
+      std::vector<double> dev((size_t)L.fn->getNumVars());
+      rdisgpu_get_x(L.fn->device(), (int64_t)dev.size(), nullptr, dev.data());
+      for (Variable* v : L.fn->getVariables()) {
+        if (v->isAssigned()) std::printf("v %lld 1 %.17g %.17g\n", v->getID(), v->eval(), dev[(size_t)v->getID()]);
+        else std::printf("v %lld 0\n", v->getID());
+      }
+      return 0;
+    }
     const bool lm = argc > 4 && std::string(argv[4]) == "lm";
     CudaSubspaceOptimizer cgd(*L.fn);
     CudaLMSubspaceOptimizer lmo(*L.fn);

@@ -311,3 +311,69 @@ def test_cpp_end_to_end_waves_from_a_bal_file(driver, tmp_path):
         ref.append(ctx.eval())
     assert objs == ref
     assert np.allclose(sums, rsum, rtol=1e-14, atol=0)
+
+
+def _parse_siblings(text):
+    lines = text.strip().splitlines()
+    head = lines[0].split()
+    info = {"n": int(head[1]), "evaluated": int(head[3]), "childFmin": float(head[5]), "assignedLower": float(head[7])}
+    kids = [ln.split() for ln in lines[1:] if ln.startswith("child ")]
+    info["outcome"] = [int(k[3]) for k in kids]
+    info["value"] = [k[5] for k in kids]            # text: NaN-safe, bit-exact (%.17g)
+    info["uab"] = np.array([[float(k[7]), float(k[8])] for k in kids])
+    info["state"] = [ln for ln in lines[1:] if ln.startswith("v ")]
+    return info
+
+
+@pytest.mark.gpu
+def test_sibling_loop_with_branch_and_bound_batched_equals_sequential(driver, tmp_path):
+    """ComponentBatcher::optimizeSiblings (ONE device call for the wave, then the reference's branch & bound decisions
+    replayed in sibling order, un-visited children rolled back) against the reference's own sequential sibling loop
+    (src/RDISOptimizer.cpp:291-314: computeFMin / checkUnassignedBound / onChildEvaluated / checkAssignedBound after
+    every child) on a wave where BOTH prunings fire: same outcome per child, same values, same parent bookkeeping, and
+    the same host + device state afterwards — to the bit."""
+    from rdis_b200 import problems as P
+    spec = P.sinusoid(7, 2, 4)
+    x0 = P.random_start(spec, 4)
+    assigned = np.zeros(spec["V"], np.uint8); assigned[:7] = 1        # 8 sibling subtrees
+    path = str(tmp_path / "sib.bin")
+    write_problem(path, spec, x0, assigned)
+
+    def run(mode, use_bounds, parent_fmin, child_fmin0):
+        out = subprocess.run([driver, mode, path, "25", str(int(use_bounds)), repr(float(parent_fmin)), repr(float(child_fmin0))],
+                             capture_output=True, text=True, check=True).stdout
+        return _parse_siblings(out)
+
+    free = run("siblings", False, 0.0, 0.0)                            # no bounds: every child optimised
+    assert free["outcome"] == [0] * 8 and free["evaluated"] == 8
+    fx = np.array([float(v) for v in free["value"]]); lb = free["uab"][:, 0]
+    assert np.isfinite(lb).all() and (lb <= fx + 1e-9).all()          # the interval bounds enclose the optima
+    gain = fx - lb
+    # (1) the parent's budget is exhausted after child 4: children 5..7 are never visited
+    parent_fmin = lb.sum() + gain[:5].sum() - 1e-9
+    # (2) childFmin goes negative after child 2: children 3, 4 are set to their lower bound without being optimised
+    child_fmin0 = gain[:3].sum() - 1e-9
+    for pf, cf in ((parent_fmin, 1e300), (1e300, child_fmin0), (lb.sum() + gain[:3].sum() + 1e-9, child_fmin0)):
+        a = run("siblings", True, pf, cf)
+        b = run("siblings_seq", True, pf, cf)
+        assert a["outcome"] == b["outcome"] and a["value"] == b["value"] and a["evaluated"] == b["evaluated"]
+        assert a["childFmin"] == b["childFmin"] and a["assignedLower"] == b["assignedLower"]
+        assert a["state"] == b["state"]
+        for ln in a["state"]:                                          # host objects and the device mirror agree
+            t = ln.split()
+            assert t[2] == "0" or t[3] == t[4]
+    def replay(pf, cf):                                               # the loop once more, in numpy, from fx and lb alone
+        out, child_fmin, alb = [2] * 8, cf, lb.sum()
+        for k in range(8):
+            skipped = (child_fmin + lb[k]) < lb[k]
+            out[k] = 1 if skipped else 0
+            val = lb[k] if skipped else fx[k]
+            child_fmin = child_fmin + lb[k] - val
+            alb += val - lb[k]
+            if k + 1 < 8 and pf <= alb:
+                break
+        return out
+    a = run("siblings", True, parent_fmin, 1e300)
+    assert a["outcome"] == replay(parent_fmin, 1e300) and 2 in a["outcome"] and a["outcome"][0] == 0
+    a = run("siblings", True, 1e300, child_fmin0)
+    assert a["outcome"] == replay(1e300, child_fmin0) and 1 in a["outcome"] and a["outcome"][:3] == [0, 0, 0]
