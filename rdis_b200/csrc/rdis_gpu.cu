@@ -24,6 +24,7 @@
 #include "nlpf_resident.cuh"
 #include "bounds_kernels.cuh"
 #include "strict_kernels.cuh"
+#include "lm_dense.cuh"
 
 using namespace rdisgpu;
 
@@ -127,6 +128,11 @@ struct rdisgpu_ctx {
   DevBuf<double> lm_scratch;
   DevBuf<int64_t> lm_off;
   bool lm_vloc_ready = false;
+  // Levenberg-Marquardt for one component of any size (lm_dense.cuh): dense normal equations + their factor, the
+  // block-sparse Jacobian, the component's incidence, vectors and scalars
+  DevBuf<double> lmd_A, lmd_L, lmd_jval, lmd_e, lmd_hx, lmd_vec, lmd_scal;
+  DevBuf<int32_t> lmd_idx;
+  DevBuf<int> lmd_flag;
   bool ba_smem_optin = false;
   // resident NonlinearProductFactor components (nlpf_resident.cuh): term table + host copies for classification
   DevBuf<int32_t> tvrow, eterm, vloc, floc;
@@ -1564,6 +1570,194 @@ int rdisgpu_solve_cgd_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_o
   return RDISGPU_OK;
 }
 
+// LMSubspaceOptimizer::optimize for ONE component of more than kLmMaxVars variables (lm_dense.cuh): levmar's dlevmar_der
+// control flow on the host, everything else on the device.  x0_dev: start values (device, m doubles) or null = device state.
+static int solve_lm_dense(rdisgpu_ctx* ctx, rdisgpu_batch* b, int64_t pidx, const double* x0_dev, int itmax, double tau, double eps1,
+                          double eps2, double eps3, ResultRec* res_host, double* xout_dev) {
+  cudaStream_t s = ctx->stream;
+  const ProblemDesc& D = b->h_probs[(size_t)pidx];
+  const int m = D.nv, nf = D.nf;
+  const int32_t* hv = reinterpret_cast<const int32_t*>(b->h_blob.p + ((const char*)b->d_vids - b->blob.p)) + D.var_off;
+  const int32_t* hf = reinterpret_cast<const int32_t*>(b->h_blob.p + ((const char*)b->d_fids - b->blob.p)) + D.fac_off;
+  // ---- the component's row pointers and variable-major incidence (host, once per solve) ----
+  std::vector<int32_t> loc((size_t)ctx->V, -1);
+  for (int i = 0; i < m; ++i) loc[(size_t)hv[i]] = i;
+  std::vector<int32_t> jptr((size_t)nf + 1, 0);
+  auto arity = [&](int32_t f) { return ctx->kind == KIND_BA ? 12 : ctx->h_rp32[(size_t)f + 1] - ctx->h_rp32[(size_t)f]; };
+  auto slot_vid = [&](int32_t f, int sl) -> int32_t {
+    if (ctx->kind == KIND_BA) return sl < 9 ? 9 * ctx->h_cam[(size_t)f] + sl : 9 * ctx->ncams + 3 * ctx->h_pt[(size_t)f] + (sl - 9);
+    return ctx->h_evid32[(size_t)ctx->h_rp32[(size_t)f] + sl];
+  };
+  for (int k = 0; k < nf; ++k) jptr[(size_t)k + 1] = jptr[(size_t)k] + arity(hf[k]);
+  const int64_t nent = jptr[(size_t)nf];
+  std::vector<int32_t> voff((size_t)m + 1, 0);
+  for (int k = 0; k < nf; ++k)
+    for (int sl = 0; sl < arity(hf[k]); ++sl) {
+      const int32_t li = loc[(size_t)slot_vid(hf[k], sl)];
+      if (li >= 0) ++voff[(size_t)li + 1];
+    }
+  for (int i = 0; i < m; ++i) voff[(size_t)i + 1] += voff[(size_t)i];
+  std::vector<int32_t> ient((size_t)voff[(size_t)m]), irow((size_t)voff[(size_t)m]), cur(voff.begin(), voff.end() - 1);
+  for (int k = 0; k < nf; ++k)
+    for (int sl = 0; sl < arity(hf[k]); ++sl) {
+      const int32_t li = loc[(size_t)slot_vid(hf[k], sl)];
+      if (li < 0) continue;
+      ient[(size_t)cur[(size_t)li]] = jptr[(size_t)k] + sl;
+      irow[(size_t)cur[(size_t)li]++] = k;
+    }
+  // ---- device buffers ----
+  const size_t mm = (size_t)m * m;
+  CK(ctx->lmd_A.ensure(mm));
+  CK(ctx->lmd_L.ensure(mm));
+  CK(ctx->lmd_jval.ensure((size_t)std::max<int64_t>(nent, 1)));
+  CK(ctx->lmd_e.ensure((size_t)nf));
+  CK(ctx->lmd_hx.ensure((size_t)nf));
+  CK(ctx->lmd_vec.ensure((size_t)m * 7));   // g | p | pDp | dp | y | diag | spare
+  CK(ctx->lmd_scal.ensure(4096));
+  CK(ctx->lmd_flag.ensure(1));
+  const size_t nidx = (size_t)nf + 1 + (size_t)nent + (size_t)m + 1 + 2 * ient.size() + 8;
+  CK(ctx->lmd_idx.ensure(nidx));
+  int32_t* d_jptr = ctx->lmd_idx.p;
+  int32_t* d_jcol = d_jptr + nf + 1;
+  int32_t* d_voff = d_jcol + nent;
+  int32_t* d_ient = d_voff + m + 1;
+  int32_t* d_irow = d_ient + ient.size();
+  CK(cudaMemcpyAsync(d_jptr, jptr.data(), jptr.size() * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_voff, voff.data(), voff.size() * 4, cudaMemcpyHostToDevice, s));
+  if (!ient.empty()) {
+    CK(cudaMemcpyAsync(d_ient, ient.data(), ient.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_irow, irow.data(), irow.size() * 4, cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaMemcpyAsync(ctx->lm_vloc.p, loc.data(), loc.size() * 4, cudaMemcpyHostToDevice, s));  // whole map: restored below
+  CK(cudaStreamSynchronize(s));  // the staging vectors above may now die
+  double* g = ctx->lmd_vec.p;
+  double* p = g + m;
+  double* pDp = p + m;
+  double* dp = pDp + m;
+  double* y = dp + m;
+  double* diag = y + m;
+  double* scal = ctx->lmd_scal.p;
+  LmDenseView L;
+  L.m = m; L.nf = nf;
+  L.fids = b->d_fids + D.fac_off;
+  L.vids = b->d_vids + D.var_off;
+  L.vloc = ctx->lm_vloc.p;
+  L.jptr = d_jptr; L.jcol = d_jcol; L.jval = ctx->lmd_jval.p;
+  L.e = ctx->lmd_e.p; L.hx = ctx->lmd_hx.p;
+  L.voff = d_voff; L.ient = d_ient; L.irow = d_irow;
+  const bool nlpf = (ctx->kind == KIND_NLPF);
+  const int fblocks = std::min(512, (nf + 255) / 256);
+  int launches = 0;
+  if (x0_dev) CK(cudaMemcpyAsync(p, x0_dev, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  else {
+    gather_x_kernel<<<(m + 255) / 256, 256, 0, s>>>(ctx->gv, m, L.vids, p);
+    ++launches;
+  }
+  // func(q): assign, residuals; returns {sum f, sum hx^2}
+  auto func = [&](const double* q, double& sumf, double& e2) -> int {
+    lm_assign_kernel<<<(m + 255) / 256, 256, 0, s>>>(ctx->gv, L.vids, m, q);
+    if (nlpf) lm_func_kernel<NlpfOps><<<fblocks, 256, 0, s>>>(ctx->gv, L, scal + 8);
+    else lm_func_kernel<BaOps><<<fblocks, 256, 0, s>>>(ctx->gv, L, scal + 8);
+    launches += 2;
+    std::vector<double> part((size_t)fblocks * 2);
+    CK(cudaMemcpyAsync(part.data(), scal + 8, part.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    sumf = 0.0; e2 = 0.0;
+    for (int i = 0; i < fblocks; ++i) { sumf += part[2 * (size_t)i]; e2 += part[2 * (size_t)i + 1]; }
+    return RDISGPU_OK;
+  };
+  auto finite = [](double v) { return std::fabs(v) <= 1.7976931348623157e308; };
+  double ival = 0, p_eL2 = 0;
+  int rc = func(p, ival, p_eL2);
+  if (rc) return rc;
+  lm_negate_kernel<<<(nf + 255) / 256, 256, 0, s>>>(L.hx, L.e, nf);
+  ++launches;
+  double mu = 0.0;
+  int nu = 2, stop = 0, nfev = 1, njev = 0, k_it = 0;
+  if (!finite(p_eL2)) stop = 7;
+  for (k_it = 0; k_it < itmax && !stop; ++k_it) {
+    if (p_eL2 <= eps3) { stop = 6; break; }
+    if (nlpf) lm_rows_kernel<NlpfOps><<<std::min(1024, (nf + 127) / 128), 128, 0, s>>>(ctx->gv, L);
+    else lm_rows_kernel<BaOps><<<std::min(1024, (nf + 127) / 128), 128, 0, s>>>(ctx->gv, L);
+    ++njev;
+    CK(cudaMemsetAsync(ctx->lmd_A.p, 0, mm * sizeof(double), s));
+    lm_assemble_kernel<<<std::min(2048, (m + 3) / 4), 128, 0, s>>>(L, ctx->lmd_A.p, g);
+    lm_scalars_kernel<<<1, 256, 0, s>>>(ctx->lmd_A.p, g, p, m, diag, scal);
+    launches += 3;
+    double h3[3];
+    CK(cudaMemcpyAsync(h3, scal, sizeof h3, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const double jacTe_inf = h3[0], p_L2 = h3[1];
+    if (jacTe_inf <= eps1) { stop = 1; break; }
+    if (k_it == 0) mu = tau * h3[2];
+    while (true) {  // adaptive damping
+      lm_augment_kernel<<<std::min<int64_t>(4096, (int64_t)((mm + 255) / 256)), 256, 0, s>>>(ctx->lmd_A.p, ctx->lmd_L.p, m, mu);
+      CK(cudaMemsetAsync(ctx->lmd_flag.p, 0, sizeof(int), s));
+      ++launches;
+      for (int kb = 0; kb < m; kb += kLmNB) {
+        const int nb = std::min(kLmNB, m - kb), rest = m - kb - nb;
+        lm_potrf_kernel<<<1, kLmNB, 0, s>>>(ctx->lmd_L.p, m, kb, ctx->lmd_flag.p);
+        ++launches;
+        if (rest > 0) {
+          lm_trsm_kernel<<<(rest + 127) / 128, 128, 0, s>>>(ctx->lmd_L.p, m, kb);
+          const int nt = (rest + kLmNB - 1) / kLmNB;
+          lm_syrk_kernel<<<dim3((unsigned)nt, (unsigned)nt), 128, 0, s>>>(ctx->lmd_L.p, m, kb, nb);
+          launches += 2;
+        }
+      }
+      lm_trsv_kernel<<<1, 1024, 0, s>>>(ctx->lmd_L.p, m, g, p, mu, y, dp, pDp, scal + 4);
+      ++launches;
+      int hflag = 0;
+      double h2[2];
+      CK(cudaMemcpyAsync(&hflag, ctx->lmd_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(h2, scal + 4, sizeof h2, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (hflag == 0 && finite(h2[0])) {
+        const double Dp_L2 = h2[0], dL = h2[1];
+        if (Dp_L2 <= eps2 * eps2 * p_L2) { stop = 2; break; }
+        if (Dp_L2 >= (p_L2 + eps2) / (1e-12 * 1e-12)) { stop = 4; break; }
+        double sumf, pDp_eL2;
+        rc = func(pDp, sumf, pDp_eL2);
+        if (rc) return rc;
+        ++nfev;
+        if (!finite(pDp_eL2)) { stop = 7; break; }
+        const double dF = p_eL2 - pDp_eL2;
+        if (dL > 0.0 && dF > 0.0) {
+          double t = (2.0 * dF / dL - 1.0);
+          t = 1.0 - t * t * t;
+          mu = mu * ((t >= 0.3333333334) ? t : 0.3333333334);
+          nu = 2;
+          CK(cudaMemcpyAsync(p, pDp, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+          lm_negate_kernel<<<(nf + 255) / 256, 256, 0, s>>>(L.hx, L.e, nf);
+          ++launches;
+          p_eL2 = pDp_eL2;
+          break;
+        }
+      }
+      mu *= nu;
+      const int nu2 = nu << 1;
+      if (nu2 <= nu) { stop = 5; break; }
+      nu = nu2;
+    }
+  }
+  if (k_it >= itmax) stop = 3;
+  double fval, e2;
+  rc = func(p, fval, e2);  // commit: quickAssignVals(xval) without clamping, fval = evalFactors (:102-110)
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(xout_dev, p, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemsetAsync(ctx->lm_vloc.p, 0xff, (size_t)ctx->V * sizeof(int32_t), s));  // -1 everywhere again
+  CK(cudaStreamSynchronize(s));
+  res_host->f_init = ival;
+  res_host->f_end = fval;
+  res_host->iters = k_it;
+  res_host->status = stop;
+  res_host->n_value = nfev;
+  res_host->n_slope = njev;
+  ctx->launches += launches;
+  b->last_launches += launches;
+  return RDISGPU_OK;
+}
+
 int rdisgpu_solve_lm_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_off, const int32_t* vids, const int64_t* fac_off,
                          const int64_t* fids, const double* x0, int maxiters, const double* opts4, double* x_out,
                          double* f_init, double* f_end, int32_t* iters, int32_t* stop, int64_t* n_feval, int64_t* n_jeval) {
@@ -1583,9 +1777,8 @@ int rdisgpu_solve_lm_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_of
   std::vector<int64_t> off((size_t)nprobs + 1, 0);
   for (int64_t p = 0; p < nprobs; ++p) {
     const int64_t m = b->h_probs[p].nv, nf = b->h_probs[p].nf;
-    if (m > kLmMaxVars) return ctx->fail(RDISGPU_ERR_ARG, "solve_lm_csr: components of more than 32 variables are not supported");
     const int64_t n = std::max(nf, m);
-    off[(size_t)p + 1] = off[(size_t)p] + n * m + 2 * n;
+    off[(size_t)p + 1] = off[(size_t)p] + ((m > kLmMaxVars) ? 0 : n * m + 2 * n);  // larger components: lm_dense.cuh, own buffers
   }
   cudaStream_t s = ctx->stream;
   CK(ctx->lm_off.ensure(off.size()));
@@ -1632,13 +1825,30 @@ int rdisgpu_solve_lm_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* var_of
     return cudaGetLastError();
   };
   CK(launch_generic(b->d_cam_order, b->n_cam));
-  CK(launch_generic(b->d_order, (int)b->h_order.size()));
+  // generic shapes: up to kLmMaxVars variables -> one CTA per component; larger -> the dense solver, one at a time
+  std::vector<int32_t> small_list, big_list;
+  for (int32_t pi : b->h_order) (b->h_probs[(size_t)pi].nv > kLmMaxVars ? big_list : small_list).push_back(pi);
+  if (!small_list.empty()) {
+    CK(ctx->s_i32b.ensure(small_list.size()));
+    CK(cudaMemcpyAsync(ctx->s_i32b.p, small_list.data(), small_list.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(launch_generic(ctx->s_i32b.p, (int)small_list.size()));
+    CK(cudaStreamSynchronize(s));  // small_list is a local
+  }
   ctx->launches += launches;
   b->last_launches = launches;
+  std::vector<std::pair<int32_t, ResultRec>> big_res;
+  for (int32_t pi : big_list) {
+    ResultRec r;
+    const ProblemDesc& D = b->h_probs[(size_t)pi];
+    rc = solve_lm_dense(ctx, b, pi, bv.x0 ? bv.x0 + D.var_off : nullptr, maxiters, tau, eps1, eps2, eps3, &r, b->xout.p + D.var_off);
+    if (rc) return rc;
+    big_res.push_back({pi, r});
+  }
   CK(cudaMemcpyAsync(b->h_res.p, b->res.p, (size_t)nprobs * sizeof(ResultRec), cudaMemcpyDeviceToHost, s));
   if (x_out && b->total_nv > 0)
     CK(cudaMemcpyAsync(b->h_x.p, b->xout.p, (size_t)b->total_nv * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));  // also keeps `off` alive until the copy is done
+  for (const auto& br : big_res) b->h_res.p[br.first] = br.second;
   if (x_out && b->total_nv > 0) std::memcpy(x_out, b->h_x.p, (size_t)b->total_nv * sizeof(double));
   for (int64_t p = 0; p < nprobs; ++p) {
     const ResultRec& r = b->h_res.p[p];

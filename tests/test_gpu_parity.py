@@ -518,15 +518,62 @@ def test_solve_lm_blocks(gpu, oracle_mod):
         tot = ctx.eval(ps.fids)
         assert abs(tot - r["f_end"].sum()) <= 1e-9 * abs(tot)
         assert (r["f_end"] <= r["f_init"] * (1 + 1e-12)).all()
-    # more than 32 variables per component is refused loudly, not silently solved some other way
+    # a component of more than 32 variables takes the dense solver (lm_dense.cuh): the whole graph as ONE problem
+    # (504 variables, 640 residuals; the oracle's dense levmar restatement needs ~1 s for it)
     big = P.full_problem(spec)
-    with pytest.raises(gpu.RdisGpuError):
-        ctx.solve_lm(big, x0[big.vids], 5, 3e-8)
+    ctx.set_x(x0)
+    r = ctx.solve_lm(big, x0[big.vids], 6, 3e-8)
+    orc = oracle_mod.OracleFunction.from_spec(spec); orc.set_x(x0)
+    o = orc.solve_lm_batch(big.var_off, big.vids, big.fac_off, big.fids, x0[big.vids], 6, 3e-8)
+    print("LM whole graph (m=%d): f %.6e -> gpu %.9e oracle %.9e, iters %d/%d stop %d/%d" % (
+        len(big.vids), r["f_init"][0], r["f_end"][0], o["f_end"][0], r["iters"][0], o["iters"][0], r["stop"][0], o["stop"][0]))
+    assert abs(r["f_init"][0] - o["f_init"][0]) <= 1e-12 * abs(o["f_init"][0])
+    assert abs(r["f_end"][0] - o["f_end"][0]) <= 1e-6 * abs(o["f_end"][0])
+    assert r["iters"][0] == o["iters"][0] and r["stop"][0] == o["stop"][0]
+    assert np.array_equal(ctx.get_x()[big.vids], r["x"]) and r["f_end"][0] < r["f_init"][0]
     # an empty component: contract of the boundary
     emp = gpu.ProblemSet.from_lists([(np.array([9 * 6, 9 * 6 + 1, 9 * 6 + 2], np.int32), np.zeros(0, np.int64))])
     ctx.set_x(x0)
     r = ctx.solve_lm(emp, x0[emp.vids], 5, 3e-8)
     assert r["f_end"][0] == 0 and np.array_equal(r["x"], x0[emp.vids])
+
+
+def test_solve_lm_dense_components(gpu, oracle_mod):
+    """Levenberg-Marquardt on components of more than 32 variables (lm_dense.cuh: block-sparse Jacobian rows, dense
+    normal equations assembled per variable, blocked Cholesky with the trailing update on the FP64 tensor cores)
+    against the oracle's dense levmar restatement: sinusoid subtrees (127 / 255 variables; several per call, sizes that
+    are not multiples of the 64-wide blocks) and a two-camera bundle-adjustment block.  PARITY UNPINNED upstream."""
+    from rdis_b200 import Context, problems as P
+    from rdis_b200.problems import ProblemSet
+    tree = P.sinusoid(8, 2, 4)
+    xt = P.random_start(tree, 9)
+    ctx = Context.from_spec(tree)
+    orc = oracle_mod.OracleFunction.from_spec(tree)
+    for lv, iters in ((2, 12), (1, 8)):
+        ps = P.sinusoid_subtree_problems(tree, lv)
+        ctx.set_x(xt); orc.set_x(xt)
+        r = ctx.solve_lm(ps, xt[ps.vids], iters, 3e-8)
+        o = orc.solve_lm_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, xt[ps.vids], iters, 3e-8)
+        rel = _relerr(r["f_end"], o["f_end"], 1e-12)
+        print("LM dense, %d subtrees of %d variables: worst rel f_end %.2e, iters %s / %s, stop %s / %s" % (
+            ps.n, ps.var_off[1], rel.max(), r["iters"].tolist(), o["iters"].tolist(), r["stop"].tolist(), o["stop"].tolist()))
+        assert _relerr(r["f_init"], o["f_init"], 1e-12).max() <= 1e-12
+        assert rel.max() <= 1e-6
+        assert np.array_equal(r["iters"], o["iters"]) and np.array_equal(r["stop"], o["stop"])
+        assert np.array_equal(ctx.get_x()[ps.vids], r["x"])
+    spec = P.ba_synthetic(ncams=4, npts=90, nobs=330, seed=2)
+    x0 = spec["x0"]
+    cam_sel = np.array([0, 2]); pt_sel = np.unique(spec["pt"][np.isin(spec["cam"], cam_sel)])[:40]
+    vids = np.sort(np.concatenate([(9 * cam_sel[:, None] + np.arange(9)).ravel(), (9 * 4 + 3 * pt_sel[:, None] + np.arange(3)).ravel()])).astype(np.int32)
+    fids = np.nonzero(np.isin(spec["cam"], cam_sel) | np.isin(spec["pt"], pt_sel))[0].astype(np.int64)
+    ps = ProblemSet([0, len(vids)], vids, [0, len(fids)], fids)
+    bctx = Context.from_spec(spec); borc = oracle_mod.OracleFunction.from_spec(spec)
+    bctx.set_x(x0); borc.set_x(x0)
+    r = bctx.solve_lm(ps, x0[vids], 10, 3e-8)
+    o = borc.solve_lm_batch(ps.var_off, ps.vids, ps.fac_off, ps.fids, x0[vids], 10, 3e-8)
+    print("LM dense, BA block m=%d n=%d: f %.6e -> gpu %.9e oracle %.9e, iters %d/%d stop %d/%d" % (
+        len(vids), len(fids), r["f_init"][0], r["f_end"][0], o["f_end"][0], r["iters"][0], o["iters"][0], r["stop"][0], o["stop"][0]))
+    assert abs(r["f_end"][0] - o["f_end"][0]) <= 1e-6 * abs(o["f_end"][0]) and r["iters"][0] == o["iters"][0]
 
 
 @pytest.mark.gpu
