@@ -6,6 +6,7 @@ fails, and if no sm_100 GPU is usable `Context()` raises.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -139,9 +140,12 @@ class Context:
             raise RdisGpuError(f"rdisgpu_create failed ({rc}): {self._lib.rdisgpu_last_error(None).decode()}")
         self._h = h
         self._keep = []
+        self._batches = weakref.WeakSet()   # live Batch objects: closed before the context (they point into it)
 
     def close(self):
         if getattr(self, "_h", None):
+            for b in list(getattr(self, "_batches", ())):
+                b.close()
             self._lib.rdisgpu_destroy(self._h)
             self._h = None
 
@@ -374,6 +378,7 @@ class Batch:
         ctx._ck(self._lib.rdisgpu_batch_create_csr(ctx._h, problems.n, _p(problems.var_off), _p(problems.vids),
                                                    _p(problems.fac_off), _p(problems.fids), C.byref(h)))
         self._h = h
+        ctx._batches.add(self)
         self._rarr = (Result * problems.n)()
         self._xout = np.empty(len(problems.vids))
         for i in range(problems.n):

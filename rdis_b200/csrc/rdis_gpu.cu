@@ -112,6 +112,7 @@ struct rdisgpu_ctx {
   std::vector<int32_t> vmark, fmark;  // sibling check: epoch stamps (no per-call clearing)
   int32_t mark_epoch = 0;
   rdisgpu_batch* scratch_batch = nullptr;  // reused by the one-shot solve entry points
+  int live_batches = 0;                    // rdisgpu_batch_create'd and not yet destroyed: rdisgpu_destroy refuses while > 0
   bool generic_only = false;  // rdisgpu_set_option("generic_only"): bypass the BA block kernels (tests)
   int cam_cluster_opt = 0;    // rdisgpu_set_option("camera_cluster"): pin the cluster width of the camera-block kernel (0 = choose)
   bool strict = false;        // rdisgpu_set_option("strict"): every solve through strict_kernels.cuh (bit-exact parity instrument)
@@ -311,6 +312,11 @@ int rdisgpu_create(rdisgpu_ctx** out, int device) {
 
 void rdisgpu_destroy(rdisgpu_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->live_batches > 0) {  // a batch holds a pointer to its context: destroying it first would leave it dangling
+    ctx->err = "rdisgpu_destroy: " + std::to_string(ctx->live_batches) + " batch(es) still alive; destroy them first (context kept)";
+    std::fprintf(stderr, "%s\n", ctx->err.c_str());
+    return;
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   delete ctx->scratch_batch;
@@ -1254,6 +1260,7 @@ int rdisgpu_batch_create(rdisgpu_ctx* ctx, const rdisgpu_problem* probs, int64_t
   const int rc = batch_build(b.get(), pv);
   if (rc) return rc;
   *out = b.release();
+  ++ctx->live_batches;
   return RDISGPU_OK;
 }
 
@@ -1273,6 +1280,7 @@ int rdisgpu_batch_create_csr(rdisgpu_ctx* ctx, int64_t nprobs, const int64_t* va
   const int rc = batch_build(b.get(), pv);
   if (rc) return rc;
   *out = b.release();
+  ++ctx->live_batches;
   return RDISGPU_OK;
 }
 
@@ -1485,6 +1493,7 @@ void rdisgpu_batch_destroy(rdisgpu_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
+  --b->ctx->live_batches;
   delete b;
 }
 
@@ -1873,7 +1882,6 @@ int rdisgpu_components(rdisgpu_ctx* ctx, const uint8_t* assigned, int32_t* var_l
   CK(ctx->cc_assigned.ensure((size_t)V));
   CK(ctx->cc_vlabel.ensure((size_t)V));
   CK(ctx->cc_flabel.ensure((size_t)F));
-  CK(ctx->cc_flag.ensure(1));
   CK(cudaMemcpyAsync(ctx->cc_assigned.p, assigned, (size_t)V, cudaMemcpyHostToDevice, s));
   ComponentsView cv;
   cv.assigned = ctx->cc_assigned.p;
@@ -1885,18 +1893,32 @@ int rdisgpu_components(rdisgpu_ctx* ctx, const uint8_t* assigned, int32_t* var_l
   const int fb = (int)std::min<int64_t>((F + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
   cc_init_kernel<<<vb, threads, 0, s>>>(ctx->gv, cv);
   ++ctx->launches;
+  // Rounds are enqueued kRoundsPerCheck at a time, each with its own change flag; the host looks at the flags once per
+  // group (one copy + one synchronisation instead of one per round): a round that changed nothing is a fixed point, and
+  // the rounds enqueued after it are no-ops.  Long chains (the 1000-variable sinusoid chain) need tens of rounds.
+  constexpr int kRoundsPerCheck = 8;
+  CK(ctx->cc_flag.ensure(kRoundsPerCheck));
   int rounds = 0;
-  for (;; ++rounds) {
+  for (bool converged = false; !converged;) {
     if (rounds > (1 << 20)) return ctx->fail(RDISGPU_ERR_CUDA, "components: label propagation did not converge");
-    CK(cudaMemsetAsync(ctx->cc_flag.p, 0, sizeof(int32_t), s));
-    cc_hook_kernel<<<fb, threads, 0, s>>>(ctx->gv, cv);
-    cc_jump_kernel<<<vb, threads, 0, s>>>(ctx->gv, cv);
-    ctx->launches += 2;
+    CK(cudaMemsetAsync(ctx->cc_flag.p, 0, kRoundsPerCheck * sizeof(int32_t), s));
+    for (int r = 0; r < kRoundsPerCheck; ++r) {
+      cv.changed = ctx->cc_flag.p + r;
+      cc_hook_kernel<<<fb, threads, 0, s>>>(ctx->gv, cv);
+      cc_jump_kernel<<<vb, threads, 0, s>>>(ctx->gv, cv);
+    }
+    ctx->launches += 2 * kRoundsPerCheck;
     CK(cudaGetLastError());
-    int32_t changed = 0;
-    CK(cudaMemcpyAsync(&changed, ctx->cc_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    int32_t changed[kRoundsPerCheck];
+    CK(cudaMemcpyAsync(changed, ctx->cc_flag.p, sizeof changed, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (!changed) break;
+    for (int r = 0; r < kRoundsPerCheck; ++r) {
+      if (!changed[r]) {
+        converged = true;
+        break;
+      }
+      ++rounds;
+    }
   }
   cc_factor_labels_kernel<<<fb, threads, 0, s>>>(ctx->gv, cv);
   ++ctx->launches;

@@ -217,8 +217,17 @@ Numeric OptimizableFunction::evalFactors(const FactorPtrVec& fctrs, Numeric& fer
   flushAssignments();
   double sum = 0;
   if (&fctrs == &factors) {
-    check(rdisgpu_eval(ctx, 0, nullptr, &sum, nullptr), "rdisgpu_eval");
-    return sum;
+    // the all-factor streaming sweep, when no factor would be skipped: every variable assigned
+    bool all = true;
+    for (const Variable* v : variables)
+      if (!v->isAssigned()) {
+        all = false;
+        break;
+      }
+    if (all) {
+      check(rdisgpu_eval(ctx, 0, nullptr, &sum, nullptr), "rdisgpu_eval");
+      return sum;
+    }
   }
   // the reference skips factors that are not fully assigned (src/OptimizableFunction.cpp:108-112)
   std::vector<int64_t> fid;
