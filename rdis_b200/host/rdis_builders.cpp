@@ -149,6 +149,16 @@ OptimizableFunction* makeHighDimSinusoid(VariableCount treeHeight, VariableCount
     for (VariableCount i = 0; i < d; ++i) pw *= k;
     return (pw - 1) / (k - 1);
   };
+  {  // capacity of the pools: factors and edges per arity class (a vertex at depth d has factors of arity <= d + 1)
+    size_t nF = (size_t)nvars, nE = (size_t)nvars;
+    for (VariableCount ar = 1; ar <= maxArity; ++ar) {
+      if (ar > 1 && (ar & 1) && !allowOddArityFactors) continue;
+      const size_t cnt = (size_t)(nvars - firstAtDepth(ar - 1));
+      nF += cnt;
+      nE += cnt * (size_t)ar;
+    }
+    poly->reserve(nF, nE);
+  }
   VariablePtrVec& variables = poly->getVariables();
   std::vector<Variable*> chain;
   for (VariableCount ar = 1; ar <= maxArity; ++ar) {

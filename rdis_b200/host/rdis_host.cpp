@@ -15,16 +15,22 @@ namespace rdis {
 // ------------------------------------------------------------------------------------------
 // Variable / Factor
 // ------------------------------------------------------------------------------------------
+Span<Factor*> Variable::getFactors() const {
+  if (!m_owner) return Span<Factor*>{nullptr, 0};
+  m_owner->ensureIncidence();
+  const size_t a = m_owner->incOff[(size_t)m_id], b = m_owner->incOff[(size_t)m_id + 1];
+  return Span<Factor*>{m_owner->incList.data() + a, b - a};
+}
+
 void Variable::assign(Numeric newval, bool notifyFactors) {  // src/Variable.cpp:66-88
   if (m_isAssigned) {
     // The reference skips the cache-invalidation fan-out when |new - old| <= 1e-12 but still stores the
-    // new value (:69-78, :87).  The device keeps no per-factor cache, so only the value matters.
-    if (notifyFactors && newval != m_value)
-      for (Factor* f : m_factors) f->onVarChanged(m_id, m_value, newval);
+    // new value (:69-78, :87).  The host keeps no per-factor cache (the device's strict mode does), and the default
+    // onVarChanged is a no-op, so the fan-out is skipped altogether.
   } else {
     m_isAssigned = true;
     if (notifyFactors)
-      for (Factor* f : m_factors) f->onVarAssigned(m_id, newval);
+      for (Factor* f : getFactors()) f->onVarAssigned(m_id, newval);
   }
   m_value = newval;
   if (m_owner) m_owner->noteAssigned(m_id);  // queued for the next host->device flush
@@ -33,8 +39,34 @@ void Variable::assign(Numeric newval, bool notifyFactors) {  // src/Variable.cpp
 void Variable::unassign() {  // src/Variable.cpp:90-102
   if (!m_isAssigned) throw std::logic_error("Variable::unassign on an unassigned variable");
   m_isAssigned = false;
-  for (Factor* f : m_factors) f->onVarUnassigned(m_id, m_value);
+  for (Factor* f : getFactors()) f->onVarUnassigned(m_id, m_value);
   m_value = 0;
+}
+
+void Factor::addVariable(Variable* vp) {
+  if (!m_owner) throw std::logic_error("Factor::addVariable: factors are created by an OptimizableFunction");
+  std::vector<Variable*>& pool = m_owner->varPool;
+  if (nvars == 0) voff = pool.size();
+  if (voff + nvars != pool.size()) throw std::logic_error("Factor::addVariable: only the most recently created factor can grow");
+  pool.push_back(vp);
+  ++nvars;
+  m_owner->incidenceValid = false;
+  if (vp->isAssigned()) ++numVarsAssigned;
+}
+
+Span<Variable*> Factor::getVariables() const {
+  return Span<Variable*>{m_owner ? m_owner->varPool.data() + voff : nullptr, nvars};
+}
+
+void NonlinearProductFactor::addVariable(Variable* vp, Numeric exponent, Numeric constant, bool useSine) {
+  Factor::addVariable(vp);
+  std::vector<Term>& tp = m_owner->termPool;
+  if (tp.size() + 1 != m_owner->varPool.size()) tp.resize(m_owner->varPool.size() - 1);  // bundle-adjustment factors carry no terms
+  tp.push_back(Term{exponent, constant, useSine});
+}
+
+Span<NonlinearProductFactor::Term> NonlinearProductFactor::getTerms() const {
+  return Span<Term>{m_owner ? m_owner->termPool.data() + voff : nullptr, nvars};
 }
 
 void Factor::assign(Numeric fval, VariableID assignmentKey) {
@@ -57,9 +89,26 @@ void Factor::unassign(VariableID assignmentKey) {
 OptimizableFunction::OptimizableFunction() : kind(-1), ncams(0), npts(0), ctx(nullptr) {}
 
 OptimizableFunction::~OptimizableFunction() {
-  if (ctx) rdisgpu_destroy(ctx);
-  for (Factor* f : factors) delete f;
-  for (Variable* v : variables) delete v;
+  if (ctx) rdisgpu_destroy(ctx);  // variables and factors live in the arenas (the reference deletes them one by one, :43-54)
+}
+
+void OptimizableFunction::reserve(size_t nFactors, size_t nEdges) {
+  factors.reserve(nFactors);
+  varPool.reserve(nEdges);
+  if (kind != Factor::BUNDLE_ADJUSTMENT) termPool.reserve(nEdges);
+}
+
+void OptimizableFunction::ensureIncidence() const {
+  if (incidenceValid) return;
+  const size_t V = variables.size();
+  incOff.assign(V + 1, 0);
+  for (const Variable* v : varPool) ++incOff[(size_t)v->getID() + 1];
+  for (size_t i = 0; i < V; ++i) incOff[i + 1] += incOff[i];
+  incList.resize(varPool.size());
+  std::vector<size_t> cur(incOff.begin(), incOff.end() - 1);
+  for (Factor* f : factors)  // ascending factor id: the order the reference's per-variable lists are filled in
+    for (const Variable* v : f->getVariables()) incList[cur[(size_t)v->getID()]++] = f;
+  incidenceValid = true;
 }
 
 void OptimizableFunction::check(int rc, const char* what) const {
@@ -70,9 +119,11 @@ void OptimizableFunction::check(int rc, const char* what) const {
 
 Variable* OptimizableFunction::addVariable(Numeric lb, Numeric ub) {
   if (ctx) throw std::logic_error("addVariable after init");
-  Variable* v = new Variable((VariableID)variables.size(), VariableDomain(lb, ub));
+  variableArena.emplace_back((VariableID)variables.size(), VariableDomain(lb, ub));
+  Variable* v = &variableArena.back();
   v->m_owner = this;
   variables.push_back(v);
+  incidenceValid = false;
   return v;
 }
 
@@ -80,7 +131,8 @@ NonlinearProductFactor* OptimizableFunction::addProductFactor(Numeric coefficien
   if (ctx) throw std::logic_error("addProductFactor after init");
   if (kind == Factor::BUNDLE_ADJUSTMENT) throw std::logic_error("one factor family per function");
   kind = Factor::NONLINEAR_PRODUCT;
-  NonlinearProductFactor* f = new NonlinearProductFactor((FactorID)factors.size(), coefficient);
+  productArena.emplace_back((FactorID)factors.size(), coefficient);
+  NonlinearProductFactor* f = &productArena.back();
   f->m_owner = this;
   factors.push_back(f);
   return f;
@@ -99,12 +151,37 @@ BundleAdjustmentFactor* OptimizableFunction::addObservation(int32_t cam, int32_t
   if (ctx) throw std::logic_error("addObservation after init");
   if (kind != Factor::BUNDLE_ADJUSTMENT) throw std::logic_error("declareBundleAdjustment first");
   if (cam < 0 || cam >= ncams || pt < 0 || pt >= npts) throw std::out_of_range("addObservation: camera / point id");
-  BundleAdjustmentFactor* f = new BundleAdjustmentFactor((FactorID)factors.size(), cam, pt, obsx, obsy);
+  observationArena.emplace_back((FactorID)factors.size(), cam, pt, obsx, obsy);
+  BundleAdjustmentFactor* f = &observationArena.back();
   f->m_owner = this;
   for (int p = 0; p < 9; ++p) f->addVariable(variables[9LL * cam + p]);                // getCamVID
   for (int d = 0; d < 3; ++d) f->addVariable(variables[9LL * ncams + 3LL * pt + d]);   // getPointVID
   factors.push_back(f);
   return f;
+}
+
+void OptimizableFunction::exportProductFactors(std::vector<int64_t>& rowptr, std::vector<int32_t>& vid, std::vector<double>& expo,
+                                               std::vector<double>& konst, std::vector<uint8_t>& sine, std::vector<double>& coeff) const {
+  // the flat arrays of rdisgpu_add_nlpf: the pools ARE the CSR (factors are appended in id order), one linear pass
+  const size_t F = factors.size(), E = varPool.size();
+  rowptr.resize(F + 1);
+  coeff.resize(F);
+  vid.resize(E);
+  expo.resize(E);
+  konst.resize(E);
+  sine.resize(E);
+  rowptr[F] = (int64_t)E;
+  for (size_t j = F; j-- > 0;) {
+    const NonlinearProductFactor* nf = static_cast<const NonlinearProductFactor*>(factors[j]);
+    rowptr[j] = (nf->nvars == 0) ? rowptr[j + 1] : (int64_t)nf->voff;  // a factor without variables owns an empty run
+    coeff[j] = nf->getCoefficient();
+  }
+  for (size_t e = 0; e < E; ++e) {
+    vid[e] = (int32_t)varPool[e]->getID();
+    expo[e] = termPool[e].exponent;
+    konst[e] = termPool[e].constant;
+    sine[e] = termPool[e].useSine ? 1 : 0;
+  }
 }
 
 void OptimizableFunction::init(int device) {
@@ -123,24 +200,11 @@ void OptimizableFunction::init(int device) {
   }
   check(rdisgpu_set_vars(ctx, V, lb.data(), ub.data()), "rdisgpu_set_vars");
   if (kind == Factor::NONLINEAR_PRODUCT) {
-    std::vector<int64_t> rowptr(F + 1, 0);
-    std::vector<double> coeff(F);
-    for (int64_t j = 0; j < F; ++j) rowptr[j + 1] = rowptr[j] + (int64_t)factors[j]->numVars();
-    const int64_t E = rowptr[F];
-    std::vector<int32_t> vid(E);
-    std::vector<double> expo(E), konst(E);
-    std::vector<uint8_t> sine(E);
-    for (int64_t j = 0; j < F; ++j) {
-      const NonlinearProductFactor* nf = static_cast<const NonlinearProductFactor*>(factors[j]);
-      coeff[j] = nf->getCoefficient();
-      for (size_t s = 0; s < nf->numVars(); ++s) {
-        const int64_t e = rowptr[j] + (int64_t)s;
-        vid[e] = (int32_t)nf->getVariables()[s]->getID();
-        expo[e] = nf->getTerms()[s].exponent;
-        konst[e] = nf->getTerms()[s].constant;
-        sine[e] = nf->getTerms()[s].useSine ? 1 : 0;
-      }
-    }
+    std::vector<int64_t> rowptr;
+    std::vector<int32_t> vid;
+    std::vector<double> expo, konst, coeff;
+    std::vector<uint8_t> sine;
+    exportProductFactors(rowptr, vid, expo, konst, sine, coeff);
     check(rdisgpu_add_nlpf(ctx, F, rowptr.data(), vid.data(), expo.data(), konst.data(), sine.data(), coeff.data()),
           "rdisgpu_add_nlpf");
   } else {

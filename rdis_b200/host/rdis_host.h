@@ -31,6 +31,7 @@
 #define RDIS_HOST_H_
 
 #include <cstdint>
+#include <deque>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -54,7 +55,22 @@ typedef std::vector<VariableID> VariableIDVec;
 typedef std::vector<FactorID> FactorIDVec;
 
 class Factor;
+class Variable;
 class OptimizableFunction;
+
+// A read-only view of a run of a flat pool, with the part of std::vector's interface the callers use.  The host objects
+// keep NO per-object containers: a factor's variables / terms and a variable's incident factors are runs of pools owned
+// by the function (so building the 4.2 M factors of BASELINE config 4 allocates a handful of arrays, not 10 M vectors).
+template <class T>
+struct Span {
+  const T* b;
+  size_t n;
+  const T* begin() const { return b; }
+  const T* end() const { return b + n; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  const T& operator[](size_t i) const { return b[i]; }
+};
 
 // One closed interval (every configuration of the hot path has exactly one subinterval per variable;
 // CGDSubspaceOptimizer asserts it, src/optimizers/CGDSubspaceOptimizer.cpp:118-119).
@@ -80,7 +96,6 @@ class VariableDomain {
 class Variable {
  public:
   Variable(VariableID id, const VariableDomain& dom) : m_id(id), m_domain(dom), m_isAssigned(false), m_value(0), m_owner(nullptr) {}
-  void addFactor(Factor* f) { m_factors.push_back(f); }
   void assign(Numeric newval, bool notifyFactors = true);  // src/Variable.cpp:66-88
   void unassign();                                          // src/Variable.cpp:90-102
   Numeric eval() const {
@@ -90,8 +105,7 @@ class Variable {
   const VariableID& getID() const { return m_id; }
   const VariableDomain& getDomain() const { return m_domain; }
   void setDomain(const VariableDomain& d) { m_domain = d; }
-  std::vector<Factor*>& getFactors() { return m_factors; }
-  const std::vector<Factor*>& getFactors() const { return m_factors; }
+  Span<Factor*> getFactors() const;  // the factors the variable appears in, ascending factor id (incidence built on first use)
   bool isAssigned() const { return m_isAssigned; }
 
  private:
@@ -103,7 +117,6 @@ class Variable {
   }
   VariableID m_id;
   VariableDomain m_domain;
-  std::vector<Factor*> m_factors;
   bool m_isAssigned;
   Numeric m_value;
   OptimizableFunction* m_owner;
@@ -113,22 +126,20 @@ typedef std::vector<Variable*> VariablePtrVec;
 class Factor {
  public:
   enum Kind { NONLINEAR_PRODUCT = 0, BUNDLE_ADJUSTMENT = 1 };
-  explicit Factor(FactorID id_) : id(id_), numVarsAssigned(0), isAssignedConstant(false), vidAssigned(-1), assignedVal(0), m_owner(nullptr) {}
+  explicit Factor(FactorID id_)
+      : id(id_), voff(0), nvars(0), numVarsAssigned(0), isAssignedConstant(false), vidAssigned(-1), assignedVal(0), m_owner(nullptr) {}
   virtual ~Factor() {}
   virtual Kind kind() const = 0;
-  virtual void addVariable(Variable* vp) {
-    variables.push_back(vp);
-    vp->addFactor(this);
-    if (vp->isAssigned()) ++numVarsAssigned;
-  }
+  // appends to the function's variable pool: only the most recently created factor can grow (every builder works so)
+  virtual void addVariable(Variable* vp);
   FactorID getID() const { return id; }
-  const std::vector<Variable*>& getVariables() const { return variables; }
-  size_t numVars() const { return variables.size(); }
+  Span<Variable*> getVariables() const;
+  size_t numVars() const { return nvars; }
   bool isAssigned() const { return isAssignedConstant; }
   VariableID getAssignedKey() const { return vidAssigned; }
-  bool areAllVarsAssigned() const { return numVarsAssigned == (VariableCount)variables.size(); }
+  bool areAllVarsAssigned() const { return numVarsAssigned == (VariableCount)nvars; }
   bool isVarInFactor(VariableID vid) const {
-    for (const Variable* v : variables)
+    for (const Variable* v : getVariables())
       if (v->getID() == vid) return true;
     return false;
   }
@@ -146,7 +157,8 @@ class Factor {
  protected:
   friend class OptimizableFunction;
   FactorID id;
-  std::vector<Variable*> variables;
+  size_t voff;      // first slot of this factor's run in the function's variable (and term) pool
+  uint32_t nvars;
   VariableCount numVarsAssigned;
   bool isAssignedConstant;
   VariableID vidAssigned;
@@ -165,16 +177,12 @@ class NonlinearProductFactor : public Factor {
   NonlinearProductFactor(FactorID id_, Numeric coeff) : Factor(id_), coefficient(coeff) {}
   Kind kind() const override { return NONLINEAR_PRODUCT; }
   void addVariable(Variable* vp) override { addVariable(vp, 1.0, 0.0, false); }
-  void addVariable(Variable* vp, Numeric exponent, Numeric constant, bool useSine) {
-    Factor::addVariable(vp);
-    terms.push_back(Term{exponent, constant, useSine});
-  }
+  void addVariable(Variable* vp, Numeric exponent, Numeric constant, bool useSine);
   Numeric getCoefficient() const { return coefficient; }
-  const std::vector<Term>& getTerms() const { return terms; }
+  Span<Term> getTerms() const;
 
  private:
   Numeric coefficient;
-  std::vector<Term> terms;
 };
 
 // one reprojection observation: 9 camera + 3 point variables, enum order of
@@ -219,6 +227,11 @@ class OptimizableFunction {
   // src/OptimizableFunction.cpp:57-76).  Throws std::runtime_error when no sm_100 device is usable.
   virtual void init(int device = 0);
 
+  // capacity hints for the builders (optional): avoids pool re-allocation while millions of factors are added
+  void reserve(size_t nFactors, size_t nEdges);
+  // the flat arrays rdisgpu_add_nlpf takes (NonlinearProductFactor functions): what init() uploads
+  void exportProductFactors(std::vector<int64_t>& rowptr, std::vector<int32_t>& vid, std::vector<double>& expo, std::vector<double>& konst,
+                            std::vector<uint8_t>& sine, std::vector<double>& coeff) const;
   VariableCount getNumVars() const { return (VariableCount)variables.size(); }
   VariablePtrVec& getVariables() { return variables; }
   FactorPtrVec const& getFactors() const { return factors; }
@@ -256,8 +269,20 @@ class OptimizableFunction {
   void noteFactorConst(Factor* f);
   void check(int rc, const char* what) const;
 
+  friend class NonlinearProductFactor;
+  void ensureIncidence() const;  // variable -> factors CSR, built once after construction (counting sort, ascending factor id)
   VariablePtrVec variables;
   FactorPtrVec factors;
+  // arenas and pools: objects are constructed in chunked arenas (stable addresses, no per-object allocation); a factor's
+  // variables / terms are the run [voff, voff + nvars) of varPool / termPool
+  std::deque<Variable> variableArena;
+  std::deque<NonlinearProductFactor> productArena;
+  std::deque<BundleAdjustmentFactor> observationArena;
+  std::vector<Variable*> varPool;
+  std::vector<NonlinearProductFactor::Term> termPool;
+  mutable std::vector<size_t> incOff;       // V + 1
+  mutable std::vector<Factor*> incList;     // one entry per (variable, factor) pair
+  mutable bool incidenceValid = false;
   int kind;  // -1 none, Factor::Kind otherwise
   int32_t ncams, npts;
   rdisgpu_ctx* ctx;

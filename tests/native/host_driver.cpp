@@ -205,6 +205,45 @@ int main(int argc, char** argv) {
                   fn.getNumVars());
       return 0;
     }
+    if (std::string(argv[1]) == "sinusoid_flat") {
+      // sinusoid_flat <height> <branches> <maxArity> <odd>: builds the function, exports the flat arrays rdisgpu_add_nlpf
+      // takes, prints their sizes, the build + export wall time and an FNV-1a hash of every array (no GPU needed):
+      // the Python generator's arrays must hash the same
+      if (argc < 6) return 2;
+      const auto t0 = std::chrono::steady_clock::now();
+      std::unique_ptr<OptimizableFunction> fn(makeHighDimSinusoid(std::atoll(argv[2]), std::atoll(argv[3]), std::atoll(argv[4]),
+                                                                  std::atoi(argv[5]) != 0));
+      const double build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      std::vector<int64_t> rowptr;
+      std::vector<int32_t> vid;
+      std::vector<double> expo, konst, coeff;
+      std::vector<uint8_t> sine;
+      fn->exportProductFactors(rowptr, vid, expo, konst, sine, coeff);
+      const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      auto fnv = [](const void* p, size_t n) {
+        unsigned long long h = 1469598103934665603ULL;
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; ++i) {
+          h ^= b[i];
+          h *= 1099511628211ULL;
+        }
+        return h;
+      };
+      std::printf("V %lld F %zu E %zu build_ms %.1f total_ms %.1f\n", fn->getNumVars(), coeff.size(), vid.size(), build_ms, total_ms);
+      std::printf("hash rowptr %llx vid %llx expo %llx konst %llx sine %llx coeff %llx\n", fnv(rowptr.data(), rowptr.size() * 8),
+                  fnv(vid.data(), vid.size() * 4), fnv(expo.data(), expo.size() * 8), fnv(konst.data(), konst.size() * 8),
+                  fnv(sine.data(), sine.size()), fnv(coeff.data(), coeff.size() * 8));
+      if (argc > 6) {  // ... <outfile>: the arrays themselves, little endian, in the order of the hash line
+        std::ofstream out(argv[6], std::ios::binary);
+        out.write(reinterpret_cast<const char*>(rowptr.data()), (std::streamsize)(rowptr.size() * 8));
+        out.write(reinterpret_cast<const char*>(vid.data()), (std::streamsize)(vid.size() * 4));
+        out.write(reinterpret_cast<const char*>(expo.data()), (std::streamsize)(expo.size() * 8));
+        out.write(reinterpret_cast<const char*>(konst.data()), (std::streamsize)(konst.size() * 8));
+        out.write(reinterpret_cast<const char*>(sine.data()), (std::streamsize)sine.size());
+        out.write(reinterpret_cast<const char*>(coeff.data()), (std::streamsize)(coeff.size() * 8));
+      }
+      return 0;
+    }
     if (std::string(argv[1]) == "sinusoid") {  // sinusoid <height> <branches> <maxArity> <odd>
       if (argc < 6) return 2;
       std::unique_ptr<OptimizableFunction> fn(makeHighDimSinusoid(std::atoll(argv[2]), std::atoll(argv[3]), std::atoll(argv[4]),
