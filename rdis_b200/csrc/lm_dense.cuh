@@ -10,11 +10,11 @@
 //                       variable's incident rows in ascending factor order, lanes over the row's entries — no atomics,
 //                       a fixed accumulation order
 //   (A + mu I) dp = g   blocked right-looking Cholesky, block width 64:
-//       lm_potrf_kernel   the 64 x 64 diagonal block in shared memory
-//       lm_trsm_kernel    the panel below it, one thread per row against the block in shared memory
-//       lm_syrk_kernel    the trailing update C -= P P^T: the ONE genuinely dense contraction of the path (2/3 m^3 of
-//                         the factorisation's flops) — on the FP64 tensor cores: mma.sync.m8n8k4.f64 (SASS DMMA),
-//                         64 x 64 tiles, 4 warps x (4 x 4) accumulator fragments, panels staged in shared memory
+//       lm_potrf_kernel   the 64 x 64 diagonal block in shared memory, and its inverse
+//       lm_tile_kernel    the two dense contractions of the factorisation on the FP64 tensor cores (mma.sync.m8n8k4.f64,
+//                         SASS DMMA; 64 x 64 tiles, 4 warps x (4 x 4) accumulator fragments, panels staged in shared
+//                         memory): the panel solve L21 = A21 L11^-T and the trailing update C -= L21 L21^T (2/3 m^3 of
+//                         the factorisation's flops)
 //       lm_trsv_kernel    forward and back substitution, one CTA
 //   control flow        levmar's dlevmar_der (stop codes 1..7, mu0 = tau max diag, gain ratio, nu doubling) on the host:
 //                       a handful of scalars come back per iteration, which is noise against a 4 754^3 / 3 factorisation
@@ -183,15 +183,23 @@ __global__ void lm_augment_kernel(const double* A, double* Lm, int m, double mu)
 }
 
 // ---- blocked Cholesky ----------------------------------------------------------------------------------
-// diagonal block [kb, kb+nb) in shared memory; *flag set when a pivot is not positive
-__global__ void __launch_bounds__(kLmNB) lm_potrf_kernel(double* Lm, int m, int kb, int* flag) {
+// Diagonal block [kb, kb+nb) in shared memory: factor it, and invert the factor (Linv = L11^-1, 64 x 64 row-major,
+// zero above the diagonal and past nb) so that the panel solve below becomes a dense contraction.  *flag is set when a
+// pivot is not positive.
+__global__ void __launch_bounds__(256) lm_potrf_kernel(double* Lm, int m, int kb, double* Linv, int* flag) {
+  // one 64 x 65 array holds both triangles: a[r][c], c <= r, is the factor; the strictly lower part of its inverse is kept
+  // transposed in the strictly upper part (inverse(r, c) at a[c][r], c < r), its diagonal in dinv
   __shared__ double a[kLmNB][kLmNB + 1];
+  __shared__ double dinv[kLmNB];
   const int nb = min(kLmNB, m - kb), t = threadIdx.x;
-  if (t < nb)
-    for (int c = 0; c <= t; ++c) a[t][c] = Lm[(size_t)(kb + t) * m + kb + c];
+  for (int p = t; p < kLmNB * kLmNB; p += blockDim.x) {
+    const int r = p / kLmNB, c = p % kLmNB;
+    a[r][c] = (r < nb && c <= r) ? Lm[(size_t)(kb + r) * m + kb + c] : 0.0;
+  }
+  if (t < kLmNB) dinv[t] = 0.0;
   __syncthreads();
   for (int j = 0; j < nb; ++j) {
-    if (t == j) {
+    if (t == 0) {
       const double d = a[j][j];
       if (!(d > 0.0)) *flag = 1;
       a[j][j] = sqrt(d);
@@ -199,46 +207,61 @@ __global__ void __launch_bounds__(kLmNB) lm_potrf_kernel(double* Lm, int m, int 
     __syncthreads();
     if (t > j && t < nb) a[t][j] = a[t][j] / a[j][j];
     __syncthreads();
-    if (t > j && t < nb)
-      for (int c = j + 1; c <= t; ++c) a[t][c] -= a[t][j] * a[c][j];
+    const int w = nb - j - 1;  // the trailing (r, c) pairs, j < c <= r < nb
+    for (int p = t; p < w * w; p += blockDim.x) {
+      const int r = j + 1 + p / w, c = j + 1 + p % w;
+      if (c <= r) a[r][c] -= a[r][j] * a[c][j];
+    }
     __syncthreads();
   }
-  if (t < nb)
-    for (int c = 0; c <= t; ++c) Lm[(size_t)(kb + t) * m + kb + c] = a[t][c];
-}
-
-// panel below the diagonal block: row r of L21 = row r of A21 times L11^-T (forward substitution along the row)
-__global__ void __launch_bounds__(128) lm_trsm_kernel(double* Lm, int m, int kb) {
-  __shared__ double l[kLmNB][kLmNB + 1];
-  const int nb = min(kLmNB, m - kb);
-  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
-    const int r = t / nb, c = t % nb;
-    l[r][c] = (c <= r) ? Lm[(size_t)(kb + r) * m + kb + c] : 0.0;
+  for (int p = t; p < nb * nb; p += blockDim.x) {
+    const int r = p / nb, c = p % nb;
+    if (c <= r) Lm[(size_t)(kb + r) * m + kb + c] = a[r][c];
+  }
+  // inverse of the lower-triangular factor, column c by forward substitution, four lanes (one warp quarter) per column:
+  // x_c = 1 / l_cc, x_r = -(sum_{k=c}^{r-1} l_rk x_k) / l_rr.  Column c is touched by its own four lanes only.
+  {
+    const int c = t >> 2, q = t & 3;
+    if (q == 0 && c < nb) dinv[c] = 1.0 / a[c][c];
+    __syncwarp();
+    for (int r = 1; r < nb; ++r) {
+      double s = 0.0;
+      if (c < r && c < nb)
+        for (int k = c + q; k < r; k += 4) s += a[r][k] * ((k == c) ? dinv[c] : a[c][k]);  // inverse(k, c)
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (q == 0 && c < r && c < nb) a[c][r] = -s / a[r][r];
+      __syncwarp();
+    }
   }
   __syncthreads();
-  const int r = kb + nb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= m) return;
-  double* row = Lm + (size_t)r * m + kb;
-  for (int j = 0; j < nb; ++j) {
-    double s = row[j];
-    for (int k = 0; k < j; ++k) s -= row[k] * l[j][k];
-    row[j] = s / l[j][j];
+  for (int p = t; p < kLmNB * kLmNB; p += blockDim.x) {
+    const int r = p / kLmNB, c = p % kLmNB;
+    Linv[p] = (r >= nb || c > r) ? 0.0 : ((c == r) ? dinv[r] : a[c][r]);
   }
 }
 
-// trailing update of the lower triangle: C[i][j] -= sum_k P[i][k] P[j][k], P = L21 (columns [kb, kb+nb)), on the FP64
-// tensor cores.  One CTA per 64 x 64 tile (ti >= tj), 4 warps, warp (wi, wj) owns a 32 x 32 quarter = 4 x 4 fragments
-// of mma.m8n8k4: A fragment = P rows (thread T: row T/4, k T%4), B fragment (col-major 4 x 8) = the other panel's rows
-// read the same way, C fragment: row T/4, columns 2 (T%4), 2 (T%4) + 1.
+// C = P Q^T on the FP64 tensor cores, one CTA per 64 x 64 tile, 4 warps, warp (wi, wj) owns a 32 x 32 quarter = 4 x 4
+// fragments of mma.sync.m8n8k4.f64 (SASS DMMA): A fragment = P rows (thread T: row T/4, k T%4), B fragment (col-major
+// 4 x 8) = Q rows read the same way, C fragment: row T/4, columns 2 (T%4), 2 (T%4) + 1.  Panels are staged in shared memory
+// 32 columns at a time.  Two uses, the two dense contractions of the factorisation:
+//   kPanelSolve   L21 = A21 L11^-T: P = the 64 rows of A21 of this tile (read completely before anything is written),
+//                 Q = Linv; the tile OVERWRITES A21.                                  grid (row tiles, 1)
+//   kTrailing     C -= L21 L21^T on the lower triangle of the trailing matrix: P, Q = row tiles ti >= tj of L21.
+//                                                                                     grid (row tiles, row tiles)
+enum LmTileOp : int { kPanelSolve = 0, kTrailing = 1 };
+
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(128) lm_syrk_kernel(double* Lm, int m, int kb, int nb) {
+template <int kOp>
+__global__ void __launch_bounds__(128) lm_tile_kernel(double* Lm, int m, int kb, int nb, const double* __restrict__ Linv) {
   const int ti = blockIdx.x, tj = blockIdx.y;
-  if (tj > ti) return;
+  if (kOp == kTrailing && tj > ti) return;
   __shared__ double Ps[kLmNB][kLmTileLd], Qs[kLmNB][kLmTileLd];  // half a panel (32 columns) at a time: 36 KB
-  const int r0 = kb + nb + ti * kLmNB, c0 = kb + nb + tj * kLmNB;  // first row of the tile's row / column range in L
+  const int r0 = kb + nb + ti * kLmNB;                             // first row of this tile's P rows in L
+  const int c0 = (kOp == kTrailing) ? kb + nb + tj * kLmNB : kb;   // kTrailing: first row of the Q rows; kPanelSolve: first output column
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wi = warp >> 1, wj = warp & 1;
   const int fr = lane >> 2, fk = lane & 3;
@@ -252,7 +275,8 @@ __global__ void __launch_bounds__(128) lm_syrk_kernel(double* Lm, int m, int kb,
     for (int t = threadIdx.x; t < kLmNB * kLmKH; t += blockDim.x) {
       const int r = t / kLmKH, k = t % kLmKH;
       Ps[r][k] = (r0 + r < m && kh + k < nb) ? Lm[(size_t)(r0 + r) * m + kb + kh + k] : 0.0;
-      Qs[r][k] = (c0 + r < m && kh + k < nb) ? Lm[(size_t)(c0 + r) * m + kb + kh + k] : 0.0;
+      if (kOp == kTrailing) Qs[r][k] = (c0 + r < m && kh + k < nb) ? Lm[(size_t)(c0 + r) * m + kb + kh + k] : 0.0;
+      else Qs[r][k] = Linv[r * kLmNB + kh + k];
     }
     __syncthreads();
 #pragma unroll
@@ -274,10 +298,15 @@ __global__ void __launch_bounds__(128) lm_syrk_kernel(double* Lm, int m, int kb,
     if (row >= m) continue;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int col = c0 + wj * 32 + b * 8 + 2 * fk;
-      double* dst = Lm + (size_t)row * m + col;
-      if (col <= row && col < m) dst[0] -= acc[a][b][0];
-      if (col + 1 <= row && col + 1 < m) dst[1] -= acc[a][b][1];
+      const int cl = wj * 32 + b * 8 + 2 * fk;  // column inside the tile
+      double* dst = Lm + (size_t)row * m + c0 + cl;
+      if (kOp == kTrailing) {
+        if (c0 + cl <= row && c0 + cl < m) dst[0] -= acc[a][b][0];
+        if (c0 + cl + 1 <= row && c0 + cl + 1 < m) dst[1] -= acc[a][b][1];
+      } else {
+        if (cl < nb) dst[0] = acc[a][b][0];
+        if (cl + 1 < nb) dst[1] = acc[a][b][1];
+      }
     }
   }
 }

@@ -1622,7 +1622,7 @@ static int solve_lm_dense(rdisgpu_ctx* ctx, rdisgpu_batch* b, int64_t pidx, cons
   CK(ctx->lmd_e.ensure((size_t)nf));
   CK(ctx->lmd_hx.ensure((size_t)nf));
   CK(ctx->lmd_vec.ensure((size_t)m * 7));   // g | p | pDp | dp | y | diag | spare
-  CK(ctx->lmd_scal.ensure(4096));
+  CK(ctx->lmd_scal.ensure(4096 + kLmNB * kLmNB));
   CK(ctx->lmd_flag.ensure(1));
   const size_t nidx = (size_t)nf + 1 + (size_t)nent + (size_t)m + 1 + 2 * ient.size() + 8;
   CK(ctx->lmd_idx.ensure(nidx));
@@ -1646,6 +1646,7 @@ static int solve_lm_dense(rdisgpu_ctx* ctx, rdisgpu_batch* b, int64_t pidx, cons
   double* y = dp + m;
   double* diag = y + m;
   double* scal = ctx->lmd_scal.p;
+  double* linv = scal + 4096;  // inverse of the current diagonal block
   LmDenseView L;
   L.m = m; L.nf = nf;
   L.fids = b->d_fids + D.fac_off;
@@ -1705,12 +1706,12 @@ static int solve_lm_dense(rdisgpu_ctx* ctx, rdisgpu_batch* b, int64_t pidx, cons
       ++launches;
       for (int kb = 0; kb < m; kb += kLmNB) {
         const int nb = std::min(kLmNB, m - kb), rest = m - kb - nb;
-        lm_potrf_kernel<<<1, kLmNB, 0, s>>>(ctx->lmd_L.p, m, kb, ctx->lmd_flag.p);
+        lm_potrf_kernel<<<1, 256, 0, s>>>(ctx->lmd_L.p, m, kb, linv, ctx->lmd_flag.p);
         ++launches;
         if (rest > 0) {
-          lm_trsm_kernel<<<(rest + 127) / 128, 128, 0, s>>>(ctx->lmd_L.p, m, kb);
           const int nt = (rest + kLmNB - 1) / kLmNB;
-          lm_syrk_kernel<<<dim3((unsigned)nt, (unsigned)nt), 128, 0, s>>>(ctx->lmd_L.p, m, kb, nb);
+          lm_tile_kernel<kPanelSolve><<<dim3((unsigned)nt, 1), 128, 0, s>>>(ctx->lmd_L.p, m, kb, nb, linv);
+          lm_tile_kernel<kTrailing><<<dim3((unsigned)nt, (unsigned)nt), 128, 0, s>>>(ctx->lmd_L.p, m, kb, nb, linv);
           launches += 2;
         }
       }
