@@ -528,7 +528,7 @@ def lm_wave(ctx, spec, pts, cams, x0, torch):
         r = ctx.solve_lm(blk, xs, maxit, FTOL)
         t = time.perf_counter() - t0
         res[label] = {"nv": int(len(blk.vids)), "nf": int(len(blk.fids)), "host_call_ms": t * 1e3, "f_init": float(r["f_init"][0]), "f_end": float(r["f_end"][0]),
-                      "iters": int(r["iters"][0]), "stop": int(r["stop"][0]), "func_evals": int(r["n_feval"][0]), "jac_evals": int(r["n_geval"][0]),
+                      "iters": int(r["iters"][0]), "stop": int(r["stop"][0]), "func_evals": int(r["n_feval"][0]), "jac_evals": int(r["n_jeval"][0]),
                       "ms_per_iteration": t * 1e3 / max(int(r["iters"][0]), 1),
                       "kernels": "lm_rows / lm_assemble / lm_potrf / lm_trsm / lm_syrk (DMMA) / lm_trsv; the reference hands levmar a dense "
                                  "11950 x 4755 Jacobian (454 MB) and an O(m^3) LU per damping trial on one core"}

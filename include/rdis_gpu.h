@@ -48,8 +48,10 @@ enum {
   RDISGPU_DONE_MAXITERS = 3,   /* "Too many iterations in frprmn", minimize_nrc.h:690 (normal)  */
   RDISGPU_DONE_DBRENT_ITMAX = 4, /* "Too many iterations in routine dbrent", minimize_nrc.h:403 */
   RDISGPU_DONE_EMPTY = 5,      /* no factors: returns 0, delta 0, x untouched (CGDSubspaceOptimizer.cpp:26-29) */
-  RDISGPU_DONE_NONFINITE = 6,  /* a non-finite line-search abscissa was produced; start point restored        */
-  RDISGPU_DONE_BRACKET_CAP = 7 /* bracket expansion exceeded the device safety cap (reference would loop)     */
+  RDISGPU_DONE_NONFINITE = 6,  /* a non-finite line-search abscissa was produced (the reference asserts, CGD.cpp:172): p and
+                                  fret of the last completed line search are kept, as after the reference's own throws */
+  RDISGPU_DONE_BRACKET_CAP = 7 /* bracket expansion exceeded the device safety cap of 2000 rounds (the reference's loop is
+                                  unbounded, minimize_nrc.h:101); same commit rule                                  */
 };
 
 /* One SubspaceOptimizer::optimize call (src/SubspaceOptimizer.h:37-39):
@@ -83,7 +85,15 @@ RDISGPU_API int rdisgpu_synchronize(rdisgpu_ctx* ctx);
 /* Tuning / test switches.  "generic_only" != 0: batches created afterwards bypass the bundle-adjustment
  * block kernels and run every problem through the generic tile / CTA / grid kernels.  "resident_threads" = 256 | 1024:
  * CTA width of the shared-memory resident NonlinearProductFactor component kernel (1024 = default; 256 reproduces the
- * generic CTA kernel's reduction order and therefore its results to the bit — used by the equality test). */
+ * generic CTA kernel's reduction order and therefore its results to the bit — used by the equality test).
+ * "strict" != 0 (needs a finalized context): every subspace solve runs through the strict kernel, which reproduces
+ * CGDSubspaceOptimizer::optimize (src/optimizers/CGDSubspaceOptimizer.cpp:19-98) operation for operation — the reference's
+ * summation orders (src/OptimizableFunction.cpp:108-132, src/State.h:157-194, minimize_nrc.h:440-446,668-673), true
+ * divisions, the per-factor value cache with Variable::assign's 1e-12 change filter (src/Variable.cpp:66-88,
+ * src/Factor.cpp:110-119; the cache persists across calls and rdisgpu_set_x applies the filter) and the reference's
+ * evaluation sequence — and is bit-identical to the CPU restatement built with the device's sin / cos.
+ * "camera_cluster" = 0..8: pins the thread-block-cluster width of the camera-block kernel (0 = choose; results do not
+ * depend on it). */
 RDISGPU_API int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value);
 
 /* ---- function definition (replaces the OptimizableFunction / Factor object graph) ------ */
