@@ -309,7 +309,10 @@ struct PointWarpTask {
   int32_t count;
 };
 
-__global__ void __launch_bounds__(32) solve_ba_points_kernel(GraphView Gv, BatchView B, const int32_t* order,
+#ifndef RDIS_PT_MIN_CTAS
+#define RDIS_PT_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(32, RDIS_PT_MIN_CTAS) solve_ba_points_kernel(GraphView Gv, BatchView B, const int32_t* order,
                                                              const PointWarpTask* tasks, int maxiters, double ftol) {
   const PointWarpTask t = tasks[blockIdx.x];
   const int slot = (int)threadIdx.x >> t.lg;
@@ -563,7 +566,11 @@ __global__ void __maxnreg__(RDIS_CAM_MAXREG) solve_ba_cameras_kernel(GraphView G
       const bool along = (kind == REQ_VALUE) || (kind == REQ_VALUE_SLOPE);
       const int N = along ? 2 : kCamRedWidth;
       if (lane == 0) mbar_arrive_expect_tx(&sh.mbar[flip], (uint32_t)(rows * N * 8));
+#ifdef RDIS_CAM_PLAIN_WAIT
+      mbar_wait(&sh.mbar[flip], (phase >> flip) & 1u);
+#else
       mbar_wait_cluster(&sh.mbar[flip], (phase >> flip) & 1u);
+#endif
       SCPROF(1);  // workers' evaluation + flight
       phase ^= (1u << flip);
       // Fold of the cluster's warp partials in an order that is a function of the row index (= observation index / 32)

@@ -996,10 +996,18 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
     ctx->mark_epoch = 1;
   }
   const int32_t epoch = ctx->mark_epoch;
+  const int32_t first_point_var = 9 * ctx->ncams;  // bundle adjustment: which sides own variables in this batch
+  bool owns_cam_vars = false, owns_pt_vars = false;
   for (int64_t p = 0; p < nprobs; ++p) {
     const ProblemDesc& D = b->h_probs[p];
     const int32_t* pvid = pv.vid(p);
     const int64_t* pfid = pv.fid(p);
+    if (D.nv > 0 && ctx->kind == KIND_BA) {
+      owns_cam_vars = owns_cam_vars || pvid[0] < first_point_var;       // ids are checked below; a mixed problem sets both
+      owns_pt_vars = owns_pt_vars || pvid[D.nv - 1] >= first_point_var;
+      if (!(owns_cam_vars && owns_pt_vars))
+        for (int64_t j = 0; j < D.nv; ++j) (pvid[j] < first_point_var ? owns_cam_vars : owns_pt_vars) = true;
+    }
     for (int64_t j = 0; j < D.nv; ++j) {
       const int32_t v = pvid[j];
       if (v < 0 || v >= ctx->V) return ctx->fail(RDISGPU_ERR_ARG, "batch: variable id out of range");
@@ -1029,9 +1037,9 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
         const ProblemDesc& D = b->h_probs[p];
         const int32_t* pf = fids + D.fac_off;
         for (int k = 0; k < D.nf; ++k) {
-          if (ba) {
+          if (ba) {  // only the sides that own variables in this batch can hold a foreign owner
             const int32_t cb = 9 * ctx->h_cam[pf[k]], qb = pbase + 3 * ctx->h_pt[pf[k]];
-            for (int sl = 0; sl < 12; ++sl) {
+            for (int sl = owns_cam_vars ? 0 : 9; sl < (owns_pt_vars ? 12 : 9); ++sl) {
               const int32_t v = (sl < 9) ? cb + sl : qb + (sl - 9);
               if (ctx->vmark[v] == epoch && ctx->vowner[v] != (int32_t)p) foreign.store(1, std::memory_order_relaxed);
             }
