@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas)
   // ---- commit (CGD.cpp:61-89) ----
   double fret = m.fret;
   bool restore = (fret > f_init);
-  if (m.status == ST_NONFINITE || m.status == ST_BRACKET_CAP) restore = true;
+  // the safety exits keep p / fret of the last completed line search, like the reference's own throws (CGD.cpp:41-61)
   if (restore) fret = f_init;
   for (int j = tid; j < nv; j += T) {
     const int32_t vid = vids[j];

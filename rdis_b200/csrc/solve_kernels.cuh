@@ -345,7 +345,7 @@ __device__ void solve_problem(const GraphView& G, Grp& grp, const BatchView& B, 
   // ---- commit (CGD.cpp:61-89) --------------------------------------------------------------
   double fret = m.fret;
   bool restore = (fret > f_init);
-  if (m.status == ST_NONFINITE || m.status == ST_BRACKET_CAP) restore = true;
+  // the safety exits keep p / fret of the last completed line search, like the reference's own throws (CGD.cpp:41-61)
   if (restore) fret = f_init;
   for (int j = grp.rank(); j < nv; j += grp.size()) {
     const int32_t vid = vids[j];

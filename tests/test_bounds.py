@@ -263,3 +263,36 @@ def test_component_optimum_lies_inside_its_unassigned_bounds(oracle_mod):
     o = orc.solve_cgd_batch(pts.var_off, pts.vids, pts.fac_off, pts.fids, ba["x0"][pts.vids], 25, 3e-8)
     for k, (lo, hi) in enumerate(bounds):
         assert lo - tol * max(1.0, abs(lo)) <= o["f_end"][k] <= hi + tol * max(1.0, abs(hi)), (k, lo, o["f_end"][k], hi)
+
+
+@pytest.mark.gpu
+def test_list_bounds_on_device_match_the_per_list_calls(built_lib, oracle_mod):
+    """rdisgpu_bounds_lists (the unassigned bounds of EVERY child of a decomposition in one launch, each list's interval
+    sum folded on the device in list order) against one rdisgpu_bounds call per list (bit for bit: same per-factor
+    arithmetic, same fold order) and against the oracle (1e-12): sinusoid subtrees and bundle-adjustment point blocks,
+    lists shorter and longer than a warp, an empty list."""
+    from rdis_b200 import Context, problems as P
+    tree = P.sinusoid(8, 2, 4)
+    x0 = P.random_start(tree, 3)
+    ps = P.sinusoid_subtree_problems(tree, 3)
+    ctx = Context.from_spec(tree); ctx.set_x(x0)
+    orc = oracle_mod.OracleFunction.from_spec(tree); orc.set_x(x0)
+    assigned = np.ones(tree["V"], np.uint8); assigned[ps.vids] = 0
+    off = np.concatenate([ps.fac_off, [ps.fac_off[-1]]])            # + one empty list at the end
+    sums = ctx.bounds_lists(assigned, off, ps.fids)
+    assert sums.shape == (ps.n + 1, 2) and sums[-1, 0] == 0.0 and sums[-1, 1] == 0.0
+    for k in range(ps.n):
+        fids = ps.fids[ps.fac_off[k]:ps.fac_off[k + 1]]
+        _, _, tot = ctx.bounds(assigned, fids)
+        assert sums[k, 0] == tot[0] and sums[k, 1] == tot[1]
+        wlo, whi = orc.bounds(assigned, fids)[2]
+        assert abs(sums[k, 0] - wlo) <= 1e-12 * max(1.0, abs(wlo)) and abs(sums[k, 1] - whi) <= 1e-12 * max(1.0, abs(whi))
+    ba = P.ba_synthetic(ncams=4, npts=60, nobs=230, seed=6)
+    ba = dict(ba); w = 0.03 * np.maximum(np.abs(ba["x0"]), 0.05); ba["lb"] = ba["x0"] - w; ba["ub"] = ba["x0"] + w
+    pts = P.ba_point_problems(ba)
+    bctx = Context.from_spec(ba); bctx.set_x(ba["x0"])
+    assigned = np.ones(ba["V"], np.uint8); assigned[pts.vids] = 0
+    sums = bctx.bounds_lists(assigned, pts.fac_off, pts.fids)
+    for k in range(0, pts.n, 7):
+        _, _, tot = bctx.bounds(assigned, pts.fids[pts.fac_off[k]:pts.fac_off[k + 1]])
+        assert sums[k, 0] == tot[0] and sums[k, 1] == tot[1]

@@ -167,3 +167,62 @@ dist.destroy_process_group()
                          capture_output=True, text=True, timeout=280)
     assert out.returncode == 0, out.stderr[-3000:]
     assert "TWO_RANK_OK" in out.stdout
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_strong_shard_step_gloo(tmp_path):
+    """world_size-2 gloo run of bench.py's multi-GPU step logic (the CPU oracle standing in for the device): ONE
+    sibling set dealt to the ranks by bench.lpt_shard, the point wave's results exchanged with the padded equal-slice
+    all-gather the bench uses and scattered into every replica, the camera wave solved on the gathered state, the
+    objective all-reduced — equal to the single-process alternating step to the bit (the solves are independent and
+    deterministic; only the partition differs)."""
+    script = tmp_path / "strong_shard.py"
+    script.write_text('''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import bench
+from rdis_b200 import problems as P
+from oracle import oracle_py as O
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+spec = P.ba_synthetic(ncams=5, npts=70, nobs=300, seed=4)
+x0 = spec["x0"]
+pts, cams = P.ba_point_problems(spec), P.ba_camera_problems(spec)
+own_p, own_c = bench.lpt_shard(pts, world), bench.lpt_shard(cams, world)
+assert np.array_equal(np.sort(np.concatenate(own_p)), np.arange(pts.n)) and np.array_equal(np.sort(np.concatenate(own_c)), np.arange(cams.n))
+nf = np.diff(cams.fac_off); loads = [nf[o].sum() for o in own_c]
+assert max(loads) <= np.mean(loads) + nf.max()                       # LPT bound
+my_pts, my_cams = pts.subset(own_p[rank]), cams.subset(own_c[rank])
+orc = O.OracleFunction.from_spec(spec); orc.set_x(x0)
+a = orc.solve_cgd_batch(my_pts.var_off, my_pts.vids, my_pts.fac_off, my_pts.fids, x0[my_pts.vids], 25, 3e-8)
+# the bench's exchange: equal-sized slices, the pad repeats the first (vid, value) pair of the rank
+nmax = max(len(pts.subset(o).vids) for o in own_p)
+pad = lambda v: np.concatenate([v, np.full(nmax - len(v), v[0], v.dtype)])
+vid_all = np.concatenate([pad(pts.subset(o).vids) for o in own_p])
+send = torch.from_numpy(pad(a["x"]))
+recv = torch.zeros(world * nmax, dtype=torch.float64)
+dist.all_gather_into_tensor(recv, send)
+state = x0.copy(); state[vid_all] = recv.numpy()
+orc.set_x(state)
+b = orc.solve_cgd_batch(my_cams.var_off, my_cams.vids, my_cams.fac_off, my_cams.fids, state[my_cams.vids], 25, 3e-8)
+part = torch.tensor([b["f_end"].sum()], dtype=torch.float64)
+dist.all_reduce(part)
+if rank == 0:
+    one = O.OracleFunction.from_spec(spec); one.set_x(x0)
+    pa = one.solve_cgd_batch(pts.var_off, pts.vids, pts.fac_off, pts.fids, x0[pts.vids], 25, 3e-8)
+    full = x0.copy(); full[pts.vids] = pa["x"]
+    assert np.array_equal(state, full)
+    one.set_x(full)
+    ca = one.solve_cgd_batch(cams.var_off, cams.vids, cams.fac_off, cams.fids, full[cams.vids], 25, 3e-8)
+    want = sum(ca["f_end"][own_c[r]].sum() for r in range(world))   # the all-reduce adds rank partials
+    assert float(part) == want, (float(part), want)
+    assert abs(float(part) - ca["f_end"].sum()) <= 1e-12 * abs(ca["f_end"].sum())
+    print("STRONG_SHARD_OK")
+dist.destroy_process_group()
+''' % ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29537", str(script)],
+                         capture_output=True, text=True, timeout=280)
+    assert out.returncode == 0, out.stderr[-3000:] + out.stdout[-1000:]
+    assert "STRONG_SHARD_OK" in out.stdout
