@@ -186,6 +186,10 @@ RDISGPU_API int rdisgpu_batch_create_csr(rdisgpu_ctx* ctx, int64_t nprobs, const
 RDISGPU_API int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiters, double ftol);
 /* Waits, then copies results out (out[i].x may be NULL).  sum_f_end (nullable) = sum of f_end. */
 RDISGPU_API int rdisgpu_batch_fetch(rdisgpu_batch* b, rdisgpu_result* out, double* sum_f_end);
+/* The same with packed outputs, laid out like rdisgpu_solve_cgd_csr's (every pointer nullable): what the C++ adapter's
+ * batch cache uses when the tree search revisits a sibling set (alternating minimisation, RDISOptimizer.cpp:1148-1181). */
+RDISGPU_API int rdisgpu_batch_fetch_csr(rdisgpu_batch* b, double* x_out, double* f_init, double* f_end, int32_t* iters, int32_t* status,
+                                        int64_t* n_feval, int64_t* n_geval);
 /* *sum_dev += sum_i f_end[i], computed on the device (sum_dev is device memory): the per-GPU partial of
  * the global objective, ready for an NCCL all-reduce on the same stream.  Asynchronous. */
 RDISGPU_API int rdisgpu_batch_objective_device(rdisgpu_batch* b, double* sum_dev);

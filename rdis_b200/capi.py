@@ -23,7 +23,7 @@ EXPORTS = (
     "rdisgpu_set_vars", "rdisgpu_add_nlpf", "rdisgpu_add_ba", "rdisgpu_finalize",
     "rdisgpu_set_x", "rdisgpu_get_x", "rdisgpu_set_factor_const",
     "rdisgpu_eval", "rdisgpu_grad", "rdisgpu_eval_device", "rdisgpu_grad_device", "rdisgpu_factor_grad", "rdisgpu_factor_rows_device",
-    "rdisgpu_solve_cgd", "rdisgpu_solve_cgd_csr", "rdisgpu_solve_lm_csr", "rdisgpu_batch_create", "rdisgpu_batch_create_csr", "rdisgpu_batch_info", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch",
+    "rdisgpu_solve_cgd", "rdisgpu_solve_cgd_csr", "rdisgpu_solve_lm_csr", "rdisgpu_batch_create", "rdisgpu_batch_create_csr", "rdisgpu_batch_info", "rdisgpu_batch_solve_cgd", "rdisgpu_batch_fetch", "rdisgpu_batch_fetch_csr",
     "rdisgpu_batch_objective_device", "rdisgpu_batch_destroy", "rdisgpu_batch_last_launches", "rdisgpu_batch_resident_info", "rdisgpu_components", "rdisgpu_bounds", "rdisgpu_bounds_lists",
     "rdisgpu_num_vars", "rdisgpu_num_factors", "rdisgpu_device_state", "rdisgpu_launch_count", "rdisgpu_version",
 )
@@ -81,6 +81,7 @@ def load_library(path=LIB_PATH):
         "rdisgpu_batch_resident_info": (C.c_int, [vp, vp]),
         "rdisgpu_batch_solve_cgd": (C.c_int, [vp, vp, C.c_int, dbl]),
         "rdisgpu_batch_fetch": (C.c_int, [vp, C.POINTER(Result), C.POINTER(dbl)]),
+        "rdisgpu_batch_fetch_csr": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "rdisgpu_batch_objective_device": (C.c_int, [vp, vp]),
         "rdisgpu_batch_destroy": (None, [vp]),
         "rdisgpu_batch_last_launches": (C.c_int, [vp]),

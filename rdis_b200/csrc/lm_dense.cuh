@@ -207,10 +207,10 @@ __global__ void __launch_bounds__(256) lm_potrf_kernel(double* Lm, int m, int kb
     __syncthreads();
     if (t > j && t < nb) a[t][j] = a[t][j] / a[j][j];
     __syncthreads();
-    const int w = nb - j - 1;  // the trailing (r, c) pairs, j < c <= r < nb
-    for (int p = t; p < w * w; p += blockDim.x) {
-      const int r = j + 1 + p / w, c = j + 1 + p % w;
-      if (c <= r) a[r][c] -= a[r][j] * a[c][j];
+    // the trailing (r, c) pairs, j < c <= r < nb: a 16 x 16 thread grid strides over them (no integer division)
+    for (int r = j + 1 + (t >> 4); r < nb; r += 16) {
+      const double arj = a[r][j];
+      for (int c = j + 1 + (t & 15); c <= r; c += 16) a[r][c] -= arj * a[c][j];
     }
     __syncthreads();
   }

@@ -1485,6 +1485,30 @@ int rdisgpu_batch_fetch(rdisgpu_batch* b, rdisgpu_result* out, double* sum_f_end
   return RDISGPU_OK;
 }
 
+int rdisgpu_batch_fetch_csr(rdisgpu_batch* b, double* x_out, double* f_init, double* f_end, int32_t* iters, int32_t* status,
+                            int64_t* n_feval, int64_t* n_geval) {
+  if (!b) return RDISGPU_ERR_ARG;
+  rdisgpu_ctx* ctx = b->ctx;
+  if (!b->solved) return ctx->fail(RDISGPU_ERR_STATE, "batch_fetch_csr before batch_solve");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemcpyAsync(b->h_res.p, b->res.p, (size_t)b->nprobs * sizeof(ResultRec), cudaMemcpyDeviceToHost, s));
+  if (x_out && b->total_nv > 0)
+    CK(cudaMemcpyAsync(b->h_x.p, b->xout.p, (size_t)b->total_nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (x_out && b->total_nv > 0) std::memcpy(x_out, b->h_x.p, (size_t)b->total_nv * sizeof(double));
+  for (int64_t p = 0; p < b->nprobs; ++p) {
+    const ResultRec& r = b->h_res.p[p];
+    if (f_init) f_init[p] = r.f_init;
+    if (f_end) f_end[p] = r.f_end;
+    if (iters) iters[p] = r.iters;
+    if (status) status[p] = r.status;
+    if (n_feval) n_feval[p] = (int64_t)r.n_value + r.n_slope;
+    if (n_geval) n_geval[p] = r.n_slope;
+  }
+  return RDISGPU_OK;
+}
+
 int rdisgpu_batch_objective_device(rdisgpu_batch* b, double* sum_dev) {
   if (!b) return RDISGPU_ERR_ARG;
   rdisgpu_ctx* ctx = b->ctx;

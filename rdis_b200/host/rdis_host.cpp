@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <limits>
 #include <cassert>
+#include <cstring>
 #include <iostream>
 #include <numeric>
 
@@ -89,7 +90,56 @@ void Factor::unassign(VariableID assignmentKey) {
 OptimizableFunction::OptimizableFunction() : kind(-1), ncams(0), npts(0), ctx(nullptr) {}
 
 OptimizableFunction::~OptimizableFunction() {
+  for (CachedBatch& c : batchCache)
+    if (c.batch) rdisgpu_batch_destroy(c.batch);
   if (ctx) rdisgpu_destroy(ctx);  // variables and factors live in the arenas (the reference deletes them one by one, :43-54)
+}
+
+rdisgpu_batch* OptimizableFunction::cachedBatch(const std::vector<int64_t>& var_off, const std::vector<int32_t>& vids,
+                                                const std::vector<int64_t>& fac_off, const std::vector<int64_t>& fids) {
+  auto mix = [](unsigned long long h, const void* p, size_t n) {  // 8 bytes at a time; equality is checked on a hit anyway
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+      unsigned long long w;
+      std::memcpy(&w, b + i, 8);
+      h = (h ^ w) * 0x9E3779B97F4A7C15ULL;
+      h ^= h >> 29;
+    }
+    for (; i < n; ++i) h = (h ^ b[i]) * 1099511628211ULL;
+    return h;
+  };
+  unsigned long long key = 1469598103934665603ULL;
+  key = mix(key, var_off.data(), var_off.size() * 8);
+  key = mix(key, vids.data(), vids.size() * 4);
+  key = mix(key, fac_off.data(), fac_off.size() * 8);
+  key = mix(key, fids.data(), fids.size() * 8);
+  for (CachedBatch& c : batchCache)
+    if (c.key == key && c.vids == vids && c.fids == fids && c.var_off == var_off && c.fac_off == fac_off) {
+      c.stamp = ++batchClock;
+      return c.batch;
+    }
+  constexpr size_t kMaxCached = 8;
+  CachedBatch* slot = nullptr;
+  if (batchCache.size() < kMaxCached) {
+    batchCache.emplace_back();
+    slot = &batchCache.back();
+  } else {  // evict the least recently used
+    slot = &batchCache[0];
+    for (CachedBatch& c : batchCache)
+      if (c.stamp < slot->stamp) slot = &c;
+    rdisgpu_batch_destroy(slot->batch);
+    slot->batch = nullptr;
+  }
+  slot->key = key;
+  slot->stamp = ++batchClock;
+  slot->vids = vids;
+  slot->fids = fids;
+  slot->var_off = var_off;
+  slot->fac_off = fac_off;
+  check(rdisgpu_batch_create_csr(ctx, (int64_t)var_off.size() - 1, var_off.data(), vids.data(), fac_off.data(), fids.data(), &slot->batch),
+        "rdisgpu_batch_create_csr");
+  return slot->batch;
 }
 
 void OptimizableFunction::reserve(size_t nFactors, size_t nEdges) {
@@ -425,6 +475,12 @@ Numeric CudaSubspaceOptimizer::optimizeBatch(std::vector<ComponentProblem>& prob
     f.check(rdisgpu_solve_lm_csr(f.device(), n, var_off.data(), vids.data(), fac_off.data(), fids.data(), x0.data(), (int)maxiters,
                                  opts, xout.data(), finit.data(), fend.data(), iters.data(), status.data(), nfe.data(), nge.data()),
             "rdisgpu_solve_lm_csr");
+  } else if (n >= 64) {
+    // a wave: its index lists stay resident (a revisit of the same sibling set uploads start values only)
+    rdisgpu_batch* b = f.cachedBatch(var_off, vids, fac_off, fids);
+    f.check(rdisgpu_batch_solve_cgd(b, x0.data(), (int)maxiters, ftol), "rdisgpu_batch_solve_cgd");
+    f.check(rdisgpu_batch_fetch_csr(b, xout.data(), finit.data(), fend.data(), iters.data(), status.data(), nfe.data(), nge.data()),
+            "rdisgpu_batch_fetch_csr");
   } else {
     f.check(rdisgpu_solve_cgd_csr(f.device(), n, var_off.data(), vids.data(), fac_off.data(), fids.data(), x0.data(), (int)maxiters,
                                   ftol, xout.data(), finit.data(), fend.data(), iters.data(), status.data(), nfe.data(), nge.data()),

@@ -38,6 +38,7 @@
 #include <vector>
 
 struct rdisgpu_ctx;
+struct rdisgpu_batch;
 
 namespace rdis {
 
@@ -289,6 +290,19 @@ class OptimizableFunction {
   std::vector<int32_t> dirtyVids;
   std::vector<uint8_t> dirtyFlag;
   std::vector<Factor*> dirtyFactors;
+  // Sibling batches the tree search comes back to (alternating minimisation re-poses the same components with new start
+  // values, src/RDISOptimizer.cpp:1148-1181): their index lists stay resident on the device (rdisgpu_batch), keyed by the
+  // lists themselves; a revisit uploads start values only.  Owned here so that they die before the context.
+  struct CachedBatch {
+    unsigned long long key = 0, stamp = 0;
+    std::vector<int32_t> vids;
+    std::vector<int64_t> fids, var_off, fac_off;
+    rdisgpu_batch* batch = nullptr;
+  };
+  std::vector<CachedBatch> batchCache;
+  unsigned long long batchClock = 0;
+  rdisgpu_batch* cachedBatch(const std::vector<int64_t>& var_off, const std::vector<int32_t>& vids, const std::vector<int64_t>& fac_off,
+                             const std::vector<int64_t>& fids);
 };
 
 class SubspaceOptimizer {

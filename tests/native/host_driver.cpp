@@ -182,7 +182,7 @@ int main(int argc, char** argv) {
         for (VariableID vid : open) vars[(size_t)vid]->assign(x0[(size_t)vid]);
       }
       const double dispatch_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - d0).count();
-      double total_ms = 0, objective = 0, pts_sum = 0;
+      double total_ms = 0, objective = 0, pts_sum = 0, objective_first = 0;
       for (int it = 0; it < warmup + steps; ++it) {
         const auto t0 = std::chrono::steady_clock::now();
         for (Variable* v : vars) v->assign(x0[(size_t)v->getID()]);
@@ -193,15 +193,16 @@ int main(int argc, char** argv) {
           if (side == 0) pts_sum = tot; else objective = tot;
         }
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (it == 0) objective_first = objective;  // first visit: the batches are built and cached; later steps hit the cache
         if (it >= warmup) total_ms += ms;
       }
       size_t nsolves = waves[0].size() + waves[1].size(), nv = 0, nf = 0;
       for (int side = 0; side < 2; ++side)
         for (const ComponentProblem& p : waves[side]) { nv += p.vars.size(); nf += p.factors.size(); }
       std::printf("{\"solves_per_step\": %zu, \"steps\": %d, \"warmup\": %d, \"ms_per_step\": %.6f, \"solves_per_s\": %.3f, "
-                  "\"objective_after_step\": %.17g, \"point_wave_sum\": %.17g, \"dispatch_ms\": %.3f, \"vars_in_problems\": %zu, "
+                  "\"objective_after_step\": %.17g, \"objective_first_step\": %.17g, \"point_wave_sum\": %.17g, \"dispatch_ms\": %.3f, \"vars_in_problems\": %zu, "
                   "\"factors_in_problems\": %zu, \"V\": %lld}\n",
-                  nsolves, steps, warmup, total_ms / steps, nsolves * steps / (total_ms * 1e-3), objective, pts_sum, dispatch_ms, nv, nf,
+                  nsolves, steps, warmup, total_ms / steps, nsolves * steps / (total_ms * 1e-3), objective, objective_first, pts_sum, dispatch_ms, nv, nf,
                   fn.getNumVars());
       return 0;
     }
