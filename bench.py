@@ -646,7 +646,8 @@ def cfg2_full_solve(device, stream, with_cpu=True):
             ts.append(a.elapsed_time(e))
         r = b.fetch()
         row = {"V": int(spec["V"]), "F": int(spec["F"]), "gpu_ms": float(min(ts[1:])), "f_init": float(r["f_init"][0]),
-               "f_end": float(r["f_end"][0]), "iters": int(r["iters"][0]), "evaluations": int(r["n_feval"][0]), "mapping": b.info()}
+               "f_end": float(r["f_end"][0]), "iters": int(r["iters"][0]), "evaluations": int(r["n_feval"][0]), "mapping": b.info(),
+               "status": int(r["status"][0])}
         if with_cpu:
             from oracle import oracle_py as O
             orc = O.OracleFunction.from_spec(spec)
@@ -759,11 +760,17 @@ def cfg4_sibling_wave(device, stream, rank, world, dist, dev):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    r = b.fetch(want_x=False)
+    r = b.fetch()
+    hist = np.bincount(r["status"], minlength=8).astype(np.int64)
+    if dist is not None:
+        t = torch.from_numpy(hist).to(dev)
+        dist.all_reduce(t)
+        hist = t.cpu().numpy()
     out = {"workload": "sinusoid h=19 k=2 arity=4 (V=%d, F=%d): %d sibling components of %d variables / %d factors after assigning "
                        "the top 10 tree levels, %d per rank" % (spec["V"], spec["F"], ps.n, ps.var_off[1], ps.fac_off[1], mine.n),
            "scaling": "strong", "n_gpus": world, "ms": ms, "solves_per_sec": ps.n / (ms * 1e-3),
            "objective_sum_f_end": float(obj.item()), "mapping": b.info(),
+           "status_histogram": hist.tolist(), "status_names": "ftol, gtol, gg_zero, maxiters, dbrent_itmax, empty, nonfinite (safety exit), bracket_cap (safety exit)",
            "kernel": "solve_nlpf_resident_kernel (one CTA per component, resident in shared memory)",
            "dram_bytes_per_launch_ncu": measured_traffic("solve_nlpf_resident_kernel"),
            "fp64_pipe_active_pct_ncu": measured_traffic("solve_nlpf_resident_kernel", "fp64_pipe_active_pct")}

@@ -172,7 +172,7 @@ struct NlpfOps {
               }
             }
           }
-          s = __fma_rn(pe * c, dir[i], s);  // explicit contraction: the resident kernel (nlpf_resident.cuh) folds the same way
+          s = s + (pe * c) * dir[i];  // product rounded, then the sum (no contraction anywhere: the resident kernel folds the same way)
         }
       }
       slope = s;
@@ -185,7 +185,7 @@ struct NlpfOps {
       bool pl;
       term<kAlongLine>(G, ei, alpha, ti, dti, pl, diri);
       prod *= ti;
-      if (diri != 0.0) s = __fma_rn(partial<kAlongLine>(G, e0, e1, ei, alpha) * c, diri, s);
+      if (diri != 0.0) s = s + (partial<kAlongLine>(G, e0, e1, ei, alpha) * c) * diri;
     }
     slope = s;
     return prod * c;

@@ -188,7 +188,7 @@ __device__ __forceinline__ void resident_fold(const ResView& R, int r0, double c
         double pe = (i == 0) ? dt[0] : t[0];  // getDerivative: own slot replaced by its derivative (1.0 when plain)
 #pragma unroll
         for (int j = 1; j < N; ++j) pe *= (j == i) ? dt[j] : t[j];
-        s = __fma_rn(pe * c, dir[i], s);
+        s = s + (pe * c) * dir[i];
       }
     }
   }
@@ -258,7 +258,7 @@ __device__ __forceinline__ void resident_line_eval(const GraphView& G, const Res
                 const int lj = R.elt[r0 + j];
                 pe *= (j == i) ? R.tdt[lj] : R.tval[lj];
               }
-              s = __fma_rn(pe * c, diri, s);
+              s = s + (pe * c) * diri;
             }
           }
         }

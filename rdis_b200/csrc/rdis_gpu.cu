@@ -114,6 +114,7 @@ struct rdisgpu_ctx {
   rdisgpu_batch* scratch_batch = nullptr;  // reused by the one-shot solve entry points
   int live_batches = 0;                    // rdisgpu_batch_create'd and not yet destroyed: rdisgpu_destroy refuses while > 0
   bool generic_only = false;  // rdisgpu_set_option("generic_only"): bypass the BA block kernels (tests)
+  int pt_tiles_cap = 32;      // rdisgpu_set_option("point_tiles_per_warp"): at most this many point blocks share a warp
   int cam_cluster_opt = 0;    // rdisgpu_set_option("camera_cluster"): pin the cluster width of the camera-block kernel (0 = choose)
   bool strict = false;        // rdisgpu_set_option("strict"): every solve through strict_kernels.cuh (bit-exact parity instrument)
   DevBuf<double> fcache;      // strict mode: the reference's per-factor value cache ...
@@ -335,6 +336,11 @@ int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return RDISGPU_ERR_ARG;
   if (std::strcmp(name, "generic_only") == 0) {
     ctx->generic_only = (value != 0);
+    return RDISGPU_OK;
+  }
+  if (std::strcmp(name, "point_tiles_per_warp") == 0) {
+    if (value < 1 || value > 32) return ctx->fail(RDISGPU_ERR_ARG, "set_option: point_tiles_per_warp must be 1..32");
+    ctx->pt_tiles_cap = (int)value;
     return RDISGPU_OK;
   }
   if (std::strcmp(name, "camera_cluster") == 0) {
@@ -964,7 +970,7 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
   b->total_nf = tf;
 
   // upper bounds of every list, then carve the pinned staging blob
-  const size_t npt_tasks_max = (size_t)nprobs + 6;
+  const size_t npt_tasks_max = (size_t)nprobs + 6;  // one task per problem at worst (point_tiles_per_warp = 1)
   auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   const size_t o_probs = 0;
   const size_t o_vids = align16(o_probs + sizeof(ProblemDesc) * (size_t)nprobs);
@@ -1109,7 +1115,7 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
     // longest-running warps are scheduled first
     int32_t npt = 0;
     for (int lg = 5; lg >= 0; --lg) {
-      const int per_warp = 32 >> lg;
+      const int per_warp = std::min(32 >> lg, ctx->pt_tiles_cap);
       const int32_t base = npt;
       const int32_t cnt = (int32_t)pt_lists[lg].size();
       if (cnt) std::memcpy(h_pt + npt, pt_lists[lg].data(), 4 * (size_t)cnt);
