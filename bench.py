@@ -398,7 +398,7 @@ def e2e_leg(args, spec, pts, cams, own_p, own_c, ctx, rank, world, local_rank, h
         res.update({"value": d["solves_per_s"], "ms_per_step": d["ms_per_step"], "objective": d["objective_after_step"],
                     "through": "rdis::CudaSubspaceOptimizer::optimizeBatch over host Variable/Factor objects (librdis_host.so, "
                                "tests/native/host_driver benchwaves): Variable::assign of x0, 2 sibling batches, Variable write-back; wall clock",
-                    "dispatch_ms_once": d["dispatch_ms"]})
+                    "dispatch_ms_once": d["dispatch_ms"], "plugin_ms_per_step": d.get("plugin_ms_per_step")})
         # the same step through the bare C-ABI from ctypes (what round 1 reported as e2e)
         x0_pts, x0_cams = x0[pts.vids].copy(), x0[cams.vids].copy()
 

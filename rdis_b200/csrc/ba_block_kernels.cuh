@@ -171,9 +171,19 @@ __device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const B
   // so, with the library built without FMA contraction and the correctly rounded quotients of BaOps::partials, a point
   // block is solved to the same BITS as the reference arithmetic produces (tests: the full real ladybug wave).
   const unsigned kFull = 0xffffffffu;
+#ifdef RDIS_PT_PROFILE  // cycle accounting of one evaluation (clock64; a tuning build, never shipped)
+  long long pprof[4] = {0, 0, 0, 0}, plast = clock64();
+  int pnev = 0;
+#define PTPROF(i) do { const long long t_ = clock64(); pprof[i] += t_ - plast; plast = t_; } while (0)
+#else
+#define PTPROF(i) do { } while (0)
+#endif
   while (true) {
     const bool fin = mc.done();
     if (__all_sync(kFull, fin)) break;
+#ifdef RDIS_PT_PROFILE
+    ++pnev;
+#endif
     const int kind = fin ? (int)REQ_DONE : mc.req;  // REQ_INIT_GRAD, REQ_VALUE, REQ_VALUE_SLOPE or REQ_GRADIENT
     const bool along = (kind == REQ_VALUE) || (kind == REQ_VALUE_SLOPE);
     const bool grad_kind = (kind == REQ_INIT_GRAD) || (kind == REQ_GRADIENT);
@@ -193,23 +203,34 @@ __device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const B
       if (fc_on) fv = fc_val;  // Factor::eval of an assigned-constant factor, src/Factor.cpp:110-119
     }
 
+    PTPROF(0);  // vote, clamp, the observation's value / partials
     // left-to-right folds over the tile's lanes (= the problem's factor list), replicated in every lane
     double fs = 0.0;
     double gr[3] = {0.0, 0.0, 0.0};
     const bool any_g = __any_sync(kFull, want_g);
-    for (int k = 0; k < G; ++k) {
-      const double bf = __shfl_sync(kFull, fv, k, G);
-      if (k < nf) fs = fs + bf;
-      if (any_g) {
+    // The broadcasts do not depend on the running sums: the loops are unrolled so that the shuffles of the next lanes
+    // are in flight while the additions of the previous ones retire (the chain is then the additions alone).
+    if (any_g) {
+#pragma unroll 4
+      for (int k = 0; k < G; ++k) {
+        const double bf = __shfl_sync(kFull, fv, k, G);
         const double b0 = __shfl_sync(kFull, g9, k, G), b1 = __shfl_sync(kFull, g10, k, G), b2 = __shfl_sync(kFull, g11, k, G);
+        if (k < nf) fs = fs + bf;
         if (k == 0) {
           gr[0] = b0; gr[1] = b1; gr[2] = b2;
         } else if (k < nf) {
           gr[0] = gr[0] + b0; gr[1] = gr[1] + b1; gr[2] = gr[2] + b2;
         }
       }
+    } else {
+#pragma unroll 4
+      for (int k = 0; k < G; ++k) {
+        const double bf = __shfl_sync(kFull, fv, k, G);
+        if (k < nf) fs = fs + bf;
+      }
     }
 
+    PTPROF(1);  // ordered folds
     // ---- the state machine's step: scalar work, the only part where tiles of a warp diverge ----
     if (!fin) {
       cache.assign(&x[9]);  // SubfunctionFD::quickAssignVals of this evaluation's point
@@ -264,7 +285,13 @@ __device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const B
       // pass that preceded it, and f_at_p is its objective — answered without another pass
       if (mc.req == REQ_VALUE && mc.phase == CgdMachine::PH_BR_FA) mc.on_eval(cache.eval(f_at_p), 0.0);
     }
+    __syncwarp();
+    PTPROF(2);  // machine step (tiles diverge)
   }
+#ifdef RDIS_PT_PROFILE
+  if ((threadIdx.x & 31) == 0 && pnev >= 300)
+    printf("ptprof G %d passes %d | eval %lld fold %lld machine %lld cycles per pass\n", G, pnev, pprof[0] / pnev, pprof[1] / pnev, pprof[2] / pnev);
+#endif
 
   if (!run) return;
   // ---- commit (CGD.cpp:61-89): quickAssignVals(gdmin.p); if worse than the start, the start is re-assigned and

@@ -44,7 +44,8 @@ namespace rdisgpu {
 #ifndef RDIS_TILE_CTAS
 #define RDIS_TILE_CTAS 3
 #endif
-constexpr int kTileThreads = RDIS_TILE_THREADS;   // consumer threads (one more warp is the TMA producer)
+constexpr int kTileThreads = RDIS_TILE_THREADS;   // consumer threads
+constexpr int kTileBlock = kTileThreads + 64;     // + the bulk-copy warp + the gather warp
 constexpr int kTileEdges = RDIS_TILE_EDGES;
 constexpr int kTileFactors = RDIS_TILE_FACTORS;
 constexpr int kTileStages = RDIS_TILE_STAGES;
@@ -75,12 +76,28 @@ struct TileStage {
 };
 static_assert(sizeof(TileStage) % 16 == 0, "stages must keep 16-byte alignment");
 
+template <bool kGrad>
 struct TileSmem {
   TileStage stage[kTileStages];
+  // kGrad: the tile's per-edge partials, parked here by phase 2 and written to gedge by ONE bulk store per tile (two
+  // buffers: the store of tile i reads its buffer while phase 2 of tile i+1 fills the other).  Slot parity = parity of
+  // the global edge index, so that the even-aligned body of the slice is 16-byte aligned on both sides.
+  double gout[kGrad ? 2 : 1][kGrad ? kTileEdges + 2 : 2];
   unsigned long long full[kTileStages];   // producer -> consumers: the stage's bytes have landed
   unsigned long long xready[kTileStages]; // producer -> consumers: ... and the gathered variable values too
   unsigned long long empty[kTileStages];  // consumers -> producer: every consumer warp is done with the stage
 };
+
+// gedge[e0 .. e0+ne) <- buf[(e0 & 1) ...]: the 16-byte aligned body as one bulk store, an odd first / last edge directly.
+// Called by one consumer thread after a consumer barrier that follows the writes to buf.
+__device__ __forceinline__ void tile_store_partials(double* __restrict__ gedge, const double* buf, int e0, int ne) {
+  const int ao = e0 & 1;
+  const int body = (ne - ao) & ~1;
+  if (body > 0) tma_bulk_s2g(gedge + e0 + ao, buf + 2 * ao, (uint32_t)body * 8u);
+  if (ao) gedge[e0] = buf[1];
+  if (ao + body < ne) gedge[e0 + ne - 1] = buf[ao + ne - 1];
+  bulk_commit();
+}
 
 // value term exactly as NlpfOps::value (no-slope path) computes it
 __device__ __forceinline__ double nlpf_term_value(double xv, double k, double ex, bool sn) {
@@ -143,9 +160,13 @@ __device__ __forceinline__ void tile_issue(const GraphView& G, const TileDesc d,
   const int f_lo = d.f0 & ~3;
   const uint32_t n_rp = (uint32_t)((d.f1 + 1 - f_lo + 3) & ~3);
   const uint32_t n_cf = (uint32_t)((d.f1 - f_lo + 1) & ~1);
+#ifdef RDIS_EXP_NOPARAMS  // timing experiment: what the sweep costs when the per-edge parameters do not cross HBM
+  mbar_arrive_expect_tx(bar, n_e * 5u + n_rp * 4u + n_cf * 8u);
+#else
   mbar_arrive_expect_tx(bar, n_e * 21u + n_rp * 4u + n_cf * 8u);
   tma_bulk_g2s(st.expo, G.expo + e_lo, n_e * 8u, bar, pol);
   tma_bulk_g2s(st.konst, G.konst + e_lo, n_e * 8u, bar, pol);
+#endif
   tma_bulk_g2s(st.evid, G.evid + e_lo, n_e * 4u, bar, pol);
   tma_bulk_g2s(st.sine, G.sine + e_lo, n_e, bar, pol);
   tma_bulk_g2s(st.rowptr, G.rowptr + f_lo, n_rp * 4u, bar, pol);
@@ -155,28 +176,24 @@ __device__ __forceinline__ void tile_issue(const GraphView& G, const TileDesc d,
 // Named barrier over the consumer warps only (the producer warp never joins it).
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTileThreads) : "memory"); }
 
-// Block layout: warps 0..kTileThreads/32-1 = consumers, one more warp = producer.
-// The producer warp runs two software-pipelined jobs per tile: lane 0 launches the six TMA bulk copies
-// (kTileStages - kGatherLag tiles ahead of the consumers), and — kGatherLag tiles later, once the slice
-// has landed — all 32 lanes gather the tile's variable values into the stage with 8-byte cp.async
-// copies from the dense value mirror (xval).  Consumers therefore find everything in shared memory:
-// no register staging, no exposed gather latency.  Terms are written IN PLACE over the stage's
-// exponent slots (derivatives over the constant slots): the thread that consumes expo[e] / konst[e] is
-// the one that produces term[e], so a tile needs exactly one CTA-wide barrier.
+// Block layout: warps 0..kTileThreads/32-1 = consumers, then the bulk-copy warp, then the gather warp.
+//   bulk-copy warp   lane 0 launches the six TMA bulk copies of a tile as soon as its stage has been released;
+//   gather warp      once a slice has landed (its `full` barrier), all 32 lanes gather the tile's variable values into
+//                    the stage with 8-byte cp.async copies from the dense value mirror (xval) and signal `xready`.
+// The two run on separate warps because each blocks on a different event: one warp doing both issues the gathers of
+// tile j only after the consumers have released the stage of tile j+1's copy, which caps a CTA at one tile per gather
+// latency (ncu of that form: 39 % of all warp samples on the consumers' `xready` wait).
+// Consumers find everything in shared memory: no register staging, no exposed gather latency.  Terms are written IN
+// PLACE over the stage's exponent slots (derivatives over the constant slots): the thread that consumes expo[e] /
+// konst[e] is the one that produces term[e], so a tile needs exactly one CTA-wide barrier.
 // Precondition (holds for every stream-ordered caller): no subspace solve is running on this context,
 // i.e. every variable is frozen and xval mirrors xbd.x.
-#ifndef RDIS_TILE_GATHER_LAG
-#define RDIS_TILE_GATHER_LAG 1
-#endif
-constexpr int kGatherLag = RDIS_TILE_GATHER_LAG;
-static_assert(kGatherLag >= 1 && kGatherLag < kTileStages, "the gather trails the bulk copy by fewer tiles than there are stages");
-
 template <bool kGrad>
-__global__ void __launch_bounds__(kTileThreads + 32, kGrad ? RDIS_TILE_CTAS_GRAD : kTileCtasPerSm)
+__global__ void __launch_bounds__(kTileBlock, kGrad ? RDIS_TILE_CTAS_GRAD : kTileCtasPerSm)
     nlpf_tile_sweep_kernel(GraphView G, const TileDesc* __restrict__ tiles, int ntiles, double* __restrict__ per_factor,
                            double* partials, unsigned int* counter, double* sum_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+  TileSmem<kGrad>& S = *reinterpret_cast<TileSmem<kGrad>*>(smem_raw);
   const int tid = threadIdx.x;
   const int stride = gridDim.x;
   const int my_tiles = (ntiles - (int)blockIdx.x + stride - 1) / stride;
@@ -192,8 +209,26 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? RDIS_TILE_CTAS_GRAD
   __syncthreads();
 
   double acc = 0.0;
-  if (tid >= kTileThreads) {
-    // ---- producer warp ----
+  if (tid >= kTileThreads + 32) {
+    // ---- gather warp ----  waits only for a slice to land (never for the consumers), so the gathers of tile j+1 are
+    // issued while those of tile j may still be in flight
+    const int lane = tid & 31;
+    const uint64_t keep = l2_policy_evict_last();
+    for (int g = 0; g < my_tiles; ++g) {
+      const int sg = g % kTileStages;
+      TileStage& st = S.stage[sg];
+      mbar_wait(&S.full[sg], (uint32_t)(g / kTileStages) & 1u);
+      const TileDesc dg = st.desc;
+      const int ne = dg.e1 - dg.e0, eo = dg.e0 & 15;
+      if (ne <= kTileEdges) {
+#ifndef RDIS_EXP_NOGATHER
+        for (int le = lane; le < ne; le += 32) cp_async_gather8(&st.xs[eo + le], G.xval + st.evid[eo + le], keep);
+#endif
+      }
+      cp_async_arrive_noinc(&S.xready[sg]);  // fires when this lane's copies have landed
+    }
+  } else if (tid >= kTileThreads) {
+    // ---- bulk-copy warp ----
     // Descriptors are fetched 32 at a time (one per lane, the next batch already in flight), so the
     // issue loop never waits on HBM for a descriptor.
     const int lane = tid & 31;
@@ -203,44 +238,30 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? RDIS_TILE_CTAS_GRAD
     };
     TileDesc mine = fetch(0), ahead = fetch(1);
     const uint64_t pol = l2_policy_evict_first();
-    const uint64_t keep = l2_policy_evict_last();
-    for (int j = 0; j < my_tiles + kGatherLag; ++j) {
-      if (j < my_tiles) {
-        if (j > 0 && (j & 31) == 0) {
-          mine = ahead;
-          ahead = fetch((j >> 5) + 1);
-        }
-        TileDesc d;
-        d.f0 = __shfl_sync(0xffffffffu, mine.f0, j & 31);
-        d.f1 = __shfl_sync(0xffffffffu, mine.f1, j & 31);
-        d.e0 = __shfl_sync(0xffffffffu, mine.e0, j & 31);
-        d.e1 = __shfl_sync(0xffffffffu, mine.e1, j & 31);
-        if (lane == 0) {
-          const int s = j % kTileStages;
-          if (j >= kTileStages) mbar_wait_backoff(&S.empty[s], (uint32_t)(j / kTileStages - 1) & 1u);  // stage released
-          S.stage[s].desc = d;
-          tile_issue(G, d, S.stage[s], &S.full[s], pol);
-        }
-        __syncwarp();
+    for (int j = 0; j < my_tiles; ++j) {
+      if (j > 0 && (j & 31) == 0) {
+        mine = ahead;
+        ahead = fetch((j >> 5) + 1);
       }
-      const int g = j - kGatherLag;  // the tile whose slice should have landed by now: gather its variables
-      if (g >= 0) {
-        const int sg = g % kTileStages;
-        TileStage& st = S.stage[sg];
-        mbar_wait(&S.full[sg], (uint32_t)(g / kTileStages) & 1u);
-        const TileDesc dg = st.desc;
-        const int ne = dg.e1 - dg.e0, eo = dg.e0 & 15;
-        if (ne <= kTileEdges) {
-#ifndef RDIS_EXP_NOGATHER
-          for (int le = lane; le < ne; le += 32) cp_async_gather8(&st.xs[eo + le], G.xval + st.evid[eo + le], keep);
-#endif
-        }
-        cp_async_arrive_noinc(&S.xready[sg]);  // fires when this lane's copies have landed
+      TileDesc d;
+      d.f0 = __shfl_sync(0xffffffffu, mine.f0, j & 31);
+      d.f1 = __shfl_sync(0xffffffffu, mine.f1, j & 31);
+      d.e0 = __shfl_sync(0xffffffffu, mine.e0, j & 31);
+      d.e1 = __shfl_sync(0xffffffffu, mine.e1, j & 31);
+      if (lane == 0) {
+        const int s = j % kTileStages;
+        if (j >= kTileStages) mbar_wait_backoff(&S.empty[s], (uint32_t)(j / kTileStages - 1) & 1u);  // stage released
+        S.stage[s].desc = d;
+        tile_issue(G, d, S.stage[s], &S.full[s], pol);
       }
+      __syncwarp();
     }
   } else {
     // ---- consumers ----
     const int lane = tid & 31;
+    // kGrad: the previous tile's partials sit in gout[(it - 1) & 1]; thread 0 stores them once a consumer barrier has
+    // ordered every thread's phase 2 before it — the barrier of the NEXT tile, so no extra barrier is paid.
+    int pend_e0 = 0, pend_ne = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % kTileStages;
       const uint32_t parity = (uint32_t)(it / kTileStages) & 1u;
@@ -251,6 +272,11 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? RDIS_TILE_CTAS_GRAD
       const int ne = d.e1 - d.e0;
 
       if (ne > kTileEdges) {  // one over-wide factor, folded serially from global memory
+        if (kGrad) {
+          consumer_barrier();
+          if (tid == 0 && pend_ne > 0) tile_store_partials(G.gedge, S.gout[(it - 1) & 1], pend_e0, pend_ne);
+          pend_ne = 0;
+        }
         if (tid == 0) {
           double fv;
           if (kGrad) {
@@ -278,7 +304,11 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? RDIS_TILE_CTAS_GRAD
 #else
             const double xv = xs[le];
 #endif
+#ifdef RDIS_EXP_NOPARAMS
+            const double ex = 1.0, kk = 0.0;
+#else
             const double ex = term[le], kk = dterm[le];
+#endif
             const bool sn = sine[le] != 0;
             if (kGrad) {
               double tv, dt;
@@ -290,7 +320,14 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? RDIS_TILE_CTAS_GRAD
             }
           }
         }
+        if (kGrad && tid == 0) bulk_wait_read_all();  // the store issued one tile ago has left gout[it & 1]
         consumer_barrier();  // the only CTA-wide wait of a tile
+        if (kGrad) {
+          if (tid == 0 && pend_ne > 0) tile_store_partials(G.gedge, S.gout[(it - 1) & 1], pend_e0, pend_ne);
+          pend_e0 = d.e0;
+          pend_ne = ne;
+        }
+        double* const gst = S.gout[kGrad ? (it & 1) : 0] + (d.e0 & 1);
         // ---- phase 2: factors ----
         const int fo = d.f0 & 3;
         const int nfac = d.f1 - d.f0;
@@ -307,7 +344,7 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? RDIS_TILE_CTAS_GRAD
             if (kGrad) {  // getDerivative: product in slot order, own slot replaced by its derivative
               const double d0 = (n > 0) ? dterm[r0] : 1.0, d1 = (n > 1) ? dterm[r0 + 1] : 1.0;
               const double d2 = (n > 2) ? dterm[r0 + 2] : 1.0, d3 = (n > 3) ? dterm[r0 + 3] : 1.0;
-              double* ge = G.gedge + d.e0 + r0;
+              double* ge = gst + r0;
               if (n > 0) ge[0] = ((((1.0 * d0) * t1) * t2) * t3) * c;
               if (n > 1) ge[1] = ((((1.0 * t0) * d1) * t2) * t3) * c;
               if (n > 2) ge[2] = ((((1.0 * t0) * t1) * d2) * t3) * c;
@@ -319,7 +356,7 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? RDIS_TILE_CTAS_GRAD
               for (int i = r0; i < r0 + n; ++i) {
                 double pe = 1.0;
                 for (int j = r0; j < r0 + n; ++j) pe *= (j == i) ? dterm[j] : term[j];
-                G.gedge[d.e0 + i] = pe * c;
+                gst[i] = pe * c;
               }
             }
           }
@@ -329,9 +366,17 @@ __global__ void __launch_bounds__(kTileThreads + 32, kGrad ? RDIS_TILE_CTAS_GRAD
           acc += fv;
         }
       }
+      if (kGrad) fence_proxy_async_smem();  // this thread's partials, before the barrier that precedes their bulk store
       // this warp is done with stage s: release it to the producer
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.empty[s]);
+    }
+    if (kGrad) {
+      consumer_barrier();
+      if (tid == 0) {
+        if (pend_ne > 0) tile_store_partials(G.gedge, S.gout[(my_tiles - 1) & 1], pend_e0, pend_ne);
+        bulk_wait_all();  // performed before the kernel ends: the gather launch reads gedge
+      }
     }
   }
   block_then_grid_sum(acc, partials, counter, sum_out);

@@ -68,6 +68,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                "l"(src_gmem), "r"(bytes), "r"(smem_addr_u32(bar)), "l"(policy)
                : "memory");
 }
+// shared -> global bulk store (bulk async-group completion).  Source, destination and size are multiples of 16 bytes.
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// every committed bulk store has finished READING its shared-memory source (the buffer may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... has been performed entirely
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory made visible to the asynchronous proxy (before a barrier that precedes a bulk store)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // the variable gather: 16 B {value, direction slot}, kept in L2 with evict-last priority
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t pol;

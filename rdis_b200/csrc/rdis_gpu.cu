@@ -540,12 +540,12 @@ int rdisgpu_finalize(rdisgpu_ctx* ctx) {
     CK(upload(ctx->tiles, tiles.data(), tiles.size(), s));
     // persistent grids: as many CTAs as fit, from the occupancy calculator (dynamic shared memory opt-in)
     {
-      const int smem_e = (int)sizeof(TileSmem), smem_g = (int)sizeof(TileSmem);
+      const int smem_e = (int)sizeof(TileSmem<false>), smem_g = (int)sizeof(TileSmem<true>);
       CK(cudaFuncSetAttribute(nlpf_tile_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_e));
       CK(cudaFuncSetAttribute(nlpf_tile_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
       int occ_e = 0, occ_g = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, nlpf_tile_sweep_kernel<false>, kTileThreads + 32, smem_e));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, nlpf_tile_sweep_kernel<true>, kTileThreads + 32, smem_g));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, nlpf_tile_sweep_kernel<false>, kTileBlock, smem_e));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, nlpf_tile_sweep_kernel<true>, kTileBlock, smem_g));
       if (occ_e < 1 || occ_g < 1) return ctx->fail(RDISGPU_ERR_CUDA, "streaming sweep kernel cannot be resident");
       ctx->tile_grid[0] = std::min(ctx->ntiles, occ_e * ctx->sm_count);
       ctx->tile_grid[1] = std::min(ctx->ntiles, occ_g * ctx->sm_count);
@@ -756,7 +756,7 @@ static int enqueue_eval(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, do
   CK(ctx->s_partials.ensure((size_t)blocks + 1));
   double* dsum = sum_dst ? sum_dst : ctx->s_partials.p + blocks;
   if (tiled)
-    nlpf_tile_sweep_kernel<false><<<blocks, kTileThreads + 32, sizeof(TileSmem), s>>>(
+    nlpf_tile_sweep_kernel<false><<<blocks, kTileBlock, sizeof(TileSmem<false>), s>>>(
         ctx->gv, ctx->tiles.p, ctx->ntiles, per_factor_dev, ctx->s_partials.p, ctx->s_counter.p, dsum);
   else if (ba_all) {
     int rc = launch_ba_sweep(ctx, blocks, per_factor_dev, nullptr, dsum);
@@ -826,7 +826,7 @@ static int enqueue_grad(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, in
     if (ctx->kind == KIND_NLPF && !filter) {
       const int tg = ctx->tile_grid[1];
       CK(ctx->s_partials.ensure((size_t)tg + 1));
-      nlpf_tile_sweep_kernel<true><<<tg, kTileThreads + 32, sizeof(TileSmem), s>>>(
+      nlpf_tile_sweep_kernel<true><<<tg, kTileBlock, sizeof(TileSmem<true>), s>>>(
           ctx->gv, ctx->tiles.p, ctx->ntiles, nullptr, ctx->s_partials.p, ctx->s_counter.p, ctx->s_partials.p + tg);
     } else {
       const int fb = (int)std::min<int64_t>((nf + threads - 1) / threads, (int64_t)ctx->sm_count * 8);
@@ -838,7 +838,10 @@ static int enqueue_grad(rdisgpu_ctx* ctx, int64_t nf, const int32_t* fid_dev, in
     ++ctx->launches;
     CK(cudaGetLastError());
   }
-  const int vb = (int)std::min<int64_t>((nv + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
+#ifndef RDIS_GATHER_BLOCKS_PER_SM
+#define RDIS_GATHER_BLOCKS_PER_SM 16
+#endif
+  const int vb = (int)std::min<int64_t>((nv + threads - 1) / threads, (int64_t)ctx->sm_count * RDIS_GATHER_BLOCKS_PER_SM);
   // with an explicit list an unlisted factor must not contribute; with nf == 0 nothing does
   const bool eff_filter = filter || nf == 0;
   if (ctx->kind == KIND_NLPF)

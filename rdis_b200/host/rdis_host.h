@@ -58,6 +58,7 @@ typedef std::vector<FactorID> FactorIDVec;
 class Factor;
 class Variable;
 class OptimizableFunction;
+struct ComponentProblem;
 
 // A read-only view of a run of a flat pool, with the part of std::vector's interface the callers use.  The host objects
 // keep NO per-object containers: a factor's variables / terms and a variable's incident factors are runs of pools owned
@@ -297,12 +298,18 @@ class OptimizableFunction {
     unsigned long long key = 0, stamp = 0;
     std::vector<int32_t> vids;
     std::vector<int64_t> fids, var_off, fac_off;
+    // the objects the lists were packed from, problem after problem: a call whose problems hold the SAME pointers in the
+    // same order is recognised by comparing pointer runs (sequential memory), without chasing 4e5 pointers for their ids
+    std::vector<const Variable*> pvars;
+    std::vector<const Factor*> pfacs;
     rdisgpu_batch* batch = nullptr;
   };
   std::vector<CachedBatch> batchCache;
   unsigned long long batchClock = 0;
-  rdisgpu_batch* cachedBatch(const std::vector<int64_t>& var_off, const std::vector<int32_t>& vids, const std::vector<int64_t>& fac_off,
-                             const std::vector<int64_t>& fids);
+  CachedBatch* cachedBatch(const std::vector<int64_t>& var_off, const std::vector<int32_t>& vids, const std::vector<int64_t>& fac_off,
+                           const std::vector<int64_t>& fids);
+  CachedBatch* findWave(const std::vector<ComponentProblem>& problems);
+  void rememberWave(CachedBatch& c, const std::vector<ComponentProblem>& problems);
 };
 
 class SubspaceOptimizer {
@@ -342,6 +349,11 @@ class CudaSubspaceOptimizer : public SubspaceOptimizer {
   // time; here the whole wave is ONE device call).  Problems must not share variables or factors.
   // Returns the sum of the problems' final objective values.
   Numeric optimizeBatch(std::vector<ComponentProblem>& problems, const bool printdbg);
+  // wall-clock milliseconds spent in optimizeBatch since the last resetTiming(): recognising / packing the wave, the
+  // device calls (upload + solve + download, synchronous), the write-back into the host objects
+  struct Timing { double pack_ms = 0, device_ms = 0, writeback_ms = 0; long calls = 0; };
+  const Timing& timing() const { return tm; }
+  void resetTiming() { tm = Timing(); }
 
  protected:
   CudaSubspaceOptimizer(OptimizableFunction& f_, bool lm) : SubspaceOptimizer(f_), useLM(lm) {}
@@ -351,6 +363,7 @@ class CudaSubspaceOptimizer : public SubspaceOptimizer {
   std::vector<int64_t> var_off, fac_off, fids, nfe, nge;
   std::vector<int32_t> vids, iters, status;
   std::vector<double> x0, xout, finit, fend;
+  Timing tm;
 };
 
 // Replaces src/optimizers/LMSubspaceOptimizer.{h,cpp} (selected by --useCGD 0, src/bundleadjust/optBA.cpp:155-158).
