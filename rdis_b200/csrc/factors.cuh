@@ -414,6 +414,8 @@ struct BaOps {
   }
 
   // Rotate + translate + project + distort + residual, given rotation(): x[3..11] are read.
+  // The two quotients by the depth share one reciprocal (QuotBy above; kExact in strict mode).
+  template <int kDiv = kCorrected>
   __device__ static __forceinline__ double project(const double* x, double2 ob, Fwd& m) {
     const double q0 = x[9], q1 = x[10], q2 = x[11];
     m.c0 = m.a1 * q2 - m.a2 * q1;
@@ -432,8 +434,9 @@ struct BaOps {
     }
     P0 += x[3]; P1 += x[4]; P2 += x[5];
     m.P0 = P0; m.P1 = P1; m.P2 = P2;
-    m.pp0 = -P0 / P2;
-    m.pp1 = -P1 / P2;
+    const QuotBy<kDiv> by_depth(P2);
+    m.pp0 = by_depth(-P0);
+    m.pp1 = by_depth(-P1);
     m.r2 = m.pp0 * m.pp0 + m.pp1 * m.pp1;
     m.dist = 1 + m.r2 * (x[7] + x[8] * m.r2);
     const double pix0 = x[6] * m.dist * m.pp0;
@@ -443,9 +446,10 @@ struct BaOps {
     return (m.res0 * m.res0 + m.res1 * m.res1) / 2.0;
   }
 
+  template <int kDiv = kCorrected>
   __device__ static __forceinline__ double forward(const double* x, double2 ob, Fwd& m) {
     rotation(x[0], x[1], x[2], m);
-    return project(x, ob, m);
+    return project<kDiv>(x, ob, m);
   }
 
   // 12 partials in slot order.  The reference divides by P_z^2, P_z and |r| 24 times per observation
@@ -536,7 +540,7 @@ struct BaOps {
     return (s < 9) ? (9 * cam + s) : (9 * G.ncams + 3 * pt + (s - 9));
   }
 
-  template <int kAlongLine>
+  template <int kAlongLine, int kDiv = kCorrected>
   __device__ static __forceinline__ double value(const GraphView& G, int64_t fid, double alpha, bool kSlope,
                                                  double& slope) {
     const int32_t cam = __ldg(&G.cam[fid]);
@@ -546,10 +550,10 @@ struct BaOps {
 #pragma unroll
     for (int s = 0; s < 12; ++s) x[s] = load_var<kAlongLine>(G, slot_vid(G, cam, pt, s), alpha, dir[s]);
     Fwd m;
-    const double fv = forward(x, ob, m);
+    const double fv = forward<kDiv>(x, ob, m);
     if (kSlope) {
       double g[12];
-      partials(x, m, g);
+      partials<kDiv>(x, m, g);
       double sl = 0.0;
 #pragma unroll
       for (int s = 0; s < 12; ++s)
@@ -570,7 +574,7 @@ struct BaOps {
 #pragma unroll
     for (int s = 0; s < 12; ++s) x[s] = load_var<kMode>(G, slot_vid(G, cam, pt, s), 0.0, dirv);
     Fwd m;
-    const double fv = forward(x, ob, m);
+    const double fv = forward<kDiv>(x, ob, m);
     double g[12];
     partials<kDiv>(x, m, g);
 #pragma unroll
@@ -579,7 +583,7 @@ struct BaOps {
   }
   __device__ static __forceinline__ double strict_value(const GraphView& G, int64_t fid) {
     double sl;
-    return value<kAssigned>(G, fid, 0.0, false, sl);
+    return value<kAssigned, kExact>(G, fid, 0.0, false, sl);
   }
   __device__ static __forceinline__ double strict_gradient(const GraphView& G, int64_t fid, double* gout) {
     return gradient<kAssigned, kExact>(G, fid, gout);
