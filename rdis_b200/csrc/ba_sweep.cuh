@@ -75,20 +75,6 @@ __global__ void __launch_bounds__(256, kRows ? 2 : RDIS_BA_SWEEP_CTAS) ba_sweep_
   // shared-memory rows are padded to 13 doubles: with 12 (48 words) the rows of a half-warp's 16 lanes fall into 4 bank
   // classes (8-byte reads, 16 lanes per wavefront), with 13 into 16 — lanes of a warp look at unrelated cameras
   double* const st = reinterpret_cast<double*>(ba_smem_raw);
-  if (kSmemTable) {
-    for (int c = threadIdx.x; c < G.ncams; c += blockDim.x) {
-      double x[9];
-#pragma unroll
-      for (int s = 0; s < 9; ++s) x[s] = G.xval[9 * c + s];
-      BaOps::Fwd m;
-      BaOps::rotation(x[0], x[1], x[2], m);
-      double* r = st + kBaSmemRow * c;
-      r[0] = m.a0; r[1] = m.a1; r[2] = m.a2; r[3] = m.theta; r[4] = m.s; r[5] = m.c;
-#pragma unroll
-      for (int s = 3; s < 9; ++s) r[3 + s] = x[s];
-    }
-    __syncthreads();
-  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const double* qbase = G.xval + 9 * (int64_t)G.ncams;
   auto load_stream = [&](int64_t j, BaStage& S) {
@@ -100,6 +86,22 @@ __global__ void __launch_bounds__(256, kRows ? 2 : RDIS_BA_SWEEP_CTAS) ba_sweep_
   auto gather = [&](BaStage& S) {
     const double* qp = qbase + 3 * (int64_t)S.p;
     S.q0 = qp[0]; S.q1 = qp[1]; S.q2 = qp[2];
+  };
+  auto build_table = [&]() {
+    if (kSmemTable) {
+      for (int c = threadIdx.x; c < G.ncams; c += blockDim.x) {
+        double x[9];
+#pragma unroll
+        for (int s = 0; s < 9; ++s) x[s] = G.xval[9 * c + s];
+        BaOps::Fwd m;
+        BaOps::rotation(x[0], x[1], x[2], m);
+        double* r = st + kBaSmemRow * c;
+        r[0] = m.a0; r[1] = m.a1; r[2] = m.a2; r[3] = m.theta; r[4] = m.s; r[5] = m.c;
+#pragma unroll
+        for (int s = 3; s < 9; ++s) r[3 + s] = x[s];
+      }
+      __syncthreads();
+    }
   };
   double acc = 0.0;
   auto compute = [&](int64_t j, const BaStage& S) {
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(256, kRows ? 2 : RDIS_BA_SWEEP_CTAS) ba_sweep_
   load_stream(j, A);
   load_stream(j + stride, Bs);
   load_stream(j + 2 * stride, Cs);
+  build_table();
   gather(A);
   gather(Bs);
 #define RDIS_BA_STEP(CUR, NEXT, NEXT2, AFTER)  \
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(256, kRows ? 2 : RDIS_BA_SWEEP_CTAS) ba_sweep_
   BaStage A, Bs, Cs;
   load_stream(j, A);
   load_stream(j + stride, Bs);
+  build_table();  // the first index / pixel loads are in flight while the CTA computes its camera table
   gather(A);
 #define RDIS_BA_STEP(CUR, NEXT, AFTER)  \
   if (j >= G.F) break;                  \

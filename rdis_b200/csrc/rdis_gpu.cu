@@ -114,7 +114,7 @@ struct rdisgpu_ctx {
   rdisgpu_batch* scratch_batch = nullptr;  // reused by the one-shot solve entry points
   int live_batches = 0;                    // rdisgpu_batch_create'd and not yet destroyed: rdisgpu_destroy refuses while > 0
   bool generic_only = false;  // rdisgpu_set_option("generic_only"): bypass the BA block kernels (tests)
-  int pt_tiles_cap = 32;      // rdisgpu_set_option("point_tiles_per_warp"): at most this many point blocks share a warp
+  int pt_tiles_cap = 0;       // rdisgpu_set_option("point_tiles_per_warp"): at most this many point blocks share a warp (0 = choose)
   int cam_cluster_opt = 0;    // rdisgpu_set_option("camera_cluster"): pin the cluster width of the camera-block kernel (0 = choose)
   bool strict = false;        // rdisgpu_set_option("strict"): every solve through strict_kernels.cuh (bit-exact parity instrument)
   DevBuf<double> fcache;      // strict mode: the reference's per-factor value cache ...
@@ -339,7 +339,7 @@ int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value) {
     return RDISGPU_OK;
   }
   if (std::strcmp(name, "point_tiles_per_warp") == 0) {
-    if (value < 1 || value > 32) return ctx->fail(RDISGPU_ERR_ARG, "set_option: point_tiles_per_warp must be 1..32");
+    if (value < 0 || value > 32) return ctx->fail(RDISGPU_ERR_ARG, "set_option: point_tiles_per_warp must be 0..32");
     ctx->pt_tiles_cap = (int)value;
     return RDISGPU_OK;
   }
@@ -1116,9 +1116,30 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
     }
     // point blocks: one warp per task, 32/G problems per warp; big classes first so that the
     // longest-running warps are scheduled first
+    // How many blocks share a warp: the state-machine steps of the blocks of one warp serialise where they diverge
+    // (1800 of the 3100 cycles of a pass with 16 two-observation blocks per warp), but fewer blocks per warp means
+    // more warps, and the kernel keeps 8 warps per SM resident (234 registers).  The smallest cap whose warp count
+    // stays within 1.3 x the resident capacity is taken (measured: cap 8 for the 7776 blocks of ladybug on one GPU,
+    // 4 / 2 / 2 for the 3888 / 1944 / 972 a rank holds at 2 / 4 / 8 GPUs); results do not depend on it.
+    int tiles_cap = ctx->pt_tiles_cap;
+    if (tiles_cap <= 0) {
+      const int64_t room = (int64_t)ctx->sm_count * 8 * 13 / 10;
+      tiles_cap = 32;
+      for (int cap = 2; cap < 32; cap <<= 1) {
+        int64_t warps = 0;
+        for (int lg = 0; lg <= 5; ++lg) {
+          const int64_t per = std::min(32 >> lg, cap);
+          warps += ((int64_t)pt_lists[lg].size() + per - 1) / per;
+        }
+        if (warps <= room) {
+          tiles_cap = cap;
+          break;
+        }
+      }
+    }
     int32_t npt = 0;
     for (int lg = 5; lg >= 0; --lg) {
-      const int per_warp = std::min(32 >> lg, ctx->pt_tiles_cap);
+      const int per_warp = std::min(32 >> lg, tiles_cap);
       const int32_t base = npt;
       const int32_t cnt = (int32_t)pt_lists[lg].size();
       if (cnt) std::memcpy(h_pt + npt, pt_lists[lg].data(), 4 * (size_t)cnt);

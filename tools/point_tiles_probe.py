@@ -4,8 +4,12 @@ sys.path.insert(0, os.getcwd())
 import numpy as np
 from rdis_b200 import Context, problems as P
 spec = P.load_golden_ba(); x0 = spec["x0"]; pts = P.ba_point_problems(spec)
+frac = int(sys.argv[1]) if len(sys.argv) > 1 else 1  # every frac-th point block only (what one of `frac` ranks holds)
+if frac > 1:
+    pts = pts.subset(np.arange(0, pts.n, frac))
+    print("subset: every %d-th point block, %d problems" % (frac, pts.n))
 ref = None
-for cap in (32, 8, 4, 2, 1):
+for cap in (0, 32, 8, 4, 2, 1):
     ctx = Context.from_spec(spec); ctx.set_option("point_tiles_per_warp", cap); ctx.set_x(x0)
     b = ctx.batch(pts); ts = []
     for it in range(5):
