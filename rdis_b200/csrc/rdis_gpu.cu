@@ -114,6 +114,7 @@ struct rdisgpu_ctx {
   rdisgpu_batch* scratch_batch = nullptr;  // reused by the one-shot solve entry points
   int live_batches = 0;                    // rdisgpu_batch_create'd and not yet destroyed: rdisgpu_destroy refuses while > 0
   bool generic_only = false;  // rdisgpu_set_option("generic_only"): bypass the BA block kernels (tests)
+  int pt_warps_per_sm = 0;    // resident warps of solve_ba_points_kernel per SM (occupancy query, once)
   int pt_tiles_cap = 0;       // rdisgpu_set_option("point_tiles_per_warp"): at most this many point blocks share a warp (0 = choose)
   int cam_cluster_opt = 0;    // rdisgpu_set_option("camera_cluster"): pin the cluster width of the camera-block kernel (0 = choose)
   bool strict = false;        // rdisgpu_set_option("strict"): every solve through strict_kernels.cuh (bit-exact parity instrument)
@@ -1118,12 +1119,17 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
     // longest-running warps are scheduled first
     // How many blocks share a warp: the state-machine steps of the blocks of one warp serialise where they diverge
     // (1800 of the 3100 cycles of a pass with 16 two-observation blocks per warp), but fewer blocks per warp means
-    // more warps, and the kernel keeps 8 warps per SM resident (234 registers).  The smallest cap whose warp count
+    // more warps, and only 8 warps per SM are resident (234 registers; occupancy query).  The smallest cap whose warp count
     // stays within 1.3 x the resident capacity is taken (measured: cap 8 for the 7776 blocks of ladybug on one GPU,
     // 4 / 2 / 2 for the 3888 / 1944 / 972 a rank holds at 2 / 4 / 8 GPUs); results do not depend on it.
     int tiles_cap = ctx->pt_tiles_cap;
     if (tiles_cap <= 0) {
-      const int64_t room = (int64_t)ctx->sm_count * 8 * 13 / 10;
+      if (ctx->pt_warps_per_sm <= 0) {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_ba_points_kernel, 32, 0));
+        ctx->pt_warps_per_sm = std::max(occ, 1);
+      }
+      const int64_t room = (int64_t)ctx->sm_count * ctx->pt_warps_per_sm * 13 / 10;
       tiles_cap = 32;
       for (int cap = 2; cap < 32; cap <<= 1) {
         int64_t warps = 0;
