@@ -93,7 +93,9 @@ RDISGPU_API int rdisgpu_synchronize(rdisgpu_ctx* ctx);
  * src/Factor.cpp:110-119; the cache persists across calls and rdisgpu_set_x applies the filter) and the reference's
  * evaluation sequence — and is bit-identical to the CPU restatement built with the device's sin / cos.
  * "camera_cluster" = 0..8: pins the thread-block-cluster width of the camera-block kernel (0 = choose; results do not
- * depend on it).  "point_tiles_per_warp" = 0..32: at most this many point blocks share a warp (0 = choose from the batch size;
+ * depend on it).  "adaptive_order" = 0 | 1 (default 1): after a batch solve the
+ * block kernels' launch order is re-sorted on the device by the evaluation counts just observed, longest first, for the next
+ * visit of the same batch (results do not depend on it).  "point_tiles_per_warp" = 0..32: at most this many point blocks share a warp (0 = choose from the batch size;
  * results do not depend on it). */
 RDISGPU_API int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value);
 

@@ -336,6 +336,61 @@ struct PointWarpTask {
   int32_t count;
 };
 
+// ------------------------------------------------------------------------------------------
+// Launch order from the previous visit.  Both block kernels are ONE wave of long dependent chains whose length (the
+// number of line-search evaluations) differs 8x between problems, and neither fits the machine entirely: 49 clusters of
+// 8 CTAs place 6 per GPC, so the last one starts when the first one ends; the point kernel has 1.2x more warps than are
+// resident.  What is dispatched last must therefore be SHORT.  A sibling set is re-posed many times by the tree search
+// (alternating minimisation, src/RDISOptimizer.cpp:1148-1181) with start values that move little, so the evaluation
+// counts of the previous solve (ResultRec) predict the next one: after every solve the clusters / warp tasks are
+// re-sorted, longest first (rank sort in one CTA, stream-ordered, no host involvement).  Results do not depend on the
+// order (every problem is solved by its own cluster / tile).  Measured on ladybug's 49 cameras: 3.14 ms in camera-id
+// order, 2.77 ms longest-first.
+// ------------------------------------------------------------------------------------------
+constexpr int kReorderMax = 2048;
+
+__global__ void __launch_bounds__(1024) cam_reorder_kernel(int32_t* __restrict__ order, int n, const ResultRec* __restrict__ res) {
+  __shared__ int32_t item[kReorderMax];
+  __shared__ float key[kReorderMax];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int32_t p = order[i];
+    item[i] = p;
+    // a value-only evaluation costs ~3600 cycles, one with the gradient ~5500 (cycle accounting in DESIGN.md)
+    key[i] = 36.0f * (float)res[p].n_value + 55.0f * (float)res[p].n_slope;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float k = key[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (key[j] > k || (key[j] == k && j < i)) ? 1 : 0;
+    order[rank] = item[i];
+  }
+}
+
+__global__ void __launch_bounds__(1024) pt_reorder_kernel(PointWarpTask* __restrict__ tasks, int n, const int32_t* __restrict__ pt_order,
+                                                          const ResultRec* __restrict__ res) {
+  __shared__ PointWarpTask item[kReorderMax];
+  __shared__ float key[kReorderMax];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const PointWarpTask t = tasks[i];
+    item[i] = t;
+    int passes = 0;  // a warp runs until its slowest block is done
+    for (int k = 0; k < t.count; ++k) {
+      const ResultRec r = res[pt_order[t.first + k]];
+      passes = max(passes, r.n_value + r.n_slope);
+    }
+    // the machine steps of the blocks of a warp serialise where they diverge: more blocks, longer passes
+    key[i] = (float)passes * (1.0f + 0.05f * (float)t.count);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float k = key[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (key[j] > k || (key[j] == k && j < i)) ? 1 : 0;
+    tasks[rank] = item[i];
+  }
+}
+
 #ifndef RDIS_PT_MIN_CTAS
 #define RDIS_PT_MIN_CTAS 1
 #endif

@@ -114,6 +114,7 @@ struct rdisgpu_ctx {
   rdisgpu_batch* scratch_batch = nullptr;  // reused by the one-shot solve entry points
   int live_batches = 0;                    // rdisgpu_batch_create'd and not yet destroyed: rdisgpu_destroy refuses while > 0
   bool generic_only = false;  // rdisgpu_set_option("generic_only"): bypass the BA block kernels (tests)
+  bool adaptive_order = true; // rdisgpu_set_option("adaptive_order"): re-sort clusters / warp tasks by the previous visit's evaluation counts
   int pt_warps_per_sm = 0;    // resident warps of solve_ba_points_kernel per SM (occupancy query, once)
   int pt_tiles_cap = 0;       // rdisgpu_set_option("point_tiles_per_warp"): at most this many point blocks share a warp (0 = choose)
   int cam_cluster_opt = 0;    // rdisgpu_set_option("camera_cluster"): pin the cluster width of the camera-block kernel (0 = choose)
@@ -337,6 +338,10 @@ int rdisgpu_set_option(rdisgpu_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return RDISGPU_ERR_ARG;
   if (std::strcmp(name, "generic_only") == 0) {
     ctx->generic_only = (value != 0);
+    return RDISGPU_OK;
+  }
+  if (std::strcmp(name, "adaptive_order") == 0) {
+    ctx->adaptive_order = (value != 0);
     return RDISGPU_OK;
   }
   if (std::strcmp(name, "point_tiles_per_warp") == 0) {
@@ -1363,6 +1368,10 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
   if (b->n_pt_warps > 0) {
     solve_ba_points_kernel<<<b->n_pt_warps, 32, 0, s>>>(gv, bv, b->d_pt_order, b->d_pt_tasks, maxiters, ftol);
     ++launches;
+    if (ctx->adaptive_order && b->n_pt_warps > 1 && b->n_pt_warps <= kReorderMax) {  // longest warps first at the next visit
+      pt_reorder_kernel<<<1, 1024, 0, s>>>(b->d_pt_tasks, b->n_pt_warps, b->d_pt_order, b->res.p);
+      ++launches;
+    }
     CK(cudaGetLastError());
   }
   if (b->n_cam > 0) {
@@ -1425,6 +1434,11 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
     int Cc = b->cam_C;
     CK(cudaLaunchKernelEx(&cfg, solve_ba_cameras_kernel, gv, bv, cord, Cc, maxiters, ftol));
     ++launches;
+    if (ctx->adaptive_order && b->n_cam > 1 && b->n_cam <= kReorderMax) {  // longest clusters first at the next visit
+      cam_reorder_kernel<<<1, 1024, 0, s>>>(b->d_cam_order, b->n_cam, b->res.p);
+      ++launches;
+      CK(cudaGetLastError());
+    }
   }
   for (const auto& c : b->classes) {
     const int32_t* ord = b->d_order + c.off;
