@@ -902,3 +902,38 @@ def test_config2_whole_graph_as_one_problem(gpu, oracle_mod):
             h, k, sp["V"], sp["F"], rel, spread, int(a["n_feval"][0] + a["n_geval"][0])))
         assert rel <= max(1e-6, 10.0 * spread)
         assert (w["f_end"] <= w["f_init"]).all() and (a["f_end"] <= a["f_init"]).all()
+
+
+def test_launch_order_history_does_not_change_results(gpu):
+    """The block kernels re-sort their launch order after every solve (longest chains of the previous visit first,
+    rdisgpu_set_option "adaptive_order"); a problem is solved by its own cluster / tile whatever its position, so three
+    visits of the real ladybug wave with the history on and off agree to the bit, problem by problem."""
+    from rdis_b200 import Context, problems as P
+    spec = P.load_golden_ba()
+    x0 = spec["x0"]
+    pts, cams = P.ba_point_problems(spec), P.ba_camera_problems(spec)
+    out = {}
+    for adaptive in (0, 1):
+        ctx = Context.from_spec(spec)
+        ctx.set_option("adaptive_order", adaptive)
+        bp, bc = ctx.batch(pts), ctx.batch(cams)
+        visits = []
+        for visit in range(3):
+            ctx.set_x(x0)
+            bp.solve(x0[pts.vids].copy(), 25, 3e-8)
+            rp = bp.fetch()
+            bc.solve(None, 25, 3e-8)
+            rc = bc.fetch()
+            visits.append((rp, rc))
+        out[adaptive] = visits
+        ctx.close()
+    for visit in range(3):
+        for side in (0, 1):
+            a, b = out[0][visit][side], out[1][visit][side]
+            for key in ("x", "f_init", "f_end"):
+                assert np.array_equal(a[key].view(np.uint64), b[key].view(np.uint64)), (visit, side, key)
+            for key in ("iters", "status", "n_feval"):
+                assert np.array_equal(a[key], b[key]), (visit, side, key)
+    # and every visit reproduces the first one (same start state)
+    for side in (0, 1):
+        assert np.array_equal(out[1][0][side]["f_end"].view(np.uint64), out[1][2][side]["f_end"].view(np.uint64))
