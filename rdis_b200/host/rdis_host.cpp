@@ -483,11 +483,16 @@ Numeric CudaSubspaceOptimizer::optimizeBatch(std::vector<ComponentProblem>& prob
   if (n == 0) return 0;
   typedef std::chrono::steady_clock Clock;
   const Clock::time_point t0 = Clock::now();
-  for (const ComponentProblem& p : problems)
+  size_t listed = 0;
+  for (const ComponentProblem& p : problems) {
     if (p.xval.size() != p.vars.size()) throw std::invalid_argument("optimizeBatch: xval / vars size mismatch");
+    listed += p.vars.size() + p.factors.size();
+  }
+  // worth keeping resident: many problems, or few with long index lists (ladybug's 49 camera components list 31 843 factors)
+  const bool keep = !useLM && (n >= 64 || (n >= 2 && listed >= 4096));
   // A wave the tree search comes back to (same objects, same order) is recognised from its pointer runs: no id lists
   // are rebuilt, only the start values are packed.
-  OptimizableFunction::CachedBatch* wave = (!useLM && n >= 64) ? f.findWave(problems) : nullptr;
+  OptimizableFunction::CachedBatch* wave = keep ? f.findWave(problems) : nullptr;
   x0.clear();
   if (wave) {
     for (const ComponentProblem& p : problems) x0.insert(x0.end(), p.xval.begin(), p.xval.end());
@@ -505,7 +510,7 @@ Numeric CudaSubspaceOptimizer::optimizeBatch(std::vector<ComponentProblem>& prob
       var_off.push_back((int64_t)vids.size());
       fac_off.push_back((int64_t)fids.size());
     }
-    if (!useLM && n >= 64) {
+    if (keep) {
       // a wave: its index lists stay resident (a revisit of the same sibling set uploads start values only)
       wave = f.cachedBatch(var_off, vids, fac_off, fids);
       f.rememberWave(*wave, problems);
@@ -513,7 +518,9 @@ Numeric CudaSubspaceOptimizer::optimizeBatch(std::vector<ComponentProblem>& prob
   }
   const std::vector<int64_t>& voff = wave ? wave->var_off : var_off;
   // every other variable the factors read must be current on the device
+  const Clock::time_point tf0 = Clock::now();
   f.flushAssignments();
+  const Clock::time_point tf1 = Clock::now();
   xout.resize(x0.size());
   finit.resize((size_t)n);
   fend.resize((size_t)n);
@@ -529,6 +536,7 @@ Numeric CudaSubspaceOptimizer::optimizeBatch(std::vector<ComponentProblem>& prob
             "rdisgpu_solve_lm_csr");
   } else if (wave) {
     f.check(rdisgpu_batch_solve_cgd(wave->batch, x0.data(), (int)maxiters, ftol), "rdisgpu_batch_solve_cgd");
+    tm.fetch_ms -= std::chrono::duration<double, std::milli>(Clock::now() - t1).count();  // fetch_ms = device_ms - time to enqueue
     f.check(rdisgpu_batch_fetch_csr(wave->batch, xout.data(), finit.data(), fend.data(), iters.data(), status.data(), nfe.data(),
                                     nge.data()),
             "rdisgpu_batch_fetch_csr");
@@ -571,8 +579,10 @@ Numeric CudaSubspaceOptimizer::optimizeBatch(std::vector<ComponentProblem>& prob
   for (int32_t vid : f.dirtyVids) f.dirtyFlag[(size_t)vid] = 0;
   f.dirtyVids.clear();
   const Clock::time_point t3 = Clock::now();
-  tm.pack_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+  tm.pack_ms += std::chrono::duration<double, std::milli>(t1 - t0).count() - std::chrono::duration<double, std::milli>(tf1 - tf0).count();
+  tm.flush_ms += std::chrono::duration<double, std::milli>(tf1 - tf0).count();
   tm.device_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();
+  if (wave) tm.fetch_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();
   tm.writeback_ms += std::chrono::duration<double, std::milli>(t3 - t2).count();
   ++tm.calls;
   return total;

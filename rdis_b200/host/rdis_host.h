@@ -351,7 +351,7 @@ class CudaSubspaceOptimizer : public SubspaceOptimizer {
   Numeric optimizeBatch(std::vector<ComponentProblem>& problems, const bool printdbg);
   // wall-clock milliseconds spent in optimizeBatch since the last resetTiming(): recognising / packing the wave, the
   // device calls (upload + solve + download, synchronous), the write-back into the host objects
-  struct Timing { double pack_ms = 0, device_ms = 0, writeback_ms = 0; long calls = 0; };
+  struct Timing { double pack_ms = 0, flush_ms = 0, device_ms = 0, fetch_ms = 0, writeback_ms = 0; long calls = 0; };
   const Timing& timing() const { return tm; }
   void resetTiming() { tm = Timing(); }
 

@@ -203,10 +203,10 @@ int main(int argc, char** argv) {
         for (const ComponentProblem& p : waves[side]) { nv += p.vars.size(); nf += p.factors.size(); }
       std::printf("{\"solves_per_step\": %zu, \"steps\": %d, \"warmup\": %d, \"ms_per_step\": %.6f, \"solves_per_s\": %.3f, "
                   "\"objective_after_step\": %.17g, \"objective_first_step\": %.17g, \"point_wave_sum\": %.17g, \"dispatch_ms\": %.3f, \"vars_in_problems\": %zu, "
-                  "\"factors_in_problems\": %zu, \"V\": %lld, \"plugin_ms_per_step\": {\"recognise_and_pack\": %.4f, \"device_calls\": %.4f, "
-                  "\"write_back\": %.4f}}\n",
+                  "\"factors_in_problems\": %zu, \"V\": %lld, \"plugin_ms_per_step\": {\"recognise_and_pack\": %.4f, \"upload_assigned\": %.4f, \"device_calls\": %.4f, "
+                  "\"of_which_fetch_wait\": %.4f, \"write_back\": %.4f}}\n",
                   nsolves, steps, warmup, total_ms / steps, nsolves * steps / (total_ms * 1e-3), objective, objective_first, pts_sum, dispatch_ms, nv, nf,
-                  fn.getNumVars(), tm.pack_ms / steps, tm.device_ms / steps, tm.writeback_ms / steps);
+                  fn.getNumVars(), tm.pack_ms / steps, tm.flush_ms / steps, tm.device_ms / steps, tm.fetch_ms / steps, tm.writeback_ms / steps);
       return 0;
     }
     if (std::string(argv[1]) == "sinusoid_flat") {

@@ -21,3 +21,5 @@ if __name__ == "__main__":
             p = subprocess.run([os.path.join(ROOT, "tests", "native", "host_driver"), "benchwaves", bal, steps, "3"],
                                capture_output=True, text=True)
             print(p.stdout.strip().splitlines()[-1] if p.returncode == 0 else p.stderr[-400:])
+            if p.stderr.strip():
+                print("\n".join(p.stderr.strip().splitlines()[-12:]))
