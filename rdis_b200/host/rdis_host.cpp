@@ -488,8 +488,9 @@ Numeric CudaSubspaceOptimizer::optimizeBatch(std::vector<ComponentProblem>& prob
     if (p.xval.size() != p.vars.size()) throw std::invalid_argument("optimizeBatch: xval / vars size mismatch");
     listed += p.vars.size() + p.factors.size();
   }
-  // worth keeping resident: many problems, or few with long index lists (ladybug's 49 camera components list 31 843 factors)
-  const bool keep = !useLM && (n >= 64 || (n >= 2 && listed >= 4096));
+  // worth keeping resident: many problems, or few (one) with long index lists (ladybug: 49 camera components list 31 843
+  // factors; the 4755-variable top-level block 11 950)
+  const bool keep = !useLM && (n >= 64 || listed >= 4096);
   // A wave the tree search comes back to (same objects, same order) is recognised from its pointer runs: no id lists
   // are rebuilt, only the start values are packed.
   OptimizableFunction::CachedBatch* wave = keep ? f.findWave(problems) : nullptr;
