@@ -104,8 +104,9 @@ struct BlockCache {
   }
 };
 
-__device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const BatchView& B, int lg, int pidx, int maxiters,
-                                                    double ftol) {
+// Returns the number of evaluation passes the WARP ran (the slowest block of the warp decides).
+__device__ __forceinline__ int solve_ba_point_tile(const GraphView& Gv, const BatchView& B, int lg, int pidx, int maxiters,
+                                                   double ftol) {
   const TileRt grp(lg);
   const int r = grp.r;
   const int G = grp.G;
@@ -178,9 +179,11 @@ __device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const B
 #else
 #define PTPROF(i) do { } while (0)
 #endif
+  int passes = 0;
   while (true) {
     const bool fin = mc.done();
     if (__all_sync(kFull, fin)) break;
+    ++passes;
 #ifdef RDIS_PT_PROFILE
     ++pnev;
 #endif
@@ -293,7 +296,7 @@ __device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const B
     printf("ptprof G %d passes %d | eval %lld fold %lld machine %lld cycles per pass\n", G, pnev, pprof[0] / pnev, pprof[1] / pnev, pprof[2] / pnev);
 #endif
 
-  if (!run) return;
+  if (!run) return passes;
   // ---- commit (CGD.cpp:61-89): quickAssignVals(gdmin.p); if worse than the start, the start is re-assigned and
   //      re-evaluated (through the cache).  The safety exits (non-finite abscissa, bracket cap) keep p and fret of the
   //      last completed line search like the reference's own exceptions do. ----
@@ -325,6 +328,7 @@ __device__ __forceinline__ void solve_ba_point_tile(const GraphView& Gv, const B
     res.n_slope = mc.n_slope;
     B.res[pidx] = res;
   }
+  return passes;
 }
 
 // One warp per CTA.  warp_task[w] = {log2 G, first slot in `order`, number of problems of that
@@ -334,6 +338,7 @@ struct PointWarpTask {
   int32_t lg;
   int32_t first;
   int32_t count;
+  float key;  // written by the solve: predicted duration of this warp at the next visit (pt_reorder_kernel sorts by it)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -342,8 +347,9 @@ struct PointWarpTask {
 // 8 CTAs place 6 per GPC, so the last one starts when the first one ends; the point kernel has 1.2x more warps than are
 // resident.  What is dispatched last must therefore be SHORT.  A sibling set is re-posed many times by the tree search
 // (alternating minimisation, src/RDISOptimizer.cpp:1148-1181) with start values that move little, so the evaluation
-// counts of the previous solve (ResultRec) predict the next one: after every solve the clusters / warp tasks are
-// re-sorted, longest first (rank sort in one CTA, stream-ordered, no host involvement).  Results do not depend on the
+// counts of the previous solve (ResultRec; a point warp records its own pass count in its task) predict the next one:
+// after every solve the clusters / warp tasks are re-sorted, longest first (rank sort in one CTA, stream-ordered, no
+// host involvement).  Results do not depend on the
 // order (every problem is solved by its own cluster / tile).  Measured on ladybug's 49 cameras: 3.14 ms in camera-id
 // order, 2.77 ms longest-first.
 // ------------------------------------------------------------------------------------------
@@ -367,38 +373,38 @@ __global__ void __launch_bounds__(1024) cam_reorder_kernel(int32_t* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(1024) pt_reorder_kernel(PointWarpTask* __restrict__ tasks, int n, const int32_t* __restrict__ pt_order,
-                                                          const ResultRec* __restrict__ res) {
-  __shared__ PointWarpTask item[kReorderMax];
-  __shared__ float key[kReorderMax];
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const PointWarpTask t = tasks[i];
-    item[i] = t;
-    int passes = 0;  // a warp runs until its slowest block is done
-    for (int k = 0; k < t.count; ++k) {
-      const ResultRec r = res[pt_order[t.first + k]];
-      passes = max(passes, r.n_value + r.n_slope);
-    }
-    // the machine steps of the blocks of a warp serialise where they diverge: more blocks, longer passes
-    key[i] = (float)passes * (1.0f + 0.05f * (float)t.count);
-  }
+// Rank sort over several CTAs: a CTA ranks kReorderItems tasks against all n keys (four threads per task, each a quarter
+// of the keys, interleaved so that a warp's four shared-memory addresses are neighbours) and writes them to their places
+// in the OTHER list (the host swaps the two lists after the launch).
+constexpr int kReorderItems = 64;
+__global__ void __launch_bounds__(4 * kReorderItems) pt_reorder_kernel(const PointWarpTask* __restrict__ src, PointWarpTask* __restrict__ dst,
+                                                                       int n) {
+  __shared__ float key[kReorderMax + 4];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) key[i] = src[i].key;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float k = key[i];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) rank += (key[j] > k || (key[j] == k && j < i)) ? 1 : 0;
-    tasks[rank] = item[i];
+  const int i = blockIdx.x * kReorderItems + ((int)threadIdx.x >> 2), q = (int)threadIdx.x & 3;
+  const float k = (i < n) ? key[i] : 0.0f;
+  int rank = 0;
+#pragma unroll 4
+  for (int j = q; j < n; j += 4) {
+    const float kj = key[j];
+    rank += (kj > k || (kj == k && j < i)) ? 1 : 0;
   }
+  rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+  if (q == 0 && i < n) dst[rank] = src[i];
 }
 
 #ifndef RDIS_PT_MIN_CTAS
 #define RDIS_PT_MIN_CTAS 1
 #endif
 __global__ void __launch_bounds__(32, RDIS_PT_MIN_CTAS) solve_ba_points_kernel(GraphView Gv, BatchView B, const int32_t* order,
-                                                             const PointWarpTask* tasks, int maxiters, double ftol) {
+                                                             PointWarpTask* tasks, int maxiters, double ftol) {
   const PointWarpTask t = tasks[blockIdx.x];
   const int slot = (int)threadIdx.x >> t.lg;
-  solve_ba_point_tile(Gv, B, t.lg, (slot < t.count) ? order[t.first + slot] : -1, maxiters, ftol);
+  const int passes = solve_ba_point_tile(Gv, B, t.lg, (slot < t.count) ? order[t.first + slot] : -1, maxiters, ftol);
+  // the machine steps of the blocks of a warp serialise where they diverge: more blocks, longer passes
+  if (threadIdx.x == 0) tasks[blockIdx.x].key = (float)passes * (1.0f + 0.05f * (float)t.count);
 }
 
 // ------------------------------------------------------------------------------------------

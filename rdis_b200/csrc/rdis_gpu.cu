@@ -177,7 +177,7 @@ struct rdisgpu_batch {
   PinnedBuf<char> h_blob;
   ProblemDesc* d_probs = nullptr;
   int32_t *d_vids = nullptr, *d_fids = nullptr, *d_order = nullptr, *d_pt_order = nullptr, *d_cam_order = nullptr;
-  PointWarpTask* d_pt_tasks = nullptr;
+  PointWarpTask *d_pt_tasks = nullptr, *d_pt_tasks_alt = nullptr;  // current launch order / where the next one is written
   DevBuf<double> x0, xout;
   DevBuf<ResultRec> res;
   // size classes of the generic kernels
@@ -988,7 +988,8 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
   const size_t o_pt = align16(o_order + 4 * (size_t)nprobs);
   const size_t o_cam = align16(o_pt + 4 * (size_t)nprobs);
   const size_t o_tasks = align16(o_cam + 4 * (size_t)nprobs);
-  const size_t total = align16(o_tasks + sizeof(PointWarpTask) * npt_tasks_max);
+  const size_t o_tasks2 = align16(o_tasks + sizeof(PointWarpTask) * npt_tasks_max);  // the re-sorted list of the next visit
+  const size_t total = align16(o_tasks2 + sizeof(PointWarpTask) * npt_tasks_max);
   CK(b->h_blob.ensure(total));
   CK(b->blob.ensure(total));
   char* hb = b->h_blob.p;
@@ -1155,7 +1156,7 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
       const int32_t cnt = (int32_t)pt_lists[lg].size();
       if (cnt) std::memcpy(h_pt + npt, pt_lists[lg].data(), 4 * (size_t)cnt);
       npt += cnt;
-      for (int32_t o = 0; o < cnt; o += per_warp) h_tasks[b->n_pt_warps++] = PointWarpTask{lg, base + o, std::min(per_warp, cnt - o)};
+      for (int32_t o = 0; o < cnt; o += per_warp) h_tasks[b->n_pt_warps++] = PointWarpTask{lg, base + o, std::min(per_warp, cnt - o), 0.0f};
     }
   }
   // NonlinearProductFactor components that fit one CTA's shared memory: the resident kernel (nlpf_resident.cuh)
@@ -1284,6 +1285,7 @@ static int batch_build(rdisgpu_batch* b, const ProblemsView& pv) {
   b->d_pt_order = reinterpret_cast<int32_t*>(db + o_pt);
   b->d_cam_order = reinterpret_cast<int32_t*>(db + o_cam);
   b->d_pt_tasks = reinterpret_cast<PointWarpTask*>(db + o_tasks);
+  b->d_pt_tasks_alt = reinterpret_cast<PointWarpTask*>(db + o_tasks2);
   CK(b->x0.ensure((size_t)tv));
   CK(b->xout.ensure((size_t)tv));
   CK(b->res.ensure((size_t)nprobs));
@@ -1369,7 +1371,9 @@ int rdisgpu_batch_solve_cgd(rdisgpu_batch* b, const double* x0_host, int maxiter
     solve_ba_points_kernel<<<b->n_pt_warps, 32, 0, s>>>(gv, bv, b->d_pt_order, b->d_pt_tasks, maxiters, ftol);
     ++launches;
     if (ctx->adaptive_order && b->n_pt_warps > 1 && b->n_pt_warps <= kReorderMax) {  // longest warps first at the next visit
-      pt_reorder_kernel<<<1, 1024, 0, s>>>(b->d_pt_tasks, b->n_pt_warps, b->d_pt_order, b->res.p);
+      pt_reorder_kernel<<<(b->n_pt_warps + kReorderItems - 1) / kReorderItems, 4 * kReorderItems, 0, s>>>(b->d_pt_tasks, b->d_pt_tasks_alt,
+                                                                                                       b->n_pt_warps);
+      std::swap(b->d_pt_tasks, b->d_pt_tasks_alt);
       ++launches;
     }
     CK(cudaGetLastError());
