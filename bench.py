@@ -312,6 +312,29 @@ def run_ours(args):
         dist.all_reduce(t)
     objective, pts_sum = float(t[0].item()), float(t[1].item())
 
+    # ---- the same step without the launch-order history (what the FIRST visit of a sibling set costs) ----
+    first_visit = None
+    if world == 1:
+        ctx.set_option("adaptive_order", 0)
+        b1p, b1c = ctx.batch(my_pts), ctx.batch(my_cams)
+        ts = []
+        for _ in range(6):
+            flush.zero_()
+            flush.sum()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            ctx.set_x_device(x0_dev.data_ptr(), V)
+            b1p.solve(None, MAXITERS, FTOL)
+            b1c.solve(None, MAXITERS, FTOL)
+            e.record(stream)
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(e))
+        first_visit = {"ms_per_step": float(np.mean(ts[1:])), "what": "launch order as built (size classes, problem order): no evaluation "
+                       "counts of a previous visit to sort by (rdisgpu_set_option adaptive_order = 0); results identical"}
+        b1p.close()
+        b1c.close()
+        ctx.set_option("adaptive_order", 1)
+
     # ---- e2e ----
     e2e = e2e_leg(args, spec, pts, cams, own_p, own_c, ctx, rank, world, local_rank, host_group, dist, torch, dev)
 
@@ -336,6 +359,10 @@ def run_ours(args):
             "per_rank_ms": None if per_rank is None else {"columns": ["total over the timed steps", "points wave", "exchange", "cameras wave"], "rows": per_rank},
             "limiting": "the longest line-search chain of one camera component (cameras wave) — per-rank work shrinks with N, the chain does not",
             "wall_s_timed_region": t_wall,
+            "first_visit": first_visit,
+            "launch_order": "block-kernel launch order re-sorted on the device after every solve by the evaluation counts just observed "
+                            "(longest chains first): the timed steps are revisits of the same sibling set, as in the tree search's "
+                            "alternating minimisation (src/RDISOptimizer.cpp:1148-1181); first_visit = without that history",
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "e2e": e2e,

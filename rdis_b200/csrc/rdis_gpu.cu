@@ -259,6 +259,19 @@ bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// page-locked (cudaHostAlloc / cudaHostRegister) host memory: a cudaMemcpyAsync from it is truly asynchronous, the caller
+// may not touch the buffer until the stream has passed the copy.  From pageable memory the driver stages the source
+// before the call returns.
+bool is_pinned_host_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 // counting-sort incidence: for each key in [0,K) the list of items with that key, ascending item id
 void build_incidence(int64_t K, const std::vector<int32_t>& key_of_item, std::vector<int32_t>& row,
                      std::vector<int32_t>& items) {
@@ -639,7 +652,9 @@ int rdisgpu_set_x(rdisgpu_ctx* ctx, int64_t n, const int32_t* vid, const double*
     scatter_x_kernel<<<blocks, threads, 0, s>>>(ctx->gv, n, vid ? ctx->s_i32a.p : nullptr, ctx->s_f64a.p);
   ++ctx->launches;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(s));  // x / vid are caller-owned pageable memory
+  // caller-owned buffers: pageable sources have been staged by the driver when cudaMemcpyAsync returns; page-locked ones
+  // are read by the DMA engine later, so the call waits for them
+  if (is_pinned_host_ptr(x) || is_pinned_host_ptr(vid)) CK(cudaStreamSynchronize(s));
   return RDISGPU_OK;
 }
 
