@@ -199,6 +199,8 @@ def ba_synthetic(ncams=49, npts=7776, nobs=31843, seed=20260417, noise_px=0.5, p
     of the generating state so that solves have real work to do."""
     rng = np.random.default_rng(seed)
     max_deg = min(29, ncams)
+    if ncams < 2 or not (2 * npts <= nobs <= max_deg * npts):
+        raise ValueError("ba_synthetic: nobs must lie in [2 * npts, min(29, ncams) * npts] (every point is seen by 2..%d cameras)" % max_deg)
     deg = 2 + np.minimum(rng.geometric(0.42, size=npts) - 1, max_deg - 2)
     # hit nobs exactly
     diff = int(nobs - deg.sum())
