@@ -226,3 +226,32 @@ dist.destroy_process_group()
                          capture_output=True, text=True, timeout=280)
     assert out.returncode == 0, out.stderr[-3000:] + out.stdout[-1000:]
     assert "STRONG_SHARD_OK" in out.stdout
+
+
+def test_synthetic_ba_generator_rejects_impossible_sizes():
+    """Every point of the synthetic bundle-adjustment graph is seen by 2..min(29, ncams) DISTINCT cameras: an observation
+    count outside [2 npts, min(29, ncams) npts] has no such graph (the generator used to loop forever on it)."""
+    from rdis_b200 import problems as P
+    with pytest.raises(ValueError):
+        P.ba_synthetic(ncams=6, npts=700, nobs=5000, seed=9)
+    with pytest.raises(ValueError):
+        P.ba_synthetic(ncams=6, npts=700, nobs=1000, seed=9)
+    spec = P.ba_synthetic(ncams=6, npts=700, nobs=4200, seed=9)  # the densest graph there is: every point in every camera
+    assert spec["F"] == 4200 and int(np.bincount(spec["pt"]).min()) == 6
+
+
+def test_bench_reads_the_committed_ncu_numbers():
+    """bench.py's roofline.traffic / fp64-pipe figures come from profiles/r02_traffic.json (tools/make_traffic.py over the
+    committed ncu summaries): the kernels bench.py asks for must be there under the names it uses."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for kernel in ("solve_ba_cameras_kernel", "solve_ba_points_kernel", "nlpf_tile_sweep_kernel<false>", "solve_nlpf_resident_kernel"):
+        dram = bench.measured_traffic(kernel)
+        assert dram is not None and dram > 0, kernel
+        assert bench.measured_traffic(kernel, "fp64_pipe_active_pct") is not None, kernel
+    # the streaming sweep moves about its algorithmic bytes, the latency-bound solve kernels almost nothing
+    assert 0.8 * 268.4e6 < bench.measured_traffic("nlpf_tile_sweep_kernel<false>") < 1.2 * 268.4e6
+    assert bench.measured_traffic("solve_ba_cameras_kernel") < 16e6
