@@ -1,3 +1,6 @@
+#!/bin/bash
+# End-of-round evidence (run under gpurun, ONE GPU): launch list of the bench step, ncu --set full of the solve kernels and of
+# the gradient-sweep kernels (summarised on the box), then both bench arms.  Copy gpurun_out/r02_* and bench_*.json to profiles/.
 NCU="ncu --set full --clock-control none --import-source on"
 summarise() {
   ncu -i gpurun_out/$1.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_raw.py > gpurun_out/r02_ncu_$1_raw.txt 2>&1
